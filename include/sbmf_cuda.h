@@ -1,0 +1,186 @@
+/*
+ * sbmf_cuda.h -- C ABI of the B200-native SBMF Gibbs sweep (libsbmf_cuda.so).
+ *
+ * The reference (rishabhmisra/Scalable-Bayesian-Matrix-Factorization) has no plugin / FFI boundary for
+ * this path: gibbs_sbpmf2.cpp ("[T]") is one monolithic main().  This header therefore DEFINES the
+ * boundary, one entry point per phase of [T]; each comment cites the reference lines it replaces.
+ * INTEGRATION.md shows the host-side binding (C++ main, ctypes) a maintainer would add.
+ *
+ * Conventions: every function returns SBMF_OK (0) or a negative sbmf_status; nothing throws across the
+ * ABI; sbmf_cuda_last_error() returns a human-readable message for the last failure on that handle
+ * (or the last create failure when handle == NULL).  Host buffers are caller-owned and only touched
+ * during the call.  Device memory is owned by the handle.  One handle = one model replica on one GPU
+ * (one rank of a multi-GPU job); calls on a handle come from one host thread.  There is NO CPU
+ * fallback: if no sm_100 device is usable, sbmf_cuda_create fails.
+ */
+#ifndef SBMF_CUDA_H_
+#define SBMF_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBMF_CUDA_ABI_VERSION 1
+#define SBMF_MAX_K 256
+
+typedef struct sbmf_handle sbmf_handle;
+
+typedef enum sbmf_status {
+    SBMF_OK = 0,
+    SBMF_ERR_INVALID = -1,      /* bad argument (null pointer, id out of range, K > SBMF_MAX_K, ...) */
+    SBMF_ERR_CUDA = -2,         /* a CUDA runtime call or kernel failed */
+    SBMF_ERR_NOMEM = -3,        /* device or host allocation failed */
+    SBMF_ERR_STATE = -4,        /* call order violated (e.g. sweep before set_train / init_factors) */
+    SBMF_ERR_NCCL = -5,         /* NCCL could not be loaded or a collective failed */
+    SBMF_ERR_UNSUPPORTED = -6   /* valid request this build does not implement */
+} sbmf_status;
+
+/* How a draw x ~ N(mu*, 1/lambda*) is realised.  [T] passes the posterior VARIANCE 1/lambda* to
+   ran_gaussian(mean, stdev) ([T]:393,406,439,465,487,509,530,551,578,599; random.h:166-172), so the
+   reference-compatible mode draws x = mu* + (1/lambda*) z.  SURVEY.md 0.3. */
+typedef enum sbmf_sample_mode {
+    SBMF_SAMPLE_REF_VAR_AS_STDEV = 0,   /* x = mu* + (1/lambda*) z      -- what [T] does */
+    SBMF_SAMPLE_SQRT = 1,               /* x = mu* + sqrt(1/lambda*) z  -- the textbook conditional */
+    SBMF_SAMPLE_ZERO_NOISE = 2          /* x = mu*; Gamma(a,b) -> a/b   -- conditional-mean updates (parity mode) */
+} sbmf_sample_mode;
+
+typedef enum sbmf_hyper_mode {
+    SBMF_HYPER_REF_T = 0                /* hyper-parameter updates exactly as [T]:366-511 */
+} sbmf_hyper_mode;
+
+/* Prior constants of [T]:284-313, indexed like the reference's names: alpha_0 (sigma_b_0), alpha_1
+   (sigma_v), alpha_2 (sigma_u), alpha_3 (unused), alpha_4 (sigma_b_i), alpha_5 (sigma_b_j); same for
+   beta_*, mu_*, sigma_*; *_dash = alpha_0_dash / beta_0_dash of the noise precision.  All 1/1/0/1 in [T]. */
+typedef struct sbmf_priors {
+    double alpha[6], beta[6], mu[6], sigma[6];
+    double alpha_dash, beta_dash;
+} sbmf_priors;
+
+typedef struct sbmf_config {
+    uint32_t struct_size;        /* = sizeof(sbmf_config); set by sbmf_cuda_config_default */
+    uint32_t K;                  /* latent dimension; [T]:224 `uint D = 20` */
+    int32_t device;              /* CUDA device ordinal */
+    int32_t sample_mode;         /* sbmf_sample_mode */
+    int32_t hyper_mode;          /* sbmf_hyper_mode */
+    uint32_t rebuild_every;      /* rebuild the residual from scratch every n-th sweep; 1 = every sweep = [T]:342-359 */
+    uint32_t burn_in;            /* sweeps before test predictions are accumulated; 0 = [T]:323 */
+    uint32_t reserved0;
+    uint64_t seed;               /* Philox key.  ([T] never seeds rand(); libFM parses -seed and ignores it) */
+    double init_stdev;           /* 0.1 = [T]:242, 248 */
+    double clamp_lo, clamp_hi;   /* 0.5 / 5.0 = [T]:627-628 */
+    sbmf_priors priors;
+    /* multi-GPU: one handle per rank, users (CSR) and items (CSC) sharded by nnz-balanced contiguous ranges */
+    int32_t rank, world_size;    /* 0 / 1 for a single GPU */
+    uint8_t nccl_id[128];        /* ncclUniqueId from sbmf_cuda_nccl_unique_id on rank 0, broadcast by the host */
+} sbmf_config;
+
+/* Filled by sbmf_cuda_get_state; NULL members are skipped.  Layouts are the reference's own:
+   U row-major per user ([T]:229-232), V dimension-major ([T]:234-237), E in rating (file) order. */
+typedef struct sbmf_state {
+    float* U;                    /* [num_users][K] */
+    float* V;                    /* [K][num_items] */
+    float *b_i, *b_j;            /* [num_users], [num_items] */
+    float *mu_b_i, *sigma_b_i;   /* [num_users] */
+    float *mu_b_j, *sigma_b_j;   /* [num_items] */
+    double *sigma_u, *mu_u, *sigma_v, *mu_v;   /* [K] */
+    float* E;                    /* [n_train], rating order; as left by the last sweep */
+    double b_0, alpha, mu_b_0, sigma_b_0;      /* out */
+    double sum_e, sum_e2;        /* out: the statistics of [T]:357-358 taken at the start of the last sweep */
+    uint32_t sweeps_done;        /* out */
+    uint32_t reserved0;
+} sbmf_state;
+
+typedef struct sbmf_timing {
+    /* CUDA-event milliseconds accumulated since the last sbmf_cuda_reset_timing, per phase of [T]'s sweep */
+    double ms_rebuild;           /* [T]:342-359 */
+    double ms_hypers;            /* [T]:366-511 */
+    double ms_user_phase;        /* [T]:514-558 */
+    double ms_exchange;          /* residual CSR->CSC permutation (+ multi-GPU exchange) */
+    double ms_item_phase;        /* [T]:563-606 */
+    double ms_eval;              /* [T]:610-636 */
+    double ms_total;
+    uint64_t sweeps;
+    uint64_t kernel_launches;    /* kernels of this library launched by those sweeps */
+    uint64_t nnz_light_user, nnz_heavy_user, nnz_light_item, nnz_heavy_item;   /* rating split by kernel path */
+} sbmf_timing;
+
+/* ---- life cycle ------------------------------------------------------------------------------------ */
+int sbmf_cuda_abi_version(void);
+/* Defaults = the constants hard-coded in [T]: K=20 ([T]:224), priors 1/1/0/1 ([T]:284-313), clamp [0.5,5]
+   ([T]:627-628), init_stdev 0.1, burn_in 0, sample_mode REF_VAR_AS_STDEV, rebuild_every 1, seed 1. */
+int sbmf_cuda_config_default(sbmf_config* cfg);
+int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out);
+int sbmf_cuda_destroy(sbmf_handle* h);
+const char* sbmf_cuda_last_error(const sbmf_handle* h);
+/* rank 0 of a multi-GPU job calls this and ships the 128 bytes to the other ranks (torch.distributed, MPI, ...) */
+int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
+
+/* ---- rating storage: replaces the jagged R / R_t build of [T]:32-221 --------------------------------- */
+/* COO in FILE ORDER (rating index n = position), 0-based ids, num_users = 1 + max user id over train U test
+   ([T]:151-153).  Builds on device: CSR by user + CSC by item, both STABLE w.r.t. file order ([T]:209-214),
+   the CSC-slot -> CSR-slot permutation that replaces [T]'s `.id` back-pointers, the residual arrays and the
+   row work lists.  Host pointers may be pageable or pinned. */
+int sbmf_cuda_set_train(sbmf_handle* h, uint64_t n, const uint32_t* user, const uint32_t* item, const float* rating,
+                        uint32_t num_users, uint32_t num_items);
+/* test pairs of [T]:98-149; resets the running prediction sums ([T]:145). */
+int sbmf_cuda_set_test(sbmf_handle* h, uint64_t nt, const uint32_t* user, const uint32_t* item, const float* rating);
+/* Integer layout for the bit-exact tests; any pointer may be NULL.  row_ptr[num_users+1], col[n] (item per
+   CSR slot), csr_id[n] (rating index per CSR slot), col_ptr[num_items+1], row[n] (user per CSC slot),
+   csc_id[n] (rating index per CSC slot), perm[n] (CSR slot of each CSC slot). */
+int sbmf_cuda_get_layout(sbmf_handle* h, int64_t* row_ptr, uint32_t* col, uint64_t* csr_id,
+                         int64_t* col_ptr, uint32_t* row, uint64_t* csc_id, uint64_t* perm);
+
+/* ---- model state ----------------------------------------------------------------------------------- */
+/* U0 [num_users][K] row-major, V0 [K][num_items]; NULL => 0.1*N(0,1) from the Philox INIT streams
+   ([T]:239-250).  Zeroes biases/hypers ([T]:268-281, 315-318), the sweep counter and the prediction sums. */
+int sbmf_cuda_init_factors(sbmf_handle* h, const float* U0, const float* V0);
+int sbmf_cuda_get_state(sbmf_handle* h, sbmf_state* out);
+
+/* ---- the hot path: n bodies of the loop [T]:335-637 ------------------------------------------------ */
+/* Each sweep: residual rebuild + statistics ([T]:342-359), alpha / global-mean chain ([T]:366-410),
+   per-dimension and bias hyper-parameters ([T]:415-511), user phase ([T]:514-558), item phase ([T]:563-606),
+   test prediction + running-mean RMSE ([T]:610-636).  Asynchronous w.r.t. the host until a getter is called. */
+int sbmf_cuda_sweep(sbmf_handle* h, uint32_t n_sweeps);
+/* RMSE of the running posterior-mean prediction (the "rmse is" value of [T]:635) and of the last sweep's own
+   prediction; synchronises and copies 2 doubles back. */
+int sbmf_cuda_eval(sbmf_handle* h, double* rmse_running_mean, double* rmse_last_sweep);
+/* RMSE trajectory: entries [first, first+count) of the per-sweep history since init_factors. */
+int sbmf_cuda_get_rmse_history(sbmf_handle* h, uint32_t first, uint32_t count, double* rmse_running_mean,
+                               double* rmse_sweep);
+/* Posterior-mean (clamped) prediction per test pair = sum/(sweeps - burn_in), libFM's -out content. */
+int sbmf_cuda_get_pred(sbmf_handle* h, float* pred);
+
+/* ---- instrumentation -------------------------------------------------------------------------------- */
+int sbmf_cuda_get_timing(sbmf_handle* h, sbmf_timing* out);
+int sbmf_cuda_reset_timing(sbmf_handle* h);
+int sbmf_cuda_synchronize(sbmf_handle* h);
+/* Per-phase timing makes every sweep wait for its own CUDA events (one host/device round trip per sweep).
+   enabled = 0 turns that off: sbmf_cuda_sweep(h, n) then only enqueues work.  Default: enabled. */
+int sbmf_cuda_set_timing_enabled(sbmf_handle* h, int enabled);
+
+/* ---- synthetic workloads (bench / tests): MovieLens/Netflix-shaped Zipf rating matrices, generated on
+   the device.  Distinct (user,item) pairs with Zipf(s_user) x Zipf(s_item) marginals over
+   randomly permuted ids, ratings from a planted rank-16 model rounded to 0.5 steps in [0.5,5], sorted by
+   (user,item) like every shipped fixture, split train/test by Bernoulli(test_frac).  Two-call protocol:
+   call with NULL arrays to learn n_train/n_test, then with buffers of that size. */
+typedef struct sbmf_synth_spec {
+    uint32_t num_users, num_items;
+    uint64_t n_ratings;          /* train + test */
+    double s_user, s_item;       /* Zipf exponents (0.8 / 1.0 in SURVEY.md 8d) */
+    double test_frac;            /* 0.1 */
+    uint64_t seed;
+    int32_t device;
+    int32_t reserved0;
+} sbmf_synth_spec;
+int sbmf_cuda_synth_generate(const sbmf_synth_spec* spec, uint64_t* n_train, uint64_t* n_test,
+                             uint32_t* train_user, uint32_t* train_item, float* train_rating,
+                             uint32_t* test_user, uint32_t* test_item, float* test_rating);
+const char* sbmf_cuda_synth_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBMF_CUDA_H_ */

@@ -1,0 +1,508 @@
+// api.cu -- the extern "C" sbmf_cuda_* boundary (include/sbmf_cuda.h) over the device model.
+// Nothing here computes on the CPU: every phase of the sweep is a kernel in kernels.cu, and there is no
+// fallback -- sbmf_cuda_create fails if no CUDA device of compute capability 10.x is usable.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "model.h"
+
+using namespace sbmf;
+
+static thread_local std::string g_create_err;
+
+#define API_CK(call)                                                                               \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            m.err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return (e_ == cudaErrorMemoryAllocation) ? SBMF_ERR_NOMEM : SBMF_ERR_CUDA;             \
+        }                                                                                          \
+    } while (0)
+
+static cudaError_t copy_out_widen(uint64_t* dst, const uint32_t* d_src, size_t n, std::vector<uint32_t>& tmp)
+{
+    tmp.resize(n ? n : 1);
+    cudaError_t e = cudaMemcpy(tmp.data(), d_src, n * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    for (size_t i = 0; i < n; ++i) dst[i] = tmp[i];
+    return cudaSuccess;
+}
+
+extern "C" {
+
+int sbmf_cuda_abi_version(void) { return SBMF_CUDA_ABI_VERSION; }
+
+int sbmf_cuda_config_default(sbmf_config* cfg)
+{
+    if (!cfg) return SBMF_ERR_INVALID;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (uint32_t)sizeof(sbmf_config);
+    cfg->K = 20;                                   // [T]:224
+    cfg->device = 0;
+    cfg->sample_mode = SBMF_SAMPLE_REF_VAR_AS_STDEV;
+    cfg->hyper_mode = SBMF_HYPER_REF_T;
+    cfg->rebuild_every = 1;                        // [T]:342-359 rebuilds E every sweep
+    cfg->burn_in = 0;                              // [T]:323
+    cfg->seed = 1;
+    cfg->init_stdev = 0.1;                         // [T]:242, 248
+    cfg->clamp_lo = 0.5;                           // [T]:627-628
+    cfg->clamp_hi = 5.0;
+    for (int i = 0; i < 6; ++i) {                  // [T]:284-313
+        cfg->priors.alpha[i] = 1.0;
+        cfg->priors.beta[i] = 1.0;
+        cfg->priors.mu[i] = 0.0;
+        cfg->priors.sigma[i] = 1.0;
+    }
+    cfg->priors.alpha_dash = 1.0;
+    cfg->priors.beta_dash = 1.0;
+    cfg->rank = 0;
+    cfg->world_size = 1;
+    return SBMF_OK;
+}
+
+int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
+{
+    if (!cfg || !out) {
+        g_create_err = "create: null argument";
+        return SBMF_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(sbmf_config)) {
+        g_create_err = "create: sbmf_config.struct_size mismatch (use sbmf_cuda_config_default)";
+        return SBMF_ERR_INVALID;
+    }
+    if (cfg->K == 0 || cfg->K > SBMF_MAX_K) {
+        g_create_err = "create: K must be in [1, SBMF_MAX_K]";
+        return SBMF_ERR_INVALID;
+    }
+    if (cfg->sample_mode < 0 || cfg->sample_mode > 2 || cfg->hyper_mode != SBMF_HYPER_REF_T) {
+        g_create_err = "create: unknown sample_mode / hyper_mode";
+        return SBMF_ERR_INVALID;
+    }
+    if (cfg->world_size != 1 || cfg->rank != 0) {
+        g_create_err = "create: world_size > 1 is not implemented in this build";
+        return SBMF_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        return SBMF_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        g_create_err = "create: device ordinal out of range";
+        return SBMF_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) {
+        g_create_err = std::string("create: cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return SBMF_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_err = "create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                       ", this library is built for sm_100a (B200) only";
+        return SBMF_ERR_UNSUPPORTED;
+    }
+    sbmf_handle* h = new (std::nothrow) sbmf_handle();
+    if (!h) {
+        g_create_err = "create: out of host memory";
+        return SBMF_ERR_NOMEM;
+    }
+    Model& m = h->m;
+    m.cfg = *cfg;
+    if (m.cfg.rebuild_every == 0) m.cfg.rebuild_every = 1;
+    m.device = cfg->device;
+    m.sm_count = prop.multiProcessorCount;
+    m.K = cfg->K;
+    m.KB = (cfg->K + KBLK - 1) / KBLK;
+    m.KP = m.KB * KBLK;
+    m.us.site_f = SITE_U; m.us.site_b = SITE_BI; m.us.site_sigma_k = SITE_SIGMA_U; m.us.site_mu_k = SITE_MU_U;
+    m.us.site_sigma_b = SITE_SIGMA_BI; m.us.site_mu_b = SITE_MU_BI; m.us.prior = 2; m.us.prior_b = 4;
+    m.it.site_f = SITE_V; m.it.site_b = SITE_BJ; m.it.site_sigma_k = SITE_SIGMA_V; m.it.site_mu_k = SITE_MU_V;
+    m.it.site_sigma_b = SITE_SIGMA_BJ; m.it.site_mu_b = SITE_MU_BJ; m.it.prior = 1; m.it.prior_b = 5;
+    bool ok = cudaSetDevice(m.device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&m.s_main, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&m.s_aux, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&m.ev_join, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&m.ev_t[i]) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&m.sc, sizeof(Scalars)) == cudaSuccess;
+    ok = ok && cudaMemset(m.sc, 0, sizeof(Scalars)) == cudaSuccess;
+    m.hist_cap = 4096;
+    ok = ok && cudaMalloc((void**)&m.rmse_hist, (size_t)m.hist_cap * 2 * sizeof(double)) == cudaSuccess;
+    if (!ok) {
+        g_create_err = std::string("create: CUDA resource setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        sbmf_cuda_destroy(h);
+        return SBMF_ERR_CUDA;
+    }
+    *out = h;
+    return SBMF_OK;
+}
+
+int sbmf_cuda_destroy(sbmf_handle* h)
+{
+    if (!h) return SBMF_OK;
+    Model& m = h->m;
+    cudaSetDevice(m.device);
+    if (m.s_main) cudaStreamSynchronize(m.s_main);
+    if (m.s_aux) cudaStreamSynchronize(m.s_aux);
+    free_storage(m);
+    free_test(m);
+    cudaFree(m.sc);
+    cudaFree(m.rmse_hist);
+    for (int i = 0; i < 8; ++i)
+        if (m.ev_t[i]) cudaEventDestroy(m.ev_t[i]);
+    if (m.ev_fork) cudaEventDestroy(m.ev_fork);
+    if (m.ev_join) cudaEventDestroy(m.ev_join);
+    if (m.s_main) cudaStreamDestroy(m.s_main);
+    if (m.s_aux) cudaStreamDestroy(m.s_aux);
+    delete h;
+    return SBMF_OK;
+}
+
+const char* sbmf_cuda_last_error(const sbmf_handle* h) { return h ? h->m.err.c_str() : g_create_err.c_str(); }
+
+int sbmf_cuda_nccl_unique_id(uint8_t out[128])
+{
+    (void)out;
+    g_create_err = "nccl_unique_id: multi-GPU is not implemented in this build";
+    return SBMF_ERR_UNSUPPORTED;
+}
+
+int sbmf_cuda_set_train(sbmf_handle* h, uint64_t n, const uint32_t* user, const uint32_t* item, const float* rating, uint32_t num_users,
+                        uint32_t num_items)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if ((n && (!user || !item || !rating)) || num_users == 0 || num_items == 0) {
+        m.err = "set_train: null array or empty id space";
+        return SBMF_ERR_INVALID;
+    }
+    API_CK(cudaSetDevice(m.device));
+    free_test(m);
+    return build_storage(m, n, user, item, rating, num_users, num_items);
+}
+
+int sbmf_cuda_set_test(sbmf_handle* h, uint64_t nt, const uint32_t* user, const uint32_t* item, const float* rating)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (!m.have_train) {
+        m.err = "set_test: call set_train first (it fixes num_users / num_items)";
+        return SBMF_ERR_STATE;
+    }
+    if (nt && (!user || !item || !rating)) {
+        m.err = "set_test: null array";
+        return SBMF_ERR_INVALID;
+    }
+    for (uint64_t t = 0; t < nt; ++t)
+        if (user[t] >= m.I || item[t] >= m.J) {
+            m.err = "set_test: id out of range at test rating " + std::to_string(t) +
+                    " (num_users / num_items must cover train and test, [T]:151-153)";
+            return SBMF_ERR_INVALID;
+        }
+    API_CK(cudaSetDevice(m.device));
+    return build_test(m, nt, user, item, rating);
+}
+
+int sbmf_cuda_get_layout(sbmf_handle* h, int64_t* row_ptr, uint32_t* col, uint64_t* csr_id, int64_t* col_ptr, uint32_t* row, uint64_t* csc_id,
+                         uint64_t* perm)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (!m.have_train) {
+        m.err = "get_layout: no training set";
+        return SBMF_ERR_STATE;
+    }
+    API_CK(cudaSetDevice(m.device));
+    API_CK(cudaStreamSynchronize(m.s_main));
+    std::vector<uint32_t> tmp;
+    if (row_ptr) API_CK(cudaMemcpy(row_ptr, m.us.ptr, ((size_t)m.I + 1) * 8, cudaMemcpyDeviceToHost));
+    if (col_ptr) API_CK(cudaMemcpy(col_ptr, m.it.ptr, ((size_t)m.J + 1) * 8, cudaMemcpyDeviceToHost));
+    if (col) API_CK(cudaMemcpy(col, m.us.idx, m.N * 4, cudaMemcpyDeviceToHost));
+    if (row) API_CK(cudaMemcpy(row, m.it.idx, m.N * 4, cudaMemcpyDeviceToHost));
+    if (csr_id) API_CK(copy_out_widen(csr_id, m.csr_id, m.N, tmp));
+    if (csc_id) API_CK(copy_out_widen(csc_id, m.csc_id, m.N, tmp));
+    if (perm) API_CK(copy_out_widen(perm, m.perm, m.N, tmp));
+    return SBMF_OK;
+}
+
+int sbmf_cuda_init_factors(sbmf_handle* h, const float* U0, const float* V0)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (!m.have_train) {
+        m.err = "init_factors: call set_train first";
+        return SBMF_ERR_STATE;
+    }
+    API_CK(cudaSetDevice(m.device));
+    cudaStream_t st = m.s_main;
+    float* d_tmp = nullptr;
+    const size_t nu = (size_t)m.I * m.K, nv = (size_t)m.K * m.J;
+    if (U0 || V0) API_CK(cudaMalloc((void**)&d_tmp, std::max(nu, nv) * 4));
+    if (U0) {
+        API_CK(cudaMemcpyAsync(d_tmp, U0, nu * 4, cudaMemcpyHostToDevice, st));
+        launch_load_factors(m, m.us, d_tmp, false, st);
+        API_CK(cudaStreamSynchronize(st));
+    } else {
+        launch_init_factors(m, m.us, SITE_INIT_U, st);
+    }
+    if (V0) {
+        API_CK(cudaMemcpyAsync(d_tmp, V0, nv * 4, cudaMemcpyHostToDevice, st));
+        launch_load_factors(m, m.it, d_tmp, true, st);
+        API_CK(cudaStreamSynchronize(st));
+    } else {
+        launch_init_factors(m, m.it, SITE_INIT_V, st);
+    }
+    cudaFree(d_tmp);
+    // [T]:268-281, 315-318: biases, bias hypers, per-dimension hypers and the scalars start at 0
+    for (Side* s : {&m.us, &m.it}) {
+        API_CK(cudaMemsetAsync(s->bias, 0, (size_t)s->n * 4, st));
+        API_CK(cudaMemsetAsync(s->mu_b, 0, (size_t)s->n * 4, st));
+        API_CK(cudaMemsetAsync(s->sigma_b, 0, (size_t)s->n * 4, st));
+        API_CK(cudaMemsetAsync(s->sigma_k, 0, (size_t)m.KP * 8, st));
+        API_CK(cudaMemsetAsync(s->mu_k, 0, (size_t)m.KP * 8, st));
+        API_CK(cudaMemsetAsync(s->sigma_kf, 0, (size_t)m.KP * 4, st));
+        API_CK(cudaMemsetAsync(s->mu_kf, 0, (size_t)m.KP * 4, st));
+    }
+    API_CK(cudaMemsetAsync(m.sc, 0, sizeof(Scalars), st));
+    API_CK(cudaMemsetAsync(m.rmse_hist, 0, (size_t)m.hist_cap * 16, st));
+    if (m.have_test) API_CK(cudaMemsetAsync(m.t_sum, 0, (m.Nt ? m.Nt : 1) * 8, st));
+    API_CK(cudaGetLastError());
+    API_CK(cudaStreamSynchronize(st));
+    m.sweeps_done = 0;
+    m.e_in_csc = false;
+    m.have_factors = true;
+    return SBMF_OK;
+}
+
+// One body of the loop [T]:335-637.
+static int one_sweep(Model& m)
+{
+    cudaStream_t st = m.s_main;
+    const bool timing = m.timing_enabled;
+    const bool rebuild = (m.sweeps_done % m.cfg.rebuild_every) == 0;
+    if (timing) cudaEventRecord(m.ev_t[0], st);
+    if (rebuild) {
+        launch_rebuild(m, st);                       // [T]:342-359
+    } else {
+        if (m.e_in_csc) launch_permute(m, false, st);
+        launch_stats(m, st);
+    }
+    if (timing) cudaEventRecord(m.ev_t[1], st);
+    launch_global_hypers(m, st);                     // [T]:366-410
+    launch_dim_hypers(m, st);                        // [T]:415-467
+    launch_bias_hypers(m, st);                       // [T]:469-511
+    if (timing) cudaEventRecord(m.ev_t[2], st);
+    launch_phase(m, m.us, m.it, true);               // [T]:514-558
+    if (timing) cudaEventRecord(m.ev_t[3], st);
+    launch_permute(m, true, st);                     // residual CSR order -> CSC order
+    if (timing) cudaEventRecord(m.ev_t[4], st);
+    launch_phase(m, m.it, m.us, false);              // [T]:563-606
+    m.e_in_csc = true;
+    if (timing) cudaEventRecord(m.ev_t[5], st);
+    launch_eval(m, st);                              // [T]:610-636
+    if (timing) cudaEventRecord(m.ev_t[6], st);
+    m.sweeps_done++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        m.err = std::string("sweep: kernel launch failed: ") + cudaGetErrorString(e);
+        return SBMF_ERR_CUDA;
+    }
+    if (timing) {
+        // per-phase timing needs the events of this sweep: it serialises host and device once per sweep
+        if ((e = cudaEventSynchronize(m.ev_t[6])) != cudaSuccess) {
+            m.err = std::string("sweep: ") + cudaGetErrorString(e);
+            return SBMF_ERR_CUDA;
+        }
+        float ms[6];
+        for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms[i], m.ev_t[i], m.ev_t[i + 1]);
+        m.timing.ms_rebuild += ms[0];
+        m.timing.ms_hypers += ms[1];
+        m.timing.ms_user_phase += ms[2];
+        m.timing.ms_exchange += ms[3];
+        m.timing.ms_item_phase += ms[4];
+        m.timing.ms_eval += ms[5];
+        float tot = 0.f;
+        cudaEventElapsedTime(&tot, m.ev_t[0], m.ev_t[6]);
+        m.timing.ms_total += tot;
+        m.timing.sweeps++;
+    }
+    return SBMF_OK;
+}
+
+int sbmf_cuda_sweep(sbmf_handle* h, uint32_t n_sweeps)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (!m.have_train || !m.have_factors) {
+        m.err = "sweep: call set_train and init_factors first";
+        return SBMF_ERR_STATE;
+    }
+    if (!m.have_test) {
+        int rc = build_test(m, 0, nullptr, nullptr, nullptr);
+        if (rc != SBMF_OK) return rc;
+    }
+    API_CK(cudaSetDevice(m.device));
+    for (uint32_t s = 0; s < n_sweeps; ++s) {
+        int rc = one_sweep(m);
+        if (rc != SBMF_OK) return rc;
+    }
+    return SBMF_OK;
+}
+
+int sbmf_cuda_synchronize(sbmf_handle* h)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    API_CK(cudaSetDevice(m.device));
+    API_CK(cudaStreamSynchronize(m.s_main));
+    API_CK(cudaStreamSynchronize(m.s_aux));
+    return SBMF_OK;
+}
+
+int sbmf_cuda_eval(sbmf_handle* h, double* rmse_running_mean, double* rmse_last_sweep)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (m.sweeps_done == 0) {
+        m.err = "eval: no sweep has run";
+        return SBMF_ERR_STATE;
+    }
+    API_CK(cudaSetDevice(m.device));
+    double v[2];
+    API_CK(cudaMemcpyAsync(v, &m.sc->rmse_mean, 16, cudaMemcpyDeviceToHost, m.s_main));
+    API_CK(cudaStreamSynchronize(m.s_main));
+    if (rmse_running_mean) *rmse_running_mean = v[0];
+    if (rmse_last_sweep) *rmse_last_sweep = v[1];
+    return SBMF_OK;
+}
+
+int sbmf_cuda_get_rmse_history(sbmf_handle* h, uint32_t first, uint32_t count, double* rmse_running_mean, double* rmse_sweep)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if ((uint64_t)first + count > m.sweeps_done || (uint64_t)first + count > m.hist_cap) {
+        m.err = "get_rmse_history: range exceeds the sweeps run (or the 4096-sweep history)";
+        return SBMF_ERR_INVALID;
+    }
+    API_CK(cudaSetDevice(m.device));
+    std::vector<double> tmp((size_t)count * 2 + 2);
+    API_CK(cudaMemcpyAsync(tmp.data(), m.rmse_hist + (size_t)first * 2, (size_t)count * 16, cudaMemcpyDeviceToHost, m.s_main));
+    API_CK(cudaStreamSynchronize(m.s_main));
+    for (uint32_t i = 0; i < count; ++i) {
+        if (rmse_running_mean) rmse_running_mean[i] = tmp[(size_t)i * 2];
+        if (rmse_sweep) rmse_sweep[i] = tmp[(size_t)i * 2 + 1];
+    }
+    return SBMF_OK;
+}
+
+int sbmf_cuda_get_pred(sbmf_handle* h, float* pred)
+{
+    if (!h || !pred) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (!m.have_test || m.sweeps_done <= m.cfg.burn_in) {
+        m.err = "get_pred: no test set or no collected sweep";
+        return SBMF_ERR_STATE;
+    }
+    API_CK(cudaSetDevice(m.device));
+    std::vector<double> tmp(m.Nt ? m.Nt : 1);
+    API_CK(cudaMemcpyAsync(tmp.data(), m.t_sum, m.Nt * 8, cudaMemcpyDeviceToHost, m.s_main));
+    API_CK(cudaStreamSynchronize(m.s_main));
+    const double denom = (double)(m.sweeps_done - m.cfg.burn_in);
+    for (uint64_t t = 0; t < m.Nt; ++t) pred[t] = (float)(tmp[t] / denom);
+    return SBMF_OK;
+}
+
+int sbmf_cuda_get_state(sbmf_handle* h, sbmf_state* out)
+{
+    if (!h || !out) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (!m.have_factors) {
+        m.err = "get_state: call init_factors first";
+        return SBMF_ERR_STATE;
+    }
+    API_CK(cudaSetDevice(m.device));
+    cudaStream_t st = m.s_main;
+    API_CK(cudaStreamSynchronize(st));
+    if (out->U || out->V) {
+        float* d_tmp = nullptr;
+        const size_t nu = (size_t)m.I * m.K, nv = (size_t)m.K * m.J;
+        API_CK(cudaMalloc((void**)&d_tmp, std::max(nu, nv) * 4));
+        if (out->U) {
+            launch_export_factors(m, m.us, d_tmp, false, st);
+            API_CK(cudaMemcpyAsync(out->U, d_tmp, nu * 4, cudaMemcpyDeviceToHost, st));
+            API_CK(cudaStreamSynchronize(st));
+        }
+        if (out->V) {
+            launch_export_factors(m, m.it, d_tmp, true, st);
+            API_CK(cudaMemcpyAsync(out->V, d_tmp, nv * 4, cudaMemcpyDeviceToHost, st));
+            API_CK(cudaStreamSynchronize(st));
+        }
+        cudaFree(d_tmp);
+    }
+    if (out->b_i) API_CK(cudaMemcpy(out->b_i, m.us.bias, (size_t)m.I * 4, cudaMemcpyDeviceToHost));
+    if (out->b_j) API_CK(cudaMemcpy(out->b_j, m.it.bias, (size_t)m.J * 4, cudaMemcpyDeviceToHost));
+    if (out->mu_b_i) API_CK(cudaMemcpy(out->mu_b_i, m.us.mu_b, (size_t)m.I * 4, cudaMemcpyDeviceToHost));
+    if (out->sigma_b_i) API_CK(cudaMemcpy(out->sigma_b_i, m.us.sigma_b, (size_t)m.I * 4, cudaMemcpyDeviceToHost));
+    if (out->mu_b_j) API_CK(cudaMemcpy(out->mu_b_j, m.it.mu_b, (size_t)m.J * 4, cudaMemcpyDeviceToHost));
+    if (out->sigma_b_j) API_CK(cudaMemcpy(out->sigma_b_j, m.it.sigma_b, (size_t)m.J * 4, cudaMemcpyDeviceToHost));
+    if (out->sigma_u) API_CK(cudaMemcpy(out->sigma_u, m.us.sigma_k, (size_t)m.K * 8, cudaMemcpyDeviceToHost));
+    if (out->mu_u) API_CK(cudaMemcpy(out->mu_u, m.us.mu_k, (size_t)m.K * 8, cudaMemcpyDeviceToHost));
+    if (out->sigma_v) API_CK(cudaMemcpy(out->sigma_v, m.it.sigma_k, (size_t)m.K * 8, cudaMemcpyDeviceToHost));
+    if (out->mu_v) API_CK(cudaMemcpy(out->mu_v, m.it.mu_k, (size_t)m.K * 8, cudaMemcpyDeviceToHost));
+    if (out->E) {
+        // residual in rating (file) order, from whichever layout holds the freshest copy
+        std::vector<float> e(m.N ? m.N : 1);
+        std::vector<uint32_t> id(m.N ? m.N : 1);
+        API_CK(cudaMemcpy(e.data(), m.e_in_csc ? m.it.e : m.us.e, m.N * 4, cudaMemcpyDeviceToHost));
+        API_CK(cudaMemcpy(id.data(), m.e_in_csc ? m.csc_id : m.csr_id, m.N * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t s = 0; s < m.N; ++s) out->E[id[s]] = e[s];
+    }
+    Scalars sc;
+    API_CK(cudaMemcpy(&sc, m.sc, sizeof(Scalars), cudaMemcpyDeviceToHost));
+    out->b_0 = sc.b_0;
+    out->alpha = sc.alpha;
+    out->mu_b_0 = sc.mu_b_0;
+    out->sigma_b_0 = sc.sigma_b_0;
+    out->sum_e = sc.sum_e;
+    out->sum_e2 = sc.sum_e2;
+    out->sweeps_done = m.sweeps_done;
+    return SBMF_OK;
+}
+
+int sbmf_cuda_get_timing(sbmf_handle* h, sbmf_timing* out)
+{
+    if (!h || !out) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    *out = m.timing;
+    out->kernel_launches = m.launches;
+    out->nnz_light_user = m.us.nnz_resident;
+    out->nnz_heavy_user = m.us.nnz_heavy;
+    out->nnz_light_item = m.it.nnz_resident;
+    out->nnz_heavy_item = m.it.nnz_heavy;
+    return SBMF_OK;
+}
+
+int sbmf_cuda_reset_timing(sbmf_handle* h)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    h->m.timing = sbmf_timing{};
+    h->m.launches = 0;
+    return SBMF_OK;
+}
+
+int sbmf_cuda_set_timing_enabled(sbmf_handle* h, int enabled)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    h->m.timing_enabled = enabled != 0;
+    return SBMF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,852 @@
+// kernels.cu -- the device side of one SBMF Gibbs sweep (gibbs_sbpmf2.cpp "[T]":335-637), sm_100a.
+//
+// The factor half-steps ([T]:538-556 users, 586-605 items) are restructured, not translated.  [T] walks a
+// row's ratings twice per latent dimension (reduce, then residual update).  Here 8 consecutive dimensions
+// ("a block") are updated from ONE pass: with f_p = the 8 opposite-side factors of rating p (one 32-byte
+// sector, one LDG.256) the kernel accumulates
+//        g[k]    = sum_p f_p[k] * e_p                  (8 values)
+//        G[k][l] = sum_p f_p[k] * f_p[l],  k <= l      (36 values)
+// and then replays [T]'s sequential coordinate updates for k = 0..7 exactly, because the sums [T] would
+// compute after the earlier dimensions of the block changed e are
+//        A_k = G[k][k],   B_k = g[k] + sum_{l<k} G[l][k] * (u_l_old - u_l_new) + G[k][k] * u_k_old .
+// The residual is then updated once, e_p += sum_k f_p[k] * (u_k_old - u_k_new).  Same chain of conditionals,
+// same scan order, 1/8 of the residual/index traffic; rows of up to 2048 ratings keep (idx, e, f) in
+// registers so the residual is read and written once per LAUNCH (possibly several blocks), longer rows stream
+// through a sliced two-kernel pipeline that applies the previous block's delta while accumulating the next.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "model.h"
+
+namespace sbmf {
+
+// --------------------------------------------------------------------------------------------------------
+struct PhaseArgs {
+    const int64_t* ptr;
+    const uint32_t* idx;
+    float* e;
+    float* Fself;
+    const float* Fother;
+    uint32_t n_self, n_other;
+    float* bias;
+    const float* mu_b;
+    const float* sigma_b;
+    const float* sigma_kf;
+    const float* mu_kf;
+    const Scalars* sc;
+    uint32_t K;
+    uint64_t seed;
+    uint32_t site_f, site_b;
+    int mode;          // SampleMode
+    int apply_shift;   // user phase: add sc->shift_f on the first touch of e ([T]:407-410)
+};
+
+__host__ __device__ constexpr int gi(int k, int l) { return 8 + k * 8 - (k * (k - 1)) / 2 + (l - k); }   // k <= l
+
+__device__ __forceinline__ void accumulate(float (&acc)[NACC], const f8& f, float e)
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = fmaf(f.v[k], e, acc[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int l = k; l < 8; ++l) acc[gi(k, l)] = fmaf(f.v[k], f.v[l], acc[gi(k, l)]);
+}
+
+__device__ __forceinline__ float dot8(const f8& a, const float (&d)[8])
+{
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = fmaf(a.v[k], d[k], s);
+    return s;
+}
+
+// ran_gaussian(mean, stdev) of random.h:166-172 with [T]'s "variance passed as stdev" 
+__device__ __forceinline__ float draw_f32(int mode, float mean, float var, float z)
+{
+    if (mode == SAMPLE_ZERO) return mean;
+    const float sd = (mode == SAMPLE_SQRT) ? sqrtf(var) : var;
+    if (sd == 0.f || isnan(sd)) return mean;
+    return fmaf(sd, z, mean);
+}
+
+// The 8 sequential coordinate updates of one block ([T]:546-551 / 594-599) from the reduced sums.
+// tot = g[8], G[36] as laid out by gi(); z[k] = this row's standard normal for dimension 8b+k.
+__device__ __forceinline__ void solve_block(const float* tot, const f8& uo, const float (&z)[8], const float* sig, const float* mu,
+                                            float alpha, int mode, int kvalid, f8& un, float (&d)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < kvalid) {
+            const float A = tot[gi(k, k)];
+            float B = fmaf(A, uo.v[k], tot[k]);
+#pragma unroll
+            for (int l = 0; l < k; ++l) B = fmaf(d[l], tot[gi(l, k)], B);
+            const float s = 1.0f / (sig[k] + alpha * A);
+            const float mean = s * (alpha * B + sig[k] * mu[k]);
+            un.v[k] = draw_f32(mode, mean, s, z[k]);
+            d[k] = uo.v[k] - un.v[k];
+        } else {   // padding dimensions of the last block stay exactly zero
+            un.v[k] = 0.f;
+            d[k] = 0.f;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Resident rows: WARPS warps own one row, each lane keeps RPL (idx, e, f) triples in registers.
+// blocks [b_begin, b_end) are processed in one launch; do_bias runs the bias half-step ([T]:517-534 / 566-582) first.
+template <int RPL, int WARPS>
+__global__ void __launch_bounds__(WARPS == 1 ? 256 : WARPS * 32)
+row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows, int b_begin, int b_end, int do_bias)
+{
+    constexpr int WPC = (WARPS == 1) ? 8 : WARPS;   // warps per CTA
+    __shared__ __align__(16) float s_tot[(WARPS == 1) ? WPC : 1][NACC];
+    __shared__ __align__(16) float s_part[(WARPS == 1) ? 1 : WARPS][NACC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t r_idx = (WARPS == 1) ? blockIdx.x * WPC + warp : blockIdx.x;
+    if (r_idx >= nrows) return;   // WARPS == 1: whole warp leaves; no block-wide barrier is used in that shape
+    const uint32_t row = rows[r_idx];
+    const int64_t beg = a.ptr[row];
+    const int c = (int)(a.ptr[row + 1] - beg);
+    const int t_in_row = (WARPS == 1) ? lane : threadIdx.x;
+    constexpr int TPR = WARPS * 32;   // threads per row
+    float* tot = (WARPS == 1) ? s_tot[warp] : s_tot[0];
+
+    const float alpha = a.sc->alpha_f;
+    const uint32_t sweep = a.sc->sweep;
+
+    uint32_t id[RPL];
+    float e[RPL];
+    bool valid[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int p = r * TPR + t_in_row;
+        valid[r] = p < c;
+        id[r] = valid[r] ? a.idx[beg + p] : 0u;
+        e[r] = valid[r] ? a.e[beg + p] : 0.f;
+    }
+
+    if (do_bias) {
+        const float shift = a.apply_shift ? a.sc->shift_f : 0.f;
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            if (valid[r]) {
+                e[r] += shift;
+                t += e[r];
+            }
+        t = warp_sum(t);
+        if (WARPS > 1) {
+            if (lane == 0) s_part[warp][0] = t;
+            __syncthreads();
+            t = 0.f;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) t += s_part[w][0];
+            __syncthreads();
+        }
+        const float bo = a.bias[row], sb = a.sigma_b[row], mb = a.mu_b[row];
+        const float s = 1.0f / (sb + alpha * (float)c);
+        const float mean = s * (sb * mb + alpha * (t + (float)c * bo));
+        float z = 0.f;
+        if (a.mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        const float bn = draw_f32(a.mode, mean, s, z);
+        const float d = bo - bn;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            if (valid[r]) e[r] += d;
+        if (t_in_row == 0) a.bias[row] = bn;
+    }
+
+    for (int b = b_begin; b < b_end; ++b) {
+        // this row's noise for the 8 dimensions of the block: lane k draws dimension 8b+k
+        float zl = 0.f;
+        if (a.mode != SAMPLE_ZERO && lane < 8) zl = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)(b * 8 + lane), sweep));
+        const float* Fo = a.Fother + (size_t)b * a.n_other * 8;
+        f8 f[RPL];
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            if (valid[r]) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[r].v[k] = 0.f;
+            }
+        }
+        float acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) accumulate(acc, f[r], e[r]);
+        warp_reduce_scatter48(acc, lane);
+        const int base = reduce_scatter_base(lane);
+        if (WARPS == 1) {
+            if ((lane & 1) == 0) {
+                tot[base] = acc[0];
+                tot[base + 1] = acc[1];
+                tot[base + 2] = acc[2];
+            }
+            __syncwarp();
+        } else {
+            if ((lane & 1) == 0) {
+                s_part[warp][base] = acc[0];
+                s_part[warp][base + 1] = acc[1];
+                s_part[warp][base + 2] = acc[2];
+            }
+            __syncthreads();
+            if (threadIdx.x < NACC) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) s += s_part[w][threadIdx.x];
+                tot[threadIdx.x] = s;
+            }
+            __syncthreads();
+        }
+        float z[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) z[k] = __shfl_sync(0xffffffffu, zl, k);
+        float* Fs = a.Fself + ((size_t)b * a.n_self + row) * 8;
+        const f8 uo = ld256(Fs);
+        f8 un;
+        float d[8];
+        solve_block(tot, uo, z, a.sigma_kf + b * 8, a.mu_kf + b * 8, alpha, a.mode, (int)a.K - b * 8, un, d);
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) e[r] += dot8(f[r], d);
+        if (t_in_row == 0) st256(Fs, un);
+        if (WARPS == 1) __syncwarp();   // tot is rewritten by the next block
+        else __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int p = r * TPR + t_in_row;
+        if (valid[r]) a.e[beg + p] = e[r];
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Heavy rows: sliced streaming pipeline.  accumulate<PREV,CUR> applies the pending delta of the previous step
+// to e (PREV: 0 = only the global shift, 1 = bias delta, 2 = delta of block pb, re-gathering f) and accumulates
+// the partial sums of the current step (CUR: 0 = nothing, 1 = bias: sum e, 2 = block b: g, G) per slice;
+// heavy_solve<CUR> combines a row's slices in slice order and performs the update(s).
+template <int PREV, int CUR>
+__global__ void __launch_bounds__(SLICE_THREADS)
+heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const float* __restrict__ hdelta, const float* __restrict__ hbias_delta,
+                        float* __restrict__ hpart, int pb, int b)
+{
+    __shared__ float s_part[SLICE_THREADS / 32][NACC];
+    const Slice sl = slices[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float dprev[8];
+    float dscalar = 0.f;
+    if (PREV == 0) dscalar = a.apply_shift ? a.sc->shift_f : 0.f;
+    if (PREV == 1) dscalar = hbias_delta[sl.hrow];
+    if (PREV == 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dprev[k] = hdelta[(size_t)sl.hrow * 8 + k];
+    }
+    const float* Fp = a.Fother + (size_t)pb * a.n_other * 8;
+    const float* Fc = a.Fother + (size_t)b * a.n_other * 8;
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    const uint32_t* idx = a.idx + sl.start;
+    float* ep = a.e + sl.start;
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < sl.len; i += SLICE_THREADS) {
+        float e = ep[i];
+        const uint32_t id = idx[i];
+        if (PREV == 2) {
+            const f8 fp = ld256_nc(Fp + (size_t)id * 8);
+            e += dot8(fp, dprev);
+        } else {
+            e += dscalar;
+        }
+        ep[i] = e;
+        if (CUR == 1) acc[0] += e;
+        if (CUR == 2) {
+            const f8 f = ld256_nc(Fc + (size_t)id * 8);
+            accumulate(acc, f, e);
+        }
+    }
+    if (CUR == 1) {
+        const float t = warp_sum(acc[0]);
+        if (lane == 0) s_part[warp][0] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < SLICE_THREADS / 32; ++w) s += s_part[w][0];
+            hpart[(size_t)blockIdx.x * NACC] = s;
+        }
+    }
+    if (CUR == 2) {
+        warp_reduce_scatter48(acc, lane);
+        const int base = reduce_scatter_base(lane);
+        if ((lane & 1) == 0) {
+            s_part[warp][base] = acc[0];
+            s_part[warp][base + 1] = acc[1];
+            s_part[warp][base + 2] = acc[2];
+        }
+        __syncthreads();
+        if (threadIdx.x < NACC) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < SLICE_THREADS / 32; ++w) s += s_part[w][threadIdx.x];
+            hpart[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
+        }
+    }
+}
+
+template <int CUR>
+__global__ void __launch_bounds__(128)
+heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const uint32_t* __restrict__ slice_ptr, uint32_t n_heavy,
+                   const float* __restrict__ hpart, float* __restrict__ hdelta, float* __restrict__ hbias_delta, int b)
+{
+    __shared__ __align__(16) float s_tot[4][NACC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t hrow = blockIdx.x * 4 + warp;
+    if (hrow >= n_heavy) return;
+    const uint32_t row = heavy_rows[hrow];
+    const uint32_t s0 = slice_ptr[hrow], s1 = slice_ptr[hrow + 1];
+    const float alpha = a.sc->alpha_f;
+    const uint32_t sweep = a.sc->sweep;
+    if (CUR == 1) {
+        float t = 0.f;
+        for (uint32_t s = s0 + lane; s < s1; s += 32) t += hpart[(size_t)s * NACC];
+        t = warp_sum(t);
+        const float c = (float)(a.ptr[row + 1] - a.ptr[row]);
+        const float bo = a.bias[row], sb = a.sigma_b[row], mb = a.mu_b[row];
+        const float s = 1.0f / (sb + alpha * c);
+        const float mean = s * (sb * mb + alpha * (t + c * bo));
+        float z = 0.f;
+        if (a.mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        const float bn = draw_f32(a.mode, mean, s, z);
+        if (lane == 0) {
+            a.bias[row] = bn;
+            hbias_delta[hrow] = bo - bn;
+        }
+    } else {
+        float zl = 0.f;
+        if (a.mode != SAMPLE_ZERO && lane < 8) zl = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)(b * 8 + lane), sweep));
+        float a0 = 0.f, a1 = 0.f;
+        for (uint32_t s = s0; s < s1; ++s) {
+            a0 += hpart[(size_t)s * NACC + lane];
+            if (lane < NACC - 32) a1 += hpart[(size_t)s * NACC + 32 + lane];
+        }
+        s_tot[warp][lane] = a0;
+        if (lane < NACC - 32) s_tot[warp][32 + lane] = a1;
+        __syncwarp();
+        float z[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) z[k] = __shfl_sync(0xffffffffu, zl, k);
+        float* Fs = a.Fself + ((size_t)b * a.n_self + row) * 8;
+        const f8 uo = ld256(Fs);
+        f8 un;
+        float d[8];
+        solve_block(s_tot[warp], uo, z, a.sigma_kf + b * 8, a.mu_kf + b * 8, alpha, a.mode, (int)a.K - b * 8, un, d);
+        if (lane == 0) {
+            st256(Fs, un);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hdelta[(size_t)hrow * 8 + k] = d[k];
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Residual rebuild [T]:342-359 in CSR slot order, with per-block partial statistics.
+constexpr int RED_THREADS = 256;
+
+__device__ __forceinline__ void block_reduce2_store(double s1, double s2, double* out)
+{
+    __shared__ double sh[2][RED_THREADS / 32];
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sh[0][warp] = s1;
+        sh[1][warp] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < RED_THREADS / 32; ++w) {
+            t1 += sh[0][w];
+            t2 += sh[1][w];
+        }
+        out[0] = t1;
+        out[1] = t2;
+    }
+}
+
+__device__ __forceinline__ float dot_blocked(const float* __restrict__ Fu, const float* __restrict__ Fv, uint32_t I, uint32_t J, uint32_t KB,
+                                             uint32_t u, uint32_t j)
+{
+    float dot = 0.f;
+#pragma unroll 4
+    for (uint32_t b = 0; b < KB; ++b) {
+        const f8 fu = ld256_nc(Fu + ((size_t)b * I + u) * 8);
+        const f8 fv = ld256_nc(Fv + ((size_t)b * J + j) * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dot = fmaf(fu.v[k], fv.v[k], dot);
+    }
+    return dot;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+rebuild_kernel(const uint32_t* __restrict__ urow, const uint32_t* __restrict__ col, const float* __restrict__ r, float* __restrict__ e,
+               const float* __restrict__ Fu, const float* __restrict__ Fv, const float* __restrict__ bi, const float* __restrict__ bj,
+               const Scalars* __restrict__ sc, uint32_t I, uint32_t J, uint32_t KB, uint64_t N, double* __restrict__ part)
+{
+    const float b0 = sc->b_0_f;
+    double s1 = 0.0, s2 = 0.0;
+    for (uint64_t s = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; s < N; s += (uint64_t)gridDim.x * RED_THREADS) {
+        const uint32_t u = urow[s], j = col[s];
+        const float dot = dot_blocked(Fu, Fv, I, J, KB, u, j);
+        const float ev = r[s] - (b0 + bi[u] + bj[j] + dot);
+        e[s] = ev;
+        s1 += (double)ev;
+        s2 += (double)ev * (double)ev;
+    }
+    block_reduce2_store(s1, s2, part + (size_t)blockIdx.x * 2);
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+stats_kernel(const float* __restrict__ e, uint64_t N, double* __restrict__ part)
+{
+    double s1 = 0.0, s2 = 0.0;
+    for (uint64_t s = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; s < N; s += (uint64_t)gridDim.x * RED_THREADS) {
+        const double ev = (double)e[s];
+        s1 += ev;
+        s2 += ev * ev;
+    }
+    block_reduce2_store(s1, s2, part + (size_t)blockIdx.x * 2);
+}
+
+// final reduce of the statistics + the scalar chain alpha, sigma_b_0, mu_b_0, b_0 of [T]:366-410
+__global__ void __launch_bounds__(RED_THREADS)
+global_hypers_kernel(Scalars* sc, const double* __restrict__ part, uint32_t nparts, uint64_t N, sbmf_priors pr, int mode, uint64_t seed)
+{
+    __shared__ double out[2];
+    double s1 = 0.0, s2 = 0.0;
+    for (uint32_t i = threadIdx.x; i < nparts; i += RED_THREADS) {
+        s1 += part[(size_t)i * 2];
+        s2 += part[(size_t)i * 2 + 1];
+    }
+    block_reduce2_store(s1, s2, out);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double S1 = out[0], S2 = out[1];
+    const uint32_t sweep = sc->sweep;
+    const double Nd = (double)N;
+    sc->sum_e = S1;
+    sc->sum_e2 = S2;
+    const double alpha = draw_gamma_f64(mode, seed, SITE_ALPHA, 0, sweep, pr.alpha_dash + Nd, pr.beta_dash + S2);
+    double b0 = sc->b_0, mu_b0 = sc->mu_b_0;
+    const double sigma_b0 = draw_gamma_f64(mode, seed, SITE_SIGMA_B0, 0, sweep, pr.alpha[0] + 1.0, pr.beta[0] + 0.5 * (b0 - mu_b0) * (b0 - mu_b0));
+    {
+        const double s = 1.0 / (pr.sigma[0] + sigma_b0);
+        const double m = s * (pr.sigma[0] * pr.mu[0] + b0 * sigma_b0);
+        mu_b0 = draw_gauss_f64(mode, seed, SITE_MU_B0, 0, 0, sweep, m, s);
+    }
+    {
+        const double s = 1.0 / (sigma_b0 + alpha * Nd);
+        const double m = s * (sigma_b0 * mu_b0 + alpha * (S1 + Nd * b0));
+        const double old = b0;
+        b0 = draw_gauss_f64(mode, seed, SITE_B0, 0, 0, sweep, m, s);
+        sc->shift_f = (float)(old - b0);
+    }
+    sc->alpha = alpha;
+    sc->sigma_b_0 = sigma_b0;
+    sc->mu_b_0 = mu_b0;
+    sc->b_0 = b0;
+    sc->alpha_f = (float)alpha;
+    sc->b_0_f = (float)b0;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Per-dimension hyper-parameters [T]:415-467.  Stage 1: (sum, sum of squared deviations from the OLD mean) per
+// chunk of rows for the 8 dimensions of a block; stage 2: ordered sum over chunks + the Gamma / Normal draws.
+constexpr int HYP_CHUNK = 16384;
+
+__global__ void __launch_bounds__(256)
+dim_hyper_partial_kernel(const float* __restrict__ F, uint32_t n, const double* __restrict__ mu_k, double* __restrict__ part, uint32_t chunks)
+{
+    __shared__ double sh[8][16];
+    const uint32_t b = blockIdx.y, chunk = blockIdx.x;
+    double mu[8], S[8], SS[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        mu[k] = mu_k[b * 8 + k];
+        S[k] = 0.0;
+        SS[k] = 0.0;
+    }
+    const uint32_t r0 = chunk * HYP_CHUNK;
+    const uint32_t r1 = min(n, r0 + HYP_CHUNK);
+    for (uint32_t r = r0 + threadIdx.x; r < r1; r += 256) {
+        const f8 f = ld256(F + ((size_t)b * n + r) * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double u = (double)f.v[k];
+            S[k] += u;
+            SS[k] += (u - mu[k]) * (u - mu[k]);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        S[k] = warp_sum(S[k]);
+        SS[k] = warp_sum(SS[k]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sh[warp][k] = S[k];
+            sh[warp][8 + k] = SS[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+        part[((size_t)b * chunks + chunk) * 16 + threadIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+dim_hyper_final_kernel(const double* __restrict__ part, uint32_t chunks, uint32_t n, uint32_t K, double* sigma_k, double* mu_k, float* sigma_kf,
+                       float* mu_kf, const Scalars* sc, double pa, double pb, double pmu, double psigma, int mode, uint64_t seed,
+                       uint32_t site_sigma, uint32_t site_mu)
+{
+    const uint32_t b = blockIdx.x, k = threadIdx.x;
+    if (k >= 8) return;
+    const uint32_t kk = b * 8 + k;
+    if (kk >= K) {
+        sigma_k[kk] = 1.0;
+        mu_k[kk] = 0.0;
+        sigma_kf[kk] = 1.f;
+        mu_kf[kk] = 0.f;
+        return;
+    }
+    double S = 0.0, SS = 0.0;
+    for (uint32_t c = 0; c < chunks; ++c) {
+        S += part[((size_t)b * chunks + c) * 16 + k];
+        SS += part[((size_t)b * chunks + c) * 16 + 8 + k];
+    }
+    const uint32_t sweep = sc->sweep;
+    const double nd = (double)n;
+    const double sig = draw_gamma_f64(mode, seed, site_sigma, kk, sweep, pa + nd, pb + 0.5 * SS);
+    const double s = 1.0 / (psigma + sig * nd);
+    const double m = s * (psigma * pmu + sig * S);
+    const double mu = draw_gauss_f64(mode, seed, site_mu, kk, 0, sweep, m, s);
+    sigma_k[kk] = sig;
+    mu_k[kk] = mu;
+    sigma_kf[kk] = (float)sig;
+    mu_kf[kk] = (float)mu;
+}
+
+// Per-row bias hyper-parameters [T]:469-511.
+__global__ void __launch_bounds__(256)
+bias_hyper_kernel(const float* __restrict__ bias, float* __restrict__ mu_b, float* __restrict__ sigma_b, uint32_t n, const Scalars* sc,
+                  double pa, double pb, double pmu, double psigma, int mode, uint64_t seed, uint32_t site_sigma, uint32_t site_mu)
+{
+    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t sweep = sc->sweep;
+    const double b = (double)bias[r], mo = (double)mu_b[r];
+    const double sig = draw_gamma_f64(mode, seed, site_sigma, r, sweep, pa + 1.0, pb + 0.5 * (b - mo) * (b - mo));
+    const double s = 1.0 / (psigma + sig);
+    const double m = s * (psigma * pmu + b * sig);
+    const double mu = draw_gauss_f64(mode, seed, site_mu, r, 0, sweep, m, s);
+    sigma_b[r] = (float)sig;
+    mu_b[r] = (float)mu;
+}
+
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+permute_gather_kernel(const float* __restrict__ src, const uint32_t* __restrict__ perm, float* __restrict__ dst, uint64_t N)
+{
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < N; t += (uint64_t)gridDim.x * 256) dst[t] = src[perm[t]];
+}
+__global__ void __launch_bounds__(256)
+permute_scatter_kernel(const float* __restrict__ src, const uint32_t* __restrict__ perm, float* __restrict__ dst, uint64_t N)
+{
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < N; t += (uint64_t)gridDim.x * 256) dst[perm[t]] = src[t];
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Test prediction + RMSE of the running posterior mean [T]:610-636.
+__global__ void __launch_bounds__(RED_THREADS)
+eval_kernel(const uint32_t* __restrict__ tu, const uint32_t* __restrict__ ti, const float* __restrict__ tr, double* __restrict__ tsum,
+            const float* __restrict__ Fu, const float* __restrict__ Fv, const float* __restrict__ bi, const float* __restrict__ bj,
+            const Scalars* __restrict__ sc, uint32_t I, uint32_t J, uint32_t KB, uint64_t Nt, uint32_t burn_in, float lo, float hi,
+            double* __restrict__ part)
+{
+    const float b0 = sc->b_0_f;
+    const uint32_t sweep = sc->sweep;
+    const bool collect = sweep >= burn_in;
+    const double denom = collect ? (double)(sweep + 1 - burn_in) : 1.0;
+    double s1 = 0.0, s2 = 0.0;
+    for (uint64_t t = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; t < Nt; t += (uint64_t)gridDim.x * RED_THREADS) {
+        const uint32_t u = tu[t], j = ti[t];
+        float p = b0 + bi[u] + bj[j] + dot_blocked(Fu, Fv, I, J, KB, u, j);
+        p = fminf(hi, p);
+        p = fmaxf(lo, p);
+        const double target = (double)tr[t];
+        double mean = (double)p;
+        if (collect) {
+            const double sm = tsum[t] + (double)p;
+            tsum[t] = sm;
+            mean = sm / denom;
+        }
+        s1 += (target - mean) * (target - mean);
+        s2 += (target - (double)p) * (target - (double)p);
+    }
+    block_reduce2_store(s1, s2, part + (size_t)blockIdx.x * 2);
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+eval_final_kernel(Scalars* sc, const double* __restrict__ part, uint32_t nparts, uint64_t Nt, double* __restrict__ hist, uint32_t hist_cap)
+{
+    __shared__ double out[2];
+    double s1 = 0.0, s2 = 0.0;
+    for (uint32_t i = threadIdx.x; i < nparts; i += RED_THREADS) {
+        s1 += part[(size_t)i * 2];
+        s2 += part[(size_t)i * 2 + 1];
+    }
+    block_reduce2_store(s1, s2, out);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const uint32_t sweep = sc->sweep;
+    const double rm = Nt ? sqrt(out[0] / (double)Nt) : 0.0;
+    const double rs = Nt ? sqrt(out[1] / (double)Nt) : 0.0;
+    sc->rmse_mean = rm;
+    sc->rmse_sweep = rs;
+    if (sweep < hist_cap) {
+        hist[(size_t)sweep * 2] = rm;
+        hist[(size_t)sweep * 2 + 1] = rs;
+    }
+    sc->sweep = sweep + 1;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Factor layout conversion / initialisation.
+__global__ void __launch_bounds__(256)
+init_factors_kernel(float* __restrict__ F, uint32_t n, uint32_t K, uint32_t KB, uint64_t seed, uint32_t site, float stdev)
+{
+    const uint64_t total = (uint64_t)KB * n * 8;
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
+        const uint32_t k8 = (uint32_t)(t & 7);
+        const uint64_t br = t >> 3;
+        const uint32_t row = (uint32_t)(br % n), b = (uint32_t)(br / n);
+        const uint32_t k = b * 8 + k8;
+        F[t] = (k < K) ? stdev * normal_f32(philox_site(seed, site, row, k, 0u)) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+load_factors_kernel(float* __restrict__ F, const float* __restrict__ src, uint32_t n, uint32_t K, uint32_t KB, int dim_major)
+{
+    const uint64_t total = (uint64_t)KB * n * 8;
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
+        const uint32_t k8 = (uint32_t)(t & 7);
+        const uint64_t br = t >> 3;
+        const uint32_t row = (uint32_t)(br % n), b = (uint32_t)(br / n);
+        const uint32_t k = b * 8 + k8;
+        float v = 0.f;
+        if (k < K) v = dim_major ? src[(size_t)k * n + row] : src[(size_t)row * K + k];
+        F[t] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+export_factors_kernel(const float* __restrict__ F, float* __restrict__ dst, uint32_t n, uint32_t K, int dim_major)
+{
+    const uint64_t total = (uint64_t)n * K;
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
+        uint32_t row, k;
+        if (dim_major) {
+            k = (uint32_t)(t / n);
+            row = (uint32_t)(t % n);
+        } else {
+            row = (uint32_t)(t / K);
+            k = (uint32_t)(t % K);
+        }
+        dst[t] = F[((size_t)(k >> 3) * n + row) * 8 + (k & 7)];
+    }
+}
+
+// ========================================================================================================
+// launch wrappers
+static inline uint32_t grid_for(uint64_t n, int threads, int cap)
+{
+    uint64_t g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > (uint64_t)cap) g = cap;
+    return (uint32_t)g;
+}
+
+void launch_init_factors(Model& m, Side& s, uint32_t site, cudaStream_t st)
+{
+    const uint64_t total = (uint64_t)m.KB * s.n * 8;
+    init_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, s.n, m.K, m.KB, m.cfg.seed, site, (float)m.cfg.init_stdev);
+    m.launches++;
+}
+
+void launch_load_factors(Model& m, Side& s, const float* d_src, bool dim_major, cudaStream_t st)
+{
+    const uint64_t total = (uint64_t)m.KB * s.n * 8;
+    load_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, d_src, s.n, m.K, m.KB, dim_major ? 1 : 0);
+    m.launches++;
+}
+
+void launch_export_factors(Model& m, const Side& s, float* d_out, bool dim_major, cudaStream_t st)
+{
+    const uint64_t total = (uint64_t)s.n * m.K;
+    export_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, d_out, s.n, m.K, dim_major ? 1 : 0);
+    m.launches++;
+}
+
+void launch_rebuild(Model& m, cudaStream_t st)
+{
+    rebuild_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.csr_urow, m.us.idx, m.csr_r, m.us.e, m.us.F, m.it.F, m.us.bias, m.it.bias, m.sc, m.I,
+                                                         m.J, m.KB, m.N, m.red_part);
+    m.launches++;
+}
+
+void launch_stats(Model& m, cudaStream_t st)
+{
+    stats_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.us.e, m.N, m.red_part);
+    m.launches++;
+}
+
+void launch_global_hypers(Model& m, cudaStream_t st)
+{
+    global_hypers_kernel<<<1, RED_THREADS, 0, st>>>(m.sc, m.red_part, m.red_blocks, m.N, m.cfg.priors, m.cfg.sample_mode, m.cfg.seed);
+    m.launches++;
+}
+
+static void dim_hypers_side(Model& m, Side& s, cudaStream_t st)
+{
+    const sbmf_priors& p = m.cfg.priors;
+    dim_hyper_partial_kernel<<<dim3(s.hyp_chunks, m.KB), 256, 0, st>>>(s.F, s.n, s.mu_k, s.hyp_part, s.hyp_chunks);
+    dim_hyper_final_kernel<<<m.KB, 32, 0, st>>>(s.hyp_part, s.hyp_chunks, s.n, m.K, s.sigma_k, s.mu_k, s.sigma_kf, s.mu_kf, m.sc, p.alpha[s.prior],
+                                                p.beta[s.prior], p.mu[s.prior], p.sigma[s.prior], m.cfg.sample_mode, m.cfg.seed, s.site_sigma_k,
+                                                s.site_mu_k);
+    m.launches += 2;
+}
+
+void launch_dim_hypers(Model& m, cudaStream_t st)
+{
+    dim_hypers_side(m, m.us, st);
+    dim_hypers_side(m, m.it, st);
+}
+
+void launch_bias_hypers(Model& m, cudaStream_t st)
+{
+    const sbmf_priors& p = m.cfg.priors;
+    for (Side* s : {&m.us, &m.it}) {
+        bias_hyper_kernel<<<(s->n + 255) / 256, 256, 0, st>>>(s->bias, s->mu_b, s->sigma_b, s->n, m.sc, p.alpha[s->prior_b], p.beta[s->prior_b],
+                                                              p.mu[s->prior_b], p.sigma[s->prior_b], m.cfg.sample_mode, m.cfg.seed,
+                                                              s->site_sigma_b, s->site_mu_b);
+        m.launches++;
+    }
+}
+
+template <int BIN>
+static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, int b1, int do_bias, cudaStream_t st)
+{
+    constexpr int RPL = kBins[BIN].rpl, WARPS = kBins[BIN].warps;
+    const uint32_t n = self.bin_count[BIN];
+    if (!n) return;
+    if (WARPS == 1) row_resident_kernel<RPL, WARPS><<<(n + 7) / 8, 256, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+    else row_resident_kernel<RPL, WARPS><<<n, WARPS * 32, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+    m.launches++;
+}
+
+// One half-sweep: bias then all factor blocks of every row of `self` ([T]:514-558 users / 563-606 items).
+void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift)
+{
+    PhaseArgs a;
+    a.ptr = self.ptr;
+    a.idx = self.idx;
+    a.e = self.e;
+    a.Fself = self.F;
+    a.Fother = other.F;
+    a.n_self = self.n;
+    a.n_other = other.n;
+    a.bias = self.bias;
+    a.mu_b = self.mu_b;
+    a.sigma_b = self.sigma_b;
+    a.sigma_kf = self.sigma_kf;
+    a.mu_kf = self.mu_kf;
+    a.sc = m.sc;
+    a.K = m.K;
+    a.seed = m.cfg.seed;
+    a.site_f = self.site_f;
+    a.site_b = self.site_b;
+    a.mode = m.cfg.sample_mode;
+    a.apply_shift = apply_shift ? 1 : 0;
+
+    const int KB = (int)m.KB;
+    const bool heavy = self.n_heavy > 0;
+    cudaStream_t sr = m.s_main, sh = m.s_aux;
+    if (heavy) {
+        cudaEventRecord(m.ev_fork, sr);
+        cudaStreamWaitEvent(sh, m.ev_fork, 0);
+    }
+    // resident rows: as many blocks per launch as keep the gathered factor blocks L2-resident
+    const size_t block_bytes = (size_t)other.n * 32;
+    int nb = (int)((size_t)(48u << 20) / (block_bytes ? block_bytes : 1));
+    if (nb < 1) nb = 1;
+    if (nb > KB) nb = KB;
+    for (int b0 = 0; b0 < KB; b0 += nb) {
+        const int b1 = (b0 + nb < KB) ? b0 + nb : KB;
+        const int do_bias = (b0 == 0) ? 1 : 0;
+        launch_bin<0>(m, a, self, b0, b1, do_bias, sr);
+        launch_bin<1>(m, a, self, b0, b1, do_bias, sr);
+        launch_bin<2>(m, a, self, b0, b1, do_bias, sr);
+        launch_bin<3>(m, a, self, b0, b1, do_bias, sr);
+        launch_bin<4>(m, a, self, b0, b1, do_bias, sr);
+        launch_bin<5>(m, a, self, b0, b1, do_bias, sr);
+        launch_bin<6>(m, a, self, b0, b1, do_bias, sr);
+    }
+    if (heavy) {
+        const uint32_t ns = self.n_slices, nh = self.n_heavy;
+        const uint32_t gs = (nh + 3) / 4;
+        float* hbias = self.hdelta + (size_t)nh * 8;
+        heavy_accumulate_kernel<0, 1><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, 0, 0);
+        heavy_solve_kernel<1><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
+        heavy_accumulate_kernel<1, 2><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, 0, 0);
+        heavy_solve_kernel<2><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
+        for (int b = 1; b < KB; ++b) {
+            heavy_accumulate_kernel<2, 2><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, b - 1, b);
+            heavy_solve_kernel<2><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, b);
+        }
+        heavy_accumulate_kernel<2, 0><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, KB - 1, 0);
+        m.launches += 2 * KB + 3;
+        cudaEventRecord(m.ev_join, sh);
+        cudaStreamWaitEvent(sr, m.ev_join, 0);
+    }
+}
+
+void launch_permute(Model& m, bool csr_to_csc, cudaStream_t st)
+{
+    const uint32_t g = grid_for(m.N, 256, m.sm_count * 16);
+    if (csr_to_csc) permute_gather_kernel<<<g, 256, 0, st>>>(m.us.e, m.perm, m.it.e, m.N);
+    else permute_scatter_kernel<<<g, 256, 0, st>>>(m.it.e, m.perm, m.us.e, m.N);
+    m.launches++;
+}
+
+void launch_eval(Model& m, cudaStream_t st)
+{
+    eval_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.t_user, m.t_item, m.t_r, m.t_sum, m.us.F, m.it.F, m.us.bias, m.it.bias, m.sc, m.I, m.J, m.KB,
+                                                      m.Nt, m.cfg.burn_in, (float)m.cfg.clamp_lo, (float)m.cfg.clamp_hi, m.red_part);
+    eval_final_kernel<<<1, RED_THREADS, 0, st>>>(m.sc, m.red_part, m.red_blocks, m.Nt, m.rmse_hist, m.hist_cap);
+    m.launches += 2;
+}
+
+}  // namespace sbmf

@@ -1,0 +1,137 @@
+// model.h -- host-side model of one SBMF replica and the launch wrappers of its kernels.
+// Internal to libsbmf_cuda.so; the public boundary is include/sbmf_cuda.h.
+//
+// Storage (replaces the jagged R / R_t of gibbs_sbpmf2.cpp "[T]":156-221):
+//   user side: CSR  ptr[I+1] (int64), idx[N] = item of each slot, e[N] = residual in CSR slot order
+//   item side: CSC  ptr[J+1],         idx[N] = user of each slot, e[N] = residual in CSC slot order
+//   perm[N] = CSR slot of each CSC slot (replaces [T]'s `.id` back-pointers)
+// Factors are stored "K8-blocked": F[b][row][8] with b = k/8 -- the 8 values of one row in one block are one
+// 32-byte sector, fetched by one LDG.256, which is the unit the row kernels gather.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sbmf_cuda.h"
+
+namespace sbmf {
+
+constexpr int KBLK = 8;             // latent dimensions per factor block (one 32-byte sector per row)
+constexpr int NACC = 48;            // g[8] + upper-triangular G[36] = 44 accumulators, padded to 48
+constexpr int NBINS = 7;            // resident-row bins, see kBin* below
+constexpr int RESIDENT_MAX = 2048;  // longer rows go through the streaming ("heavy") pipeline
+constexpr int SLICE_LEN = 4096;     // ratings per heavy-row slice (one CTA)
+constexpr int SLICE_THREADS = 256;
+
+// resident bins: a row of c ratings is handled by WARPS warps holding RPL ratings per lane in registers
+struct BinShape { int rpl, warps, cap; };
+constexpr BinShape kBins[NBINS] = {{1, 1, 32}, {2, 1, 64}, {4, 1, 128}, {8, 1, 256}, {4, 4, 512}, {8, 4, 1024}, {8, 8, 2048}};
+
+// Device-resident scalars of the sweep ([T]:315-318 plus the statistics of [T]:342-359).
+struct Scalars {
+    double b_0, alpha, mu_b_0, sigma_b_0;
+    double sum_e, sum_e2;
+    double rmse_mean, rmse_sweep;
+    float alpha_f, b_0_f;
+    float shift_f;       // b0_old - b0_new of [T]:407-410, folded into the user phase's first residual touch
+    uint32_t sweep;      // 0-based sweep counter = Philox counter word 3; bumped by the eval kernel
+};
+
+struct Slice {
+    int64_t start;       // first slot of the slice in this side's order
+    uint32_t len;
+    uint32_t hrow;       // index into Side::heavy_rows
+};
+
+// One side of the model: users with the CSR layout, or items with the CSC layout.
+struct Side {
+    uint32_t n = 0;                   // rows on this side (I or J)
+    int64_t* ptr = nullptr;           // [n+1]
+    uint32_t* idx = nullptr;          // [N] opposite-side id of each slot
+    float* e = nullptr;               // [N] residual e_ij in this side's slot order
+    float* F = nullptr;               // [KB][n][8]  K8-blocked factors (own rows; gather target of the other side)
+    float *bias = nullptr, *mu_b = nullptr, *sigma_b = nullptr;   // [n]
+    double *sigma_k = nullptr, *mu_k = nullptr;                   // [KP] hyper-parameters (fp64 masters)
+    float *sigma_kf = nullptr, *mu_kf = nullptr;                  // [KP] fp32 mirrors read by the row kernels
+    double* hyp_part = nullptr;       // [KB][hyp_chunks][16] partial (sum, sumsq) of the per-dimension hyper step
+    uint32_t hyp_chunks = 0;
+    // work lists
+    uint32_t* bin_rows[NBINS] = {};
+    uint32_t bin_count[NBINS] = {};
+    uint32_t n_heavy = 0, n_slices = 0;
+    uint32_t* heavy_rows = nullptr;       // [n_heavy] row id
+    uint32_t* heavy_slice_ptr = nullptr;  // [n_heavy+1] slice range of each heavy row
+    Slice* slices = nullptr;              // [n_slices]
+    float* hpart = nullptr;               // [n_slices][NACC]
+    float* hdelta = nullptr;              // [2][n_heavy][8] pending factor deltas (double-buffered by block parity)
+    uint64_t nnz_resident = 0, nnz_heavy = 0;
+    uint32_t site_f = 0, site_b = 0;      // Philox streams of the factor / bias draws
+    uint32_t site_sigma_k = 0, site_mu_k = 0, site_sigma_b = 0, site_mu_b = 0;
+    int prior = 0;                        // index into sbmf_priors of the factor hyper-prior (2 = users, 1 = items)
+    int prior_b = 0;                      // ... of the bias hyper-prior (4 = users, 5 = items)
+};
+
+struct Model {
+    sbmf_config cfg{};
+    int device = 0;
+    int sm_count = 148;
+    uint32_t K = 0, KB = 0, KP = 0;
+    uint64_t N = 0, Nt = 0;
+    uint32_t I = 0, J = 0;
+    bool have_train = false, have_test = false, have_factors = false;
+    uint32_t sweeps_done = 0;
+
+    Side us, it;                      // user side (CSR), item side (CSC)
+    uint32_t* csr_urow = nullptr;     // [N] user of each CSR slot (COO row index for the flat rebuild)
+    float* csr_r = nullptr;           // [N] rating per CSR slot
+    uint32_t* csr_id = nullptr;       // [N] rating (file) index of each CSR slot
+    uint32_t* csc_id = nullptr;       // [N] rating index of each CSC slot
+    uint32_t* perm = nullptr;         // [N] CSR slot of each CSC slot
+    bool e_in_csc = false;            // where the freshest residual lives
+    // test set
+    uint32_t *t_user = nullptr, *t_item = nullptr;
+    float* t_r = nullptr;
+    double* t_sum = nullptr;          // running prediction sum, [T]:145, 629
+    Scalars* sc = nullptr;
+    double* red_part = nullptr;       // [red_blocks][2] per-block partial sums of the reductions
+    uint32_t red_blocks = 0;
+    double* rmse_hist = nullptr;      // [hist_cap][2]
+    uint32_t hist_cap = 0;
+
+    cudaStream_t s_main = nullptr, s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_t[8] = {};
+    bool timing_enabled = true;
+    sbmf_timing timing{};
+    uint64_t launches = 0;
+    std::string err;
+};
+
+// ---- storage.cu
+int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* item, const float* rating,
+                  uint32_t num_users, uint32_t num_items);
+int build_test(Model& m, uint64_t nt, const uint32_t* user, const uint32_t* item, const float* rating);
+void free_storage(Model& m);
+void free_test(Model& m);
+
+// ---- kernels.cu: launch wrappers (all asynchronous on the given stream)
+void launch_init_factors(Model& m, Side& s, uint32_t site, cudaStream_t st);
+// host layout -> K8-blocked.  dim_major: src is [K][n] (V of [T]:234-237), else [n][K] (U of [T]:229-232)
+void launch_load_factors(Model& m, Side& s, const float* d_src, bool dim_major, cudaStream_t st);
+void launch_export_factors(Model& m, const Side& s, float* d_out, bool dim_major, cudaStream_t st);
+void launch_rebuild(Model& m, cudaStream_t st);          // [T]:342-359 into the CSR-order residual + partial stats
+void launch_stats(Model& m, cudaStream_t st);            // partial stats of the existing CSR-order residual
+void launch_global_hypers(Model& m, cudaStream_t st);    // [T]:366-410 (final reduce of the stats + 4 scalar draws)
+void launch_dim_hypers(Model& m, cudaStream_t st);       // [T]:415-467
+void launch_bias_hypers(Model& m, cudaStream_t st);      // [T]:469-511
+void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift);   // [T]:514-558 / 563-606
+void launch_permute(Model& m, bool csr_to_csc, cudaStream_t st);
+void launch_eval(Model& m, cudaStream_t st);             // [T]:610-636
+
+}  // namespace sbmf
+
+struct sbmf_handle {
+    sbmf::Model m;
+};

@@ -1,0 +1,284 @@
+// storage.cu -- rating storage on the device: COO in file order -> CSR (by user) + CSC (by item) + the
+// CSC-slot -> CSR-slot permutation + residual arrays + row work lists.
+//
+// Replaces the jagged R / R_t build of gibbs_sbpmf2.cpp ("[T]"):156-221.  [T] appends every rating, in FILE
+// order, to its user's row and to its item's row ([T]:209-214), so both layouts are stable w.r.t. file order;
+// here that is two stable LSD radix sorts (cub::DeviceRadixSort) of the rating index by user and by item.
+// [T]'s `.id` back-pointer (rating index of each slot) becomes csr_id / csc_id, and the pair of them the
+// permutation perm[csc slot] = csr slot that moves the residual between the two orders.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cub/cub.cuh>
+#include <vector>
+
+#include "model.h"
+
+namespace sbmf {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            m.err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return (e_ == cudaErrorMemoryAllocation) ? SBMF_ERR_NOMEM : SBMF_ERR_CUDA;             \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t n)
+{
+    return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+}
+
+__global__ void iota_kernel(uint32_t* v, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] = (uint32_t)i;
+}
+
+__global__ void max_id_kernel(const uint32_t* a, const uint32_t* b, uint64_t n, uint32_t* out)
+{
+    uint32_t ma = 0, mb = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        ma = max(ma, a[i]);
+        mb = max(mb, b[i]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        ma = max(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+        mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, ma);
+        atomicMax(out + 1, mb);
+    }
+}
+
+// ptr[r] = first slot whose (sorted) key is >= r
+__global__ void row_ptr_kernel(const uint32_t* sorted_keys, uint64_t n, uint32_t nrows, int64_t* ptr)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > nrows) return;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < r) lo = mid + 1;
+        else hi = mid;
+    }
+    ptr[r] = (int64_t)lo;
+}
+
+__global__ void gather_u32_kernel(const uint32_t* src, const uint32_t* id, uint32_t* dst, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[id[i]];
+}
+__global__ void gather_f32_kernel(const float* src, const uint32_t* id, float* dst, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[id[i]];
+}
+__global__ void invert_kernel(const uint32_t* id, uint32_t* inv, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) inv[id[i]] = (uint32_t)i;
+}
+
+static int bits_for(uint32_t n)
+{
+    int b = 1;
+    while (b < 32 && (1ull << b) < (uint64_t)n) ++b;
+    return b;
+}
+
+static void free_side(Side& s)
+{
+    cudaFree(s.ptr); cudaFree(s.idx); cudaFree(s.e); cudaFree(s.F);
+    cudaFree(s.bias); cudaFree(s.mu_b); cudaFree(s.sigma_b);
+    cudaFree(s.sigma_k); cudaFree(s.mu_k); cudaFree(s.sigma_kf); cudaFree(s.mu_kf); cudaFree(s.hyp_part);
+    for (int b = 0; b < NBINS; ++b) cudaFree(s.bin_rows[b]);
+    cudaFree(s.heavy_rows); cudaFree(s.heavy_slice_ptr); cudaFree(s.slices); cudaFree(s.hpart); cudaFree(s.hdelta);
+    const uint32_t sf = s.site_f, sb = s.site_b, a = s.site_sigma_k, b_ = s.site_mu_k, c = s.site_sigma_b, d = s.site_mu_b;
+    const int pr = s.prior, prb = s.prior_b;
+    s = Side();
+    s.site_f = sf; s.site_b = sb; s.site_sigma_k = a; s.site_mu_k = b_; s.site_sigma_b = c; s.site_mu_b = d;
+    s.prior = pr; s.prior_b = prb;
+}
+
+void free_storage(Model& m)
+{
+    free_side(m.us);
+    free_side(m.it);
+    cudaFree(m.csr_urow); cudaFree(m.csr_r); cudaFree(m.csr_id); cudaFree(m.csc_id); cudaFree(m.perm);
+    m.csr_urow = nullptr; m.csr_r = nullptr; m.csr_id = nullptr; m.csc_id = nullptr; m.perm = nullptr;
+    cudaFree(m.red_part); m.red_part = nullptr;
+    m.have_train = false;
+    m.have_factors = false;
+    m.N = 0;
+}
+
+void free_test(Model& m)
+{
+    cudaFree(m.t_user); cudaFree(m.t_item); cudaFree(m.t_r); cudaFree(m.t_sum);
+    m.t_user = m.t_item = nullptr; m.t_r = nullptr; m.t_sum = nullptr;
+    m.have_test = false;
+    m.Nt = 0;
+}
+
+// Row work lists: resident bins by row length, heavy rows cut into slices.  Built on the host from the row
+// pointer (one-time; the order of rows inside a list does not influence any result).
+static int build_worklists(Model& m, Side& s)
+{
+    std::vector<int64_t> ptr((size_t)s.n + 1);
+    CK(cudaMemcpy(ptr.data(), s.ptr, ptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> bins[NBINS], heavy, hsp;
+    std::vector<Slice> slices;
+    s.nnz_resident = s.nnz_heavy = 0;
+    hsp.push_back(0);
+    for (uint32_t r = 0; r < s.n; ++r) {
+        const int64_t c = ptr[r + 1] - ptr[r];
+        if (c <= RESIDENT_MAX) {
+            int b = 0;
+            while (c > kBins[b].cap) ++b;
+            bins[b].push_back(r);
+            s.nnz_resident += (uint64_t)c;
+        } else {
+            const uint32_t h = (uint32_t)heavy.size();
+            heavy.push_back(r);
+            // equal-length slices (the last one is not a short tail)
+            const int64_t ns = (c + SLICE_LEN - 1) / SLICE_LEN;
+            const int64_t len = (c + ns - 1) / ns;
+            for (int64_t o = 0; o < c; o += len) slices.push_back(Slice{ptr[r] + o, (uint32_t)std::min<int64_t>(len, c - o), h});
+            hsp.push_back((uint32_t)slices.size());
+            s.nnz_heavy += (uint64_t)c;
+        }
+    }
+    for (int b = 0; b < NBINS; ++b) {
+        s.bin_count[b] = (uint32_t)bins[b].size();
+        CK(dmalloc(&s.bin_rows[b], bins[b].size()));
+        if (!bins[b].empty()) CK(cudaMemcpy(s.bin_rows[b], bins[b].data(), bins[b].size() * 4, cudaMemcpyHostToDevice));
+    }
+    s.n_heavy = (uint32_t)heavy.size();
+    s.n_slices = (uint32_t)slices.size();
+    CK(dmalloc(&s.heavy_rows, heavy.size()));
+    CK(dmalloc(&s.heavy_slice_ptr, hsp.size()));
+    CK(dmalloc(&s.slices, slices.size()));
+    CK(dmalloc(&s.hpart, slices.size() * NACC));
+    CK(dmalloc(&s.hdelta, heavy.size() * 9));   // [n_heavy][8] block deltas + [n_heavy] bias deltas
+    if (!heavy.empty()) {
+        CK(cudaMemcpy(s.heavy_rows, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.slices, slices.data(), slices.size() * sizeof(Slice), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemcpy(s.heavy_slice_ptr, hsp.data(), hsp.size() * 4, cudaMemcpyHostToDevice));
+    return SBMF_OK;
+}
+
+static int alloc_side_state(Model& m, Side& s)
+{
+    CK(dmalloc(&s.F, (size_t)m.KB * s.n * 8));
+    CK(dmalloc(&s.bias, s.n)); CK(dmalloc(&s.mu_b, s.n)); CK(dmalloc(&s.sigma_b, s.n));
+    CK(dmalloc(&s.sigma_k, m.KP)); CK(dmalloc(&s.mu_k, m.KP)); CK(dmalloc(&s.sigma_kf, m.KP)); CK(dmalloc(&s.mu_kf, m.KP));
+    s.hyp_chunks = (s.n + 16383) / 16384;
+    if (s.hyp_chunks < 1) s.hyp_chunks = 1;
+    CK(dmalloc(&s.hyp_part, (size_t)m.KB * s.hyp_chunks * 16));
+    return SBMF_OK;
+}
+
+int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* item, const float* rating, uint32_t num_users,
+                  uint32_t num_items)
+{
+    free_storage(m);
+    if (n >= (1ull << 31)) {
+        m.err = "set_train: more than 2^31-1 ratings per GPU are not supported (shard across GPUs)";
+        return SBMF_ERR_UNSUPPORTED;
+    }
+    m.N = n; m.I = num_users; m.J = num_items;
+    m.us.n = num_users; m.it.n = num_items;
+    cudaStream_t st = m.s_main;
+    const int T = 256;
+    const uint32_t G = (uint32_t)std::min<uint64_t>((n + T - 1) / T + 1, (uint64_t)m.sm_count * 16);
+
+    uint32_t *d_user = nullptr, *d_item = nullptr, *d_iota = nullptr, *d_keys = nullptr, *d_inv = nullptr, *d_max = nullptr;
+    float* d_rating = nullptr;
+    void* d_tmp = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_user); cudaFree(d_item); cudaFree(d_iota); cudaFree(d_keys); cudaFree(d_inv); cudaFree(d_max); cudaFree(d_rating); cudaFree(d_tmp);
+    };
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            m.err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            cleanup();                                                                             \
+            return (e_ == cudaErrorMemoryAllocation) ? SBMF_ERR_NOMEM : SBMF_ERR_CUDA;             \
+        }                                                                                          \
+    } while (0)
+
+    CKC(dmalloc(&d_user, n)); CKC(dmalloc(&d_item, n)); CKC(dmalloc(&d_rating, n)); CKC(dmalloc(&d_iota, n)); CKC(dmalloc(&d_keys, n));
+    CKC(dmalloc(&d_inv, n)); CKC(dmalloc(&d_max, 2));
+    CKC(cudaMemcpyAsync(d_user, user, n * 4, cudaMemcpyHostToDevice, st));
+    CKC(cudaMemcpyAsync(d_item, item, n * 4, cudaMemcpyHostToDevice, st));
+    CKC(cudaMemcpyAsync(d_rating, rating, n * 4, cudaMemcpyHostToDevice, st));
+    CKC(cudaMemsetAsync(d_max, 0, 8, st));
+    if (n) max_id_kernel<<<G, T, 0, st>>>(d_user, d_item, n, d_max);
+    uint32_t h_max[2] = {0, 0};
+    CKC(cudaMemcpyAsync(h_max, d_max, 8, cudaMemcpyDeviceToHost, st));
+    CKC(cudaStreamSynchronize(st));
+    if (n && (h_max[0] >= num_users || h_max[1] >= num_items)) {
+        m.err = "set_train: user/item id out of range (max user " + std::to_string(h_max[0]) + ", max item " + std::to_string(h_max[1]) + ")";
+        cleanup();
+        return SBMF_ERR_INVALID;
+    }
+
+    CKC(dmalloc(&m.us.ptr, (size_t)num_users + 1)); CKC(dmalloc(&m.it.ptr, (size_t)num_items + 1));
+    CKC(dmalloc(&m.us.idx, n)); CKC(dmalloc(&m.it.idx, n)); CKC(dmalloc(&m.us.e, n)); CKC(dmalloc(&m.it.e, n));
+    CKC(dmalloc(&m.csr_urow, n)); CKC(dmalloc(&m.csr_r, n)); CKC(dmalloc(&m.csr_id, n)); CKC(dmalloc(&m.csc_id, n)); CKC(dmalloc(&m.perm, n));
+
+    size_t tmp_bytes = 0;
+    CKC(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_user, d_keys, d_iota, m.csr_id, (int)n, 0, 32, st));
+    CKC(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+    iota_kernel<<<G, T, 0, st>>>(d_iota, n);
+    // CSR: stable sort of the rating index by user
+    CKC(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_user, m.csr_urow, d_iota, m.csr_id, (int)n, 0, bits_for(num_users), st));
+    row_ptr_kernel<<<(num_users + 1 + T - 1) / T, T, 0, st>>>(m.csr_urow, n, num_users, m.us.ptr);
+    gather_u32_kernel<<<G, T, 0, st>>>(d_item, m.csr_id, m.us.idx, n);
+    gather_f32_kernel<<<G, T, 0, st>>>(d_rating, m.csr_id, m.csr_r, n);
+    invert_kernel<<<G, T, 0, st>>>(m.csr_id, d_inv, n);
+    // CSC: stable sort of the rating index by item
+    CKC(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_item, d_keys, d_iota, m.csc_id, (int)n, 0, bits_for(num_items), st));
+    row_ptr_kernel<<<(num_items + 1 + T - 1) / T, T, 0, st>>>(d_keys, n, num_items, m.it.ptr);
+    gather_u32_kernel<<<G, T, 0, st>>>(d_user, m.csc_id, m.it.idx, n);
+    gather_u32_kernel<<<G, T, 0, st>>>(d_inv, m.csc_id, m.perm, n);
+    CKC(cudaMemsetAsync(m.us.e, 0, (n ? n : 1) * 4, st));
+    CKC(cudaMemsetAsync(m.it.e, 0, (n ? n : 1) * 4, st));
+    CKC(cudaGetLastError());
+    CKC(cudaStreamSynchronize(st));
+    cleanup();
+#undef CKC
+
+    int rc;
+    if ((rc = build_worklists(m, m.us)) != SBMF_OK) return rc;
+    if ((rc = build_worklists(m, m.it)) != SBMF_OK) return rc;
+    if ((rc = alloc_side_state(m, m.us)) != SBMF_OK) return rc;
+    if ((rc = alloc_side_state(m, m.it)) != SBMF_OK) return rc;
+    m.red_blocks = (uint32_t)m.sm_count * 8;
+    CK(dmalloc(&m.red_part, (size_t)m.red_blocks * 2));
+    m.have_train = true;
+    m.e_in_csc = false;
+    return SBMF_OK;
+}
+
+int build_test(Model& m, uint64_t nt, const uint32_t* user, const uint32_t* item, const float* rating)
+{
+    free_test(m);
+    m.Nt = nt;
+    CK(dmalloc(&m.t_user, nt)); CK(dmalloc(&m.t_item, nt)); CK(dmalloc(&m.t_r, nt)); CK(dmalloc(&m.t_sum, nt));
+    if (nt) {
+        CK(cudaMemcpyAsync(m.t_user, user, nt * 4, cudaMemcpyHostToDevice, m.s_main));
+        CK(cudaMemcpyAsync(m.t_item, item, nt * 4, cudaMemcpyHostToDevice, m.s_main));
+        CK(cudaMemcpyAsync(m.t_r, rating, nt * 4, cudaMemcpyHostToDevice, m.s_main));
+    }
+    CK(cudaMemsetAsync(m.t_sum, 0, (nt ? nt : 1) * 8, m.s_main));
+    CK(cudaStreamSynchronize(m.s_main));
+    m.have_test = true;
+    return SBMF_OK;
+}
+
+}  // namespace sbmf

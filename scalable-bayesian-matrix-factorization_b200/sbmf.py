@@ -1,0 +1,243 @@
+"""sbmf.py -- ctypes binding of libsbmf_cuda.so (include/sbmf_cuda.h) for tests and bench.py.
+
+This is a thin mirror of the C ABI, not a second implementation: every method is one sbmf_cuda_* call on
+host (numpy) buffers.  There is no CPU path here -- if the shared library is missing or no B200 is visible,
+loading / SbmfModel() raises.  The product host program is the C++ CLI (csrc/main.cpp -> bin/sbmf), which
+links the same library.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libsbmf_cuda.so")
+
+SAMPLE_REF, SAMPLE_SQRT, SAMPLE_ZERO = 0, 1, 2
+
+
+class Priors(C.Structure):
+    _fields_ = [("alpha", C.c_double * 6), ("beta", C.c_double * 6), ("mu", C.c_double * 6), ("sigma", C.c_double * 6),
+                ("alpha_dash", C.c_double), ("beta_dash", C.c_double)]
+
+
+class Config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("K", C.c_uint32), ("device", C.c_int32), ("sample_mode", C.c_int32),
+                ("hyper_mode", C.c_int32), ("rebuild_every", C.c_uint32), ("burn_in", C.c_uint32), ("reserved0", C.c_uint32),
+                ("seed", C.c_uint64), ("init_stdev", C.c_double), ("clamp_lo", C.c_double), ("clamp_hi", C.c_double),
+                ("priors", Priors), ("rank", C.c_int32), ("world_size", C.c_int32), ("nccl_id", C.c_uint8 * 128)]
+
+
+class State(C.Structure):
+    _fields_ = [("U", C.c_void_p), ("V", C.c_void_p), ("b_i", C.c_void_p), ("b_j", C.c_void_p),
+                ("mu_b_i", C.c_void_p), ("sigma_b_i", C.c_void_p), ("mu_b_j", C.c_void_p), ("sigma_b_j", C.c_void_p),
+                ("sigma_u", C.c_void_p), ("mu_u", C.c_void_p), ("sigma_v", C.c_void_p), ("mu_v", C.c_void_p),
+                ("E", C.c_void_p),
+                ("b_0", C.c_double), ("alpha", C.c_double), ("mu_b_0", C.c_double), ("sigma_b_0", C.c_double),
+                ("sum_e", C.c_double), ("sum_e2", C.c_double), ("sweeps_done", C.c_uint32), ("reserved0", C.c_uint32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("ms_rebuild", C.c_double), ("ms_hypers", C.c_double), ("ms_user_phase", C.c_double), ("ms_exchange", C.c_double),
+                ("ms_item_phase", C.c_double), ("ms_eval", C.c_double), ("ms_total", C.c_double), ("sweeps", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("nnz_light_user", C.c_uint64), ("nnz_heavy_user", C.c_uint64),
+                ("nnz_light_item", C.c_uint64), ("nnz_heavy_item", C.c_uint64)]
+
+
+class SynthSpec(C.Structure):
+    _fields_ = [("num_users", C.c_uint32), ("num_items", C.c_uint32), ("n_ratings", C.c_uint64), ("s_user", C.c_double),
+                ("s_item", C.c_double), ("test_frac", C.c_double), ("seed", C.c_uint64), ("device", C.c_int32),
+                ("reserved0", C.c_int32)]
+
+
+class SbmfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sbmf_cuda error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libsbmf_cuda.so; raises OSError if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    lib = C.CDLL(path or LIB_PATH)
+    P = C.POINTER
+    lib.sbmf_cuda_abi_version.restype = C.c_int
+    lib.sbmf_cuda_config_default.argtypes = [P(Config)]
+    lib.sbmf_cuda_create.argtypes = [P(Config), P(C.c_void_p)]
+    lib.sbmf_cuda_destroy.argtypes = [C.c_void_p]
+    lib.sbmf_cuda_last_error.argtypes = [C.c_void_p]
+    lib.sbmf_cuda_last_error.restype = C.c_char_p
+    lib.sbmf_cuda_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.sbmf_cuda_set_train.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.sbmf_cuda_set_test.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sbmf_cuda_get_layout.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    lib.sbmf_cuda_init_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sbmf_cuda_get_state.argtypes = [C.c_void_p, P(State)]
+    lib.sbmf_cuda_sweep.argtypes = [C.c_void_p, C.c_uint32]
+    lib.sbmf_cuda_eval.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double)]
+    lib.sbmf_cuda_get_rmse_history.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.sbmf_cuda_get_pred.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sbmf_cuda_get_timing.argtypes = [C.c_void_p, P(Timing)]
+    lib.sbmf_cuda_reset_timing.argtypes = [C.c_void_p]
+    lib.sbmf_cuda_synchronize.argtypes = [C.c_void_p]
+    lib.sbmf_cuda_set_timing_enabled.argtypes = [C.c_void_p, C.c_int]
+    lib.sbmf_cuda_synth_generate.argtypes = [P(SynthSpec), P(C.c_uint64), P(C.c_uint64)] + [C.c_void_p] * 6
+    lib.sbmf_cuda_synth_last_error.restype = C.c_char_p
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def default_config(**kw):
+    cfg = Config()
+    load_library().sbmf_cuda_config_default(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class SbmfModel:
+    """One handle of the C ABI.  Method names follow the sbmf_cuda_* entry points."""
+
+    def __init__(self, cfg=None, **kw):
+        self.lib = load_library()
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        self.h = C.c_void_p()
+        rc = self.lib.sbmf_cuda_create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            raise SbmfError(rc, self.lib.sbmf_cuda_last_error(None).decode())
+        self.K = self.cfg.K
+        self.N = self.Nt = self.I = self.J = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SbmfError(rc, self.lib.sbmf_cuda_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.sbmf_cuda_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_train(self, user, item, rating, num_users, num_items):
+        user, item, rating = _u32(user), _u32(item), _f32(rating)
+        assert user.shape == item.shape == rating.shape
+        self._ck(self.lib.sbmf_cuda_set_train(self.h, user.size, _ptr(user), _ptr(item), _ptr(rating), num_users, num_items))
+        self.N, self.I, self.J = user.size, num_users, num_items
+
+    def set_test(self, user, item, rating):
+        user, item, rating = _u32(user), _u32(item), _f32(rating)
+        self._ck(self.lib.sbmf_cuda_set_test(self.h, user.size, _ptr(user), _ptr(item), _ptr(rating)))
+        self.Nt = user.size
+
+    def get_layout(self):
+        N, I, J = self.N, self.I, self.J
+        out = {"row_ptr": np.empty(I + 1, np.int64), "col": np.empty(N, np.uint32), "csr_id": np.empty(N, np.uint64),
+               "col_ptr": np.empty(J + 1, np.int64), "row": np.empty(N, np.uint32), "csc_id": np.empty(N, np.uint64),
+               "perm": np.empty(N, np.uint64)}
+        self._ck(self.lib.sbmf_cuda_get_layout(self.h, *[_ptr(out[k]) for k in ("row_ptr", "col", "csr_id", "col_ptr", "row", "csc_id", "perm")]))
+        return out
+
+    def init_factors(self, U0=None, V0=None):
+        u = _f32(U0) if U0 is not None else None
+        v = _f32(V0) if V0 is not None else None
+        if u is not None:
+            assert u.shape == (self.I, self.K)
+        if v is not None:
+            assert v.shape == (self.K, self.J)
+        self._ck(self.lib.sbmf_cuda_init_factors(self.h, _ptr(u), _ptr(v)))
+
+    def sweep(self, n=1):
+        self._ck(self.lib.sbmf_cuda_sweep(self.h, n))
+
+    def eval(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.sbmf_cuda_eval(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def rmse_history(self, first, count):
+        a, b = np.empty(count, np.float64), np.empty(count, np.float64)
+        self._ck(self.lib.sbmf_cuda_get_rmse_history(self.h, first, count, _ptr(a), _ptr(b)))
+        return a, b
+
+    def get_pred(self):
+        p = np.empty(self.Nt, np.float32)
+        self._ck(self.lib.sbmf_cuda_get_pred(self.h, _ptr(p)))
+        return p
+
+    def get_state(self, with_E=True):
+        I, J, K, N = self.I, self.J, self.K, self.N
+        arr = {"U": np.empty((I, K), np.float32), "V": np.empty((K, J), np.float32), "b_i": np.empty(I, np.float32),
+               "b_j": np.empty(J, np.float32), "mu_b_i": np.empty(I, np.float32), "sigma_b_i": np.empty(I, np.float32),
+               "mu_b_j": np.empty(J, np.float32), "sigma_b_j": np.empty(J, np.float32), "sigma_u": np.empty(K, np.float64),
+               "mu_u": np.empty(K, np.float64), "sigma_v": np.empty(K, np.float64), "mu_v": np.empty(K, np.float64)}
+        if with_E:
+            arr["E"] = np.empty(N, np.float32)
+        st = State()
+        for k, v in arr.items():
+            setattr(st, k, v.ctypes.data)
+        self._ck(self.lib.sbmf_cuda_get_state(self.h, C.byref(st)))
+        for k in ("b_0", "alpha", "mu_b_0", "sigma_b_0", "sum_e", "sum_e2", "sweeps_done"):
+            arr[k] = getattr(st, k)
+        return arr
+
+    def timing(self):
+        t = Timing()
+        self._ck(self.lib.sbmf_cuda_get_timing(self.h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    def reset_timing(self):
+        self._ck(self.lib.sbmf_cuda_reset_timing(self.h))
+
+    def set_timing_enabled(self, on):
+        self._ck(self.lib.sbmf_cuda_set_timing_enabled(self.h, 1 if on else 0))
+
+    def synchronize(self):
+        self._ck(self.lib.sbmf_cuda_synchronize(self.h))
+
+
+def synth_generate(num_users, num_items, n_ratings, s_user=0.8, s_item=1.0, test_frac=0.1, seed=20151001, device=0):
+    """Device-side synthetic rating matrix (csrc/synth.cu).  Returns dict of host arrays."""
+    lib = load_library()
+    spec = SynthSpec(num_users, num_items, n_ratings, s_user, s_item, test_frac, seed, device, 0)
+    ntr, nte = C.c_uint64(), C.c_uint64()
+    rc = lib.sbmf_cuda_synth_generate(C.byref(spec), C.byref(ntr), C.byref(nte), None, None, None, None, None, None)
+    if rc != 0:
+        raise SbmfError(rc, lib.sbmf_cuda_synth_last_error().decode())
+    out = {"train_user": np.empty(ntr.value, np.uint32), "train_item": np.empty(ntr.value, np.uint32),
+           "train_rating": np.empty(ntr.value, np.float32), "test_user": np.empty(nte.value, np.uint32),
+           "test_item": np.empty(nte.value, np.uint32), "test_rating": np.empty(nte.value, np.float32)}
+    rc = lib.sbmf_cuda_synth_generate(C.byref(spec), C.byref(ntr), C.byref(nte), *[_ptr(out[k]) for k in
+                                      ("train_user", "train_item", "train_rating", "test_user", "test_item", "test_rating")])
+    if rc != 0:
+        raise SbmfError(rc, lib.sbmf_cuda_synth_last_error().decode())
+    out["num_users"], out["num_items"] = num_users, num_items
+    return out
+
+
+def read_triples(path):
+    """`user SEP item SEP rating` triples, 0-based ids ([T]:35-73 semantics for well-formed files)."""
+    a = np.loadtxt(path, dtype=np.float64, ndmin=2)
+    return a[:, 0].astype(np.uint32), a[:, 1].astype(np.uint32), a[:, 2].astype(np.float32)
