@@ -105,6 +105,11 @@ typedef struct sbmf_timing {
     uint64_t sweeps;
     uint64_t kernel_launches;    /* kernels of this library launched by those sweeps */
     uint64_t nnz_light_user, nnz_heavy_user, nnz_light_item, nnz_heavy_item;   /* rating split by kernel path */
+    /* the dominant kernel, timed per launch with CUDA events on its own stream (only while detail timing is on):
+       the item-phase streaming block step heavy_accumulate_kernel<2,2> (kernels.cu) */
+    double ms_top_kernel;        /* sum of its launch durations */
+    uint64_t top_kernel_launches;
+    uint64_t top_kernel_ratings; /* ratings one launch streams (each for 8 latent dimensions) */
 } sbmf_timing;
 
 /* ---- life cycle ------------------------------------------------------------------------------------ */
@@ -160,6 +165,13 @@ int sbmf_cuda_synchronize(sbmf_handle* h);
 /* Per-phase timing makes every sweep wait for its own CUDA events (one host/device round trip per sweep).
    enabled = 0 turns that off: sbmf_cuda_sweep(h, n) then only enqueues work.  Default: enabled. */
 int sbmf_cuda_set_timing_enabled(sbmf_handle* h, int enabled);
+/* enabled = 2 additionally brackets every launch of the dominant kernel with events (sbmf_timing.ms_top_kernel). */
+/* Device time of the last sbmf_cuda_sweep call (all its sweeps), from two CUDA events on the library's main
+   stream; waits for that call to finish. */
+int sbmf_cuda_last_sweep_call_ms(sbmf_handle* h, double* ms);
+/* Pinned host buffers for callers that want full-speed host<->device copies in set_train / set_test / get_*. */
+int sbmf_cuda_host_alloc(void** ptr, size_t bytes);
+int sbmf_cuda_host_free(void* ptr);
 
 /* ---- synthetic workloads (bench / tests): MovieLens/Netflix-shaped Zipf rating matrices, generated on
    the device.  Distinct (user,item) pairs with Zipf(s_user) x Zipf(s_item) marginals over

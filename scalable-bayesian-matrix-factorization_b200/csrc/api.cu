@@ -132,6 +132,7 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
     ok = ok && cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&m.ev_join, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&m.ev_t[i]) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreate(&m.ev_call[i]) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&m.sc, sizeof(Scalars)) == cudaSuccess;
     ok = ok && cudaMemset(m.sc, 0, sizeof(Scalars)) == cudaSuccess;
     m.hist_cap = 4096;
@@ -158,6 +159,9 @@ int sbmf_cuda_destroy(sbmf_handle* h)
     cudaFree(m.rmse_hist);
     for (int i = 0; i < 8; ++i)
         if (m.ev_t[i]) cudaEventDestroy(m.ev_t[i]);
+    for (int i = 0; i < 2; ++i)
+        if (m.ev_call[i]) cudaEventDestroy(m.ev_call[i]);
+    for (cudaEvent_t ev : m.ev_top) cudaEventDestroy(ev);
     if (m.ev_fork) cudaEventDestroy(m.ev_fork);
     if (m.ev_join) cudaEventDestroy(m.ev_join);
     if (m.s_main) cudaStreamDestroy(m.s_main);
@@ -333,6 +337,16 @@ static int one_sweep(Model& m)
         cudaEventElapsedTime(&tot, m.ev_t[0], m.ev_t[6]);
         m.timing.ms_total += tot;
         m.timing.sweeps++;
+        if (m.timing_detail && m.ev_top_used) {
+            for (uint32_t i = 0; i + 1 < m.ev_top_used; i += 2) {
+                float t = 0.f;
+                cudaEventElapsedTime(&t, m.ev_top[i], m.ev_top[i + 1]);
+                m.timing.ms_top_kernel += t;
+                m.timing.top_kernel_launches++;
+            }
+            m.timing.top_kernel_ratings = m.it.nnz_heavy;
+            m.ev_top_used = 0;
+        }
     }
     return SBMF_OK;
 }
@@ -350,10 +364,45 @@ int sbmf_cuda_sweep(sbmf_handle* h, uint32_t n_sweeps)
         if (rc != SBMF_OK) return rc;
     }
     API_CK(cudaSetDevice(m.device));
+    API_CK(cudaEventRecord(m.ev_call[0], m.s_main));
     for (uint32_t s = 0; s < n_sweeps; ++s) {
         int rc = one_sweep(m);
         if (rc != SBMF_OK) return rc;
     }
+    API_CK(cudaEventRecord(m.ev_call[1], m.s_main));
+    return SBMF_OK;
+}
+
+int sbmf_cuda_last_sweep_call_ms(sbmf_handle* h, double* ms)
+{
+    if (!h || !ms) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (m.sweeps_done == 0) {
+        m.err = "last_sweep_call_ms: no sweep has run";
+        return SBMF_ERR_STATE;
+    }
+    API_CK(cudaSetDevice(m.device));
+    API_CK(cudaEventSynchronize(m.ev_call[1]));
+    float t = 0.f;
+    API_CK(cudaEventElapsedTime(&t, m.ev_call[0], m.ev_call[1]));
+    *ms = (double)t;
+    return SBMF_OK;
+}
+
+int sbmf_cuda_host_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) return SBMF_ERR_INVALID;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        g_create_err = std::string("host_alloc: ") + cudaGetErrorString(e);
+        return SBMF_ERR_NOMEM;
+    }
+    return SBMF_OK;
+}
+
+int sbmf_cuda_host_free(void* ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
     return SBMF_OK;
 }
 
@@ -502,6 +551,7 @@ int sbmf_cuda_set_timing_enabled(sbmf_handle* h, int enabled)
 {
     if (!h) return SBMF_ERR_INVALID;
     h->m.timing_enabled = enabled != 0;
+    h->m.timing_detail = enabled == 2;
     return SBMF_OK;
 }
 

@@ -822,8 +822,19 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift)
         heavy_solve_kernel<1><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
         heavy_accumulate_kernel<1, 2><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, 0, 0);
         heavy_solve_kernel<2><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
+        const bool detail = m.timing_detail && !apply_shift;   // item phase only
+        if (detail && m.ev_top.size() < (size_t)2 * KB) {
+            while (m.ev_top.size() < (size_t)2 * KB) {
+                cudaEvent_t ev;
+                cudaEventCreate(&ev);
+                m.ev_top.push_back(ev);
+            }
+        }
+        if (detail) m.ev_top_used = 0;
         for (int b = 1; b < KB; ++b) {
+            if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
             heavy_accumulate_kernel<2, 2><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, b - 1, b);
+            if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
             heavy_solve_kernel<2><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, b);
         }
         heavy_accumulate_kernel<2, 0><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, KB - 1, 0);

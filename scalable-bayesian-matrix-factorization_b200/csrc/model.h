@@ -103,7 +103,11 @@ struct Model {
     cudaStream_t s_main = nullptr, s_aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_t[8] = {};
+    cudaEvent_t ev_call[2] = {};
+    std::vector<cudaEvent_t> ev_top;   // 2 per launch of the dominant kernel in one phase
+    uint32_t ev_top_used = 0;
     bool timing_enabled = true;
+    bool timing_detail = false;
     sbmf_timing timing{};
     uint64_t launches = 0;
     std::string err;

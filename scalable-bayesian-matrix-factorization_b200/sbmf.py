@@ -41,7 +41,8 @@ class Timing(C.Structure):
     _fields_ = [("ms_rebuild", C.c_double), ("ms_hypers", C.c_double), ("ms_user_phase", C.c_double), ("ms_exchange", C.c_double),
                 ("ms_item_phase", C.c_double), ("ms_eval", C.c_double), ("ms_total", C.c_double), ("sweeps", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("nnz_light_user", C.c_uint64), ("nnz_heavy_user", C.c_uint64),
-                ("nnz_light_item", C.c_uint64), ("nnz_heavy_item", C.c_uint64)]
+                ("nnz_light_item", C.c_uint64), ("nnz_heavy_item", C.c_uint64), ("ms_top_kernel", C.c_double),
+                ("top_kernel_launches", C.c_uint64), ("top_kernel_ratings", C.c_uint64)]
 
 
 class SynthSpec(C.Structure):
@@ -86,6 +87,9 @@ def load_library(path=None):
     lib.sbmf_cuda_reset_timing.argtypes = [C.c_void_p]
     lib.sbmf_cuda_synchronize.argtypes = [C.c_void_p]
     lib.sbmf_cuda_set_timing_enabled.argtypes = [C.c_void_p, C.c_int]
+    lib.sbmf_cuda_last_sweep_call_ms.argtypes = [C.c_void_p, P(C.c_double)]
+    lib.sbmf_cuda_host_alloc.argtypes = [P(C.c_void_p), C.c_size_t]
+    lib.sbmf_cuda_host_free.argtypes = [C.c_void_p]
     lib.sbmf_cuda_synth_generate.argtypes = [P(SynthSpec), P(C.c_uint64), P(C.c_uint64)] + [C.c_void_p] * 6
     lib.sbmf_cuda_synth_last_error.restype = C.c_char_p
     if path is None:
@@ -212,10 +216,30 @@ class SbmfModel:
         self._ck(self.lib.sbmf_cuda_reset_timing(self.h))
 
     def set_timing_enabled(self, on):
-        self._ck(self.lib.sbmf_cuda_set_timing_enabled(self.h, 1 if on else 0))
+        """0 = off (sweeps only enqueue work), 1 = per-phase events, 2 = also per-launch events of the dominant kernel"""
+        self._ck(self.lib.sbmf_cuda_set_timing_enabled(self.h, int(on)))
+
+    def last_sweep_call_ms(self):
+        ms = C.c_double()
+        self._ck(self.lib.sbmf_cuda_last_sweep_call_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def synchronize(self):
         self._ck(self.lib.sbmf_cuda_synchronize(self.h))
+
+
+def pinned_empty(n, dtype):
+    """numpy array over cudaMallocHost memory (sbmf_cuda_host_alloc); keeps itself alive via a finalizer."""
+    import weakref
+    lib = load_library()
+    dt = np.dtype(dtype)
+    p = C.c_void_p()
+    if lib.sbmf_cuda_host_alloc(C.byref(p), int(n) * dt.itemsize) != 0:
+        raise MemoryError("sbmf_cuda_host_alloc failed")
+    buf = (C.c_char * (int(n) * dt.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(n))
+    weakref.finalize(buf, lib.sbmf_cuda_host_free, p)
+    return arr
 
 
 def synth_generate(num_users, num_items, n_ratings, s_user=0.8, s_item=1.0, test_frac=0.1, seed=20151001, device=0):
