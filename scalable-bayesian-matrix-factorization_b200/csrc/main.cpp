@@ -1,0 +1,294 @@
+// main.cpp -- the host program: the reference's gibbs_sbpmf2 ("[T]" = gibbs_sbpmf2.cpp) with its Gibbs loop running on a
+// B200 through the extern "C" sbmf_cuda_* boundary (include/sbmf_cuda.h).  Plain C++; no CUDA, no Python.
+//
+// Drop-in behaviour:
+//   * no arguments: [T]'s hard-coded inputs ../../data/ra.train_sbpmf / ra.test_sbpmf ([T]:32, 98), D = 20 ([T]:224),
+//     T = 100 ([T]:322), and [T]'s stdout: "number rows =", "number of user =", "number of items =" ([T]:225-227), one
+//     "rmse is <v>" per sweep ([T]:635).
+//   * libFM's flag syntax and names (src/util/cmdline.h:29-120, src/libfm/libfm.cpp:86-110): -name value | --name value,
+//     ',' or ';' list delimiter, duplicate or unknown flag => "ERROR: ..." like libFM's main (libfm.cpp:636-640).
+//       -train F -test F     rating files: `user SEP item SEP rating` triples ([T]:35-73) or libFM text `y u:1 i:1` (auto-detected)
+//       -dim 'k0,k1,K'       K = latent dimension (third field, libFM's k2); k0/k1 are accepted and must be 1 (biases are part of SBMF)
+//       -iter T              sweeps (default 100)        -init_stdev s   (default 0.1, [T]:242)
+//       -out F               posterior-mean clamped test predictions, one per line (libfm.cpp:629-634, DVector::save)
+//       -rlog F              tab-separated per-sweep log (src/util/rlog.h)
+//       -seed n              Philox key (libFM parses -seed and ignores it, libfm.cpp:124; [T] never seeds)
+//       -method mcmc|sbmf    accepted for libFM command lines; -task r; -verbosity n; -help
+//     extensions: -do_sampling 0 (conditional-mean updates; libFM's do_sample=false), -stdev_mode ref|sqrt,
+//       -burn_in n, -rebuild_every n, -device n, -item_offset n|auto (libFM text: item feature id - offset = item id)
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "sbmf_cuda.h"
+
+namespace {
+
+struct CmdLine {   // same grammar as src/util/cmdline.h:29-74
+    std::map<std::string, std::string> help, value;
+    static bool parse_name(std::string& s)
+    {
+        if (!s.empty() && s[0] == '-') {
+            s = (s.size() > 1 && s[1] == '-') ? s.substr(2) : s.substr(1);
+            return true;
+        }
+        return false;
+    }
+    CmdLine(int argc, char** argv)
+    {
+        for (int i = 1; i < argc; ++i) {
+            std::string s(argv[i]);
+            if (!parse_name(s)) throw "cannot parse " + s;
+            if (value.count(s)) throw "the parameter " + s + " is already specified";
+            if (i + 1 < argc) {
+                std::string nx(argv[i + 1]);
+                // a value may be a negative number: only treat "-x" as a flag if it is not numeric
+                std::string probe = nx;
+                const bool is_flag = parse_name(probe) && !(nx.size() > 1 && (isdigit((unsigned char)nx[1]) || nx[1] == '.'));
+                if (!is_flag) {
+                    value[s] = nx;
+                    ++i;
+                    continue;
+                }
+            }
+            value[s] = "";
+        }
+    }
+    const std::string& reg(const std::string& p, const std::string& h)
+    {
+        help[p] = h;
+        return p;
+    }
+    bool has(const std::string& p) const { return value.count(p) != 0; }
+    std::string get(const std::string& p, const std::string& def) const { return has(p) ? value.at(p) : def; }
+    long geti(const std::string& p, long def) const { return has(p) ? atol(value.at(p).c_str()) : def; }
+    double getd(const std::string& p, double def) const { return has(p) ? atof(value.at(p).c_str()) : def; }
+    void check() const
+    {
+        for (const auto& kv : value)
+            if (!help.count(kv.first)) throw "the parameter " + kv.first + " does not exist";
+    }
+    void print_help() const
+    {
+        for (const auto& kv : help) {
+            std::cout << "-" << kv.first;
+            for (size_t i = kv.first.size() + 1; i < 16; ++i) std::cout << " ";
+            std::cout << kv.second << std::endl;
+        }
+    }
+    static std::vector<std::string> split(const std::string& s, const std::string& delim = ";,")
+    {
+        std::vector<std::string> out;
+        std::string cur;
+        for (char c : s) {
+            if (delim.find(c) != std::string::npos) {
+                out.push_back(cur);
+                cur.clear();
+            } else {
+                cur += c;
+            }
+        }
+        out.push_back(cur);
+        return out;
+    }
+};
+
+struct Ratings {
+    std::vector<uint32_t> user, item;
+    std::vector<float> rating;
+    uint32_t user_max = 0, item_max = 0;
+};
+
+// [T]:35-73: sscanf("%u%c%u%c%lf"), a line counts iff all 5 conversions succeed.  libFM text lines ("y u:1 i:1") fail the
+// third conversion's separator test (':' then a digit is read as the item id of a triple only if there is no ':' form),
+// so the format is detected on the first non-empty line by looking for ':'.
+void read_ratings(const std::string& path, Ratings& out, long item_offset, bool& was_libfm)
+{
+    std::ifstream f(path.c_str());
+    if (!f.is_open()) throw "unable to open " + path;
+    std::string line;
+    bool detected = false, libfm = false;
+    std::vector<uint32_t> raw_item;
+    uint64_t lineno = 0;
+    while (std::getline(f, line)) {
+        ++lineno;
+        if (!detected) {
+            if (line.find_first_not_of(" \t\r\n") == std::string::npos) continue;
+            libfm = line.find(':') != std::string::npos;
+            detected = true;
+        }
+        unsigned u, m;
+        double r;
+        if (!libfm) {
+            char w1, w2;
+            if (sscanf(line.c_str(), "%u%c%u%c%lf", &u, &w1, &m, &w2, &r) >= 5) {
+                out.user.push_back(u);
+                out.item.push_back(m);
+                out.rating.push_back((float)r);
+            } else if (line.find_first_not_of(" \t\r\n") != std::string::npos) {
+                // [T] would skip the line but still advance its rating index and write out of bounds later
+                throw "malformed rating line " + std::to_string(lineno) + " in " + path;
+            }
+        } else {
+            double v1, v2;
+            if (sscanf(line.c_str(), "%lf %u:%lf %u:%lf", &r, &u, &v1, &m, &v2) == 5) {
+                out.user.push_back(u);
+                out.item.push_back(m);
+                out.rating.push_back((float)r);
+            } else if (line.find_first_not_of(" \t\r\n") != std::string::npos) {
+                throw "libFM text line " + std::to_string(lineno) + " in " + path + " is not `y user:1 item:1`";
+            }
+        }
+    }
+    was_libfm = libfm;
+    if (libfm && item_offset > 0)
+        for (auto& m : out.item) {
+            if ((long)m < item_offset) throw std::string("libFM text: item feature id below -item_offset in ") + path;
+            m -= (uint32_t)item_offset;
+        }
+    for (size_t n = 0; n < out.user.size(); ++n) {
+        if (out.user[n] > out.user_max) out.user_max = out.user[n];
+        if (out.item[n] > out.item_max) out.item_max = out.item[n];
+    }
+}
+
+void ck(int rc, sbmf_handle* h, const char* what)
+{
+    if (rc != SBMF_OK) throw std::string(what) + ": " + sbmf_cuda_last_error(h);
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    try {
+        CmdLine cmd(argc, argv);
+        const std::string p_task = cmd.reg("task", "r=regression (the only task of SBMF)");
+        const std::string p_train = cmd.reg("train", "filename for training data; default=../../data/ra.train_sbpmf");
+        const std::string p_test = cmd.reg("test", "filename for test data; default=../../data/ra.test_sbpmf");
+        const std::string p_out = cmd.reg("out", "filename for output (posterior-mean test predictions)");
+        const std::string p_dim = cmd.reg("dim", "'k0,k1,k2': k2=number of latent dimensions; default=1,1,20");
+        const std::string p_init = cmd.reg("init_stdev", "stdev for initialization of the factors; default=0.1");
+        const std::string p_iter = cmd.reg("iter", "number of Gibbs sweeps; default=100");
+        const std::string p_method = cmd.reg("method", "learning method (mcmc | sbmf); default=sbmf");
+        const std::string p_verb = cmd.reg("verbosity", "how much infos to print; default=0");
+        const std::string p_rlog = cmd.reg("rlog", "write measurements within iterations to a file; default=''");
+        const std::string p_seed = cmd.reg("seed", "integer value, default=1");
+        const std::string p_help = cmd.reg("help", "this screen");
+        const std::string p_samp = cmd.reg("do_sampling", "0 = conditional-mean updates (no noise); default=1");
+        const std::string p_sdm = cmd.reg("stdev_mode", "ref = draw with stdev 1/lambda like the reference, sqrt = sqrt(1/lambda); default=ref");
+        const std::string p_burn = cmd.reg("burn_in", "sweeps before predictions are averaged; default=0");
+        const std::string p_reb = cmd.reg("rebuild_every", "rebuild the residual every n sweeps; default=1");
+        const std::string p_dev = cmd.reg("device", "CUDA device ordinal; default=0");
+        const std::string p_off = cmd.reg("item_offset", "libFM text input: item id = item feature id - offset; default=auto");
+        if (cmd.has(p_help)) {
+            cmd.print_help();
+            return 0;
+        }
+        cmd.check();
+        const std::string method = cmd.get(p_method, "sbmf");
+        if (method != "sbmf" && method != "mcmc" && method != "MCMC") throw "unknown method " + method + " (this program is the SBMF Gibbs sampler)";
+        if (cmd.get(p_task, "r") != "r") throw std::string("only -task r is supported");
+        uint32_t K = 20;
+        if (cmd.has(p_dim)) {
+            const std::vector<std::string> d = CmdLine::split(cmd.get(p_dim, ""));
+            if (d.size() != 3) throw std::string("-dim needs 'k0,k1,k2'");
+            if (atoi(d[0].c_str()) != 1 || atoi(d[1].c_str()) != 1) throw std::string("-dim: k0 and k1 must be 1 (global mean and biases are part of SBMF)");
+            K = (uint32_t)atoi(d[2].c_str());
+        }
+        const uint32_t T = (uint32_t)cmd.geti(p_iter, 100);
+        const std::string train_file = cmd.get(p_train, "../../data/ra.train_sbpmf");
+        const std::string test_file = cmd.get(p_test, "../../data/ra.test_sbpmf");
+
+        Ratings tr, te;
+        bool libfm_tr = false, libfm_te = false;
+        long off = 0;
+        const std::string offs = cmd.get(p_off, "auto");
+        if (offs != "auto") off = atol(offs.c_str());
+        read_ratings(train_file, tr, off, libfm_tr);
+        if (libfm_tr && offs == "auto") {
+            // libFM MF files number items after the users (scripts/triple_format_to_libfm.pl): offset = 1 + max user id
+            uint32_t min_item = UINT32_MAX;
+            for (uint32_t m : tr.item) min_item = m < min_item ? m : min_item;
+            off = (min_item > tr.user_max) ? (long)tr.user_max + 1 : 0;
+            if (off) {
+                for (auto& m : tr.item) m -= (uint32_t)off;
+                tr.item_max -= (uint32_t)off;
+            }
+        }
+        read_ratings(test_file, te, libfm_tr ? off : 0, libfm_te);
+        const uint32_t user_max = tr.user_max > te.user_max ? tr.user_max : te.user_max;   // [T]:45-52, 112-119
+        const uint32_t item_max = tr.item_max > te.item_max ? tr.item_max : te.item_max;
+        const uint32_t num_users = user_max + 1, num_items = item_max + 1;                  // [T]:151-153
+        std::cout << "number rows =" << tr.user.size() << "\n";                             // [T]:225-227
+        std::cout << "number of user =" << num_users << "\n";
+        std::cout << "number of items =" << num_items << "\n";
+
+        sbmf_config cfg;
+        sbmf_cuda_config_default(&cfg);
+        cfg.K = K;
+        cfg.device = (int32_t)cmd.geti(p_dev, 0);
+        cfg.seed = (uint64_t)cmd.geti(p_seed, 1);
+        cfg.init_stdev = cmd.getd(p_init, 0.1);
+        cfg.burn_in = (uint32_t)cmd.geti(p_burn, 0);
+        cfg.rebuild_every = (uint32_t)cmd.geti(p_reb, 1);
+        const std::string sdm = cmd.get(p_sdm, "ref");
+        if (sdm != "ref" && sdm != "sqrt") throw std::string("-stdev_mode must be ref or sqrt");
+        cfg.sample_mode = cmd.geti(p_samp, 1) == 0 ? SBMF_SAMPLE_ZERO_NOISE : (sdm == "sqrt" ? SBMF_SAMPLE_SQRT : SBMF_SAMPLE_REF_VAR_AS_STDEV);
+
+        sbmf_handle* h = NULL;
+        if (sbmf_cuda_create(&cfg, &h) != SBMF_OK) throw std::string("sbmf_cuda_create: ") + sbmf_cuda_last_error(NULL);
+        ck(sbmf_cuda_set_train(h, tr.user.size(), tr.user.data(), tr.item.data(), tr.rating.data(), num_users, num_items), h, "set_train");
+        ck(sbmf_cuda_set_test(h, te.user.size(), te.user.data(), te.item.data(), te.rating.data()), h, "set_test");
+        ck(sbmf_cuda_init_factors(h, NULL, NULL), h, "init_factors");
+        ck(sbmf_cuda_set_timing_enabled(h, 0), h, "set_timing_enabled");
+
+        std::ofstream rlog;
+        if (cmd.has(p_rlog) && !cmd.get(p_rlog, "").empty()) {
+            rlog.open(cmd.get(p_rlog, "").c_str());
+            if (!rlog.is_open()) throw "unable to open " + cmd.get(p_rlog, "");
+            rlog << "rmse\trmse_sweep\talpha\tb_0\ttime_learn\n";
+        }
+        const int verbosity = (int)cmd.geti(p_verb, 0);
+        for (uint32_t iter = 0; iter < T; ++iter) {
+            const auto t0 = std::chrono::steady_clock::now();
+            double rmse = 0.0, rmse_sweep = 0.0;
+            ck(sbmf_cuda_sweep(h, 1), h, "sweep");
+            ck(sbmf_cuda_eval(h, &rmse, &rmse_sweep), h, "eval");
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            std::cout << "rmse is " << rmse << std::endl;                                   // [T]:635
+            if (rlog.is_open() || verbosity > 0) {
+                sbmf_state st;
+                memset(&st, 0, sizeof(st));
+                ck(sbmf_cuda_get_state(h, &st), h, "get_state");
+                if (rlog.is_open()) rlog << rmse << "\t" << rmse_sweep << "\t" << st.alpha << "\t" << st.b_0 << "\t" << dt << "\n" << std::flush;
+                if (verbosity > 0)
+                    std::cout << "#Iter=" << iter << "\tTest=" << rmse_sweep << "\talpha=" << st.alpha << "\tb_0=" << st.b_0 << "\ttime=" << dt << std::endl;
+            }
+        }
+        if (cmd.has(p_out)) {
+            std::vector<float> pred(te.user.size());
+            if (T > cfg.burn_in) ck(sbmf_cuda_get_pred(h, pred.data()), h, "get_pred");
+            std::ofstream o(cmd.get(p_out, "").c_str());
+            if (!o.is_open()) throw "unable to open " + cmd.get(p_out, "");
+            for (float v : pred) o << (double)v << std::endl;                               // DVector::save, matrix.h:268-277
+        }
+        sbmf_cuda_destroy(h);
+    } catch (std::string& e) {
+        std::cerr << std::endl << "ERROR: " << e << std::endl;
+        return 1;
+    } catch (char const*& e) {
+        std::cerr << std::endl << "ERROR: " << e << std::endl;
+        return 1;
+    }
+    return 0;
+}

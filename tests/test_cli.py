@@ -1,0 +1,108 @@
+"""Host program (bin/sbmf, csrc/main.cpp): libFM flag grammar and error behaviour on CPU; on the GPU the same trajectory and
+prediction file as the ctypes binding, from triple files and from libFM text files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "scalable-bayesian-matrix-factorization_b200")
+CLI = os.path.join(PKG, "bin", "sbmf")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    subprocess.run(["make", "-C", PKG], check=True, capture_output=True)
+    return CLI
+
+
+def run(cli, *args, cwd=None):
+    return subprocess.run([cli, *args], capture_output=True, text=True, cwd=cwd)
+
+
+def test_help_lists_libfm_flags(cli):
+    r = run(cli, "-help")
+    assert r.returncode == 0
+    for flag in ("-train", "-test", "-dim", "-iter", "-out", "-rlog", "-seed", "-init_stdev", "-method", "-task", "-verbosity"):
+        assert flag in r.stdout
+
+
+def test_unknown_and_duplicate_flags_error_like_libfm(cli):
+    r = run(cli, "-bogus", "1")
+    assert r.returncode == 1 and "ERROR: the parameter bogus does not exist" in r.stderr
+    r = run(cli, "-iter", "1", "--iter", "2")
+    assert r.returncode == 1 and "ERROR: the parameter iter is already specified" in r.stderr
+    r = run(cli, "stray")
+    assert r.returncode == 1 and "ERROR: cannot parse stray" in r.stderr
+
+
+def test_missing_and_malformed_input(cli, tmp_path):
+    r = run(cli, "-train", str(tmp_path / "nope"), "-test", str(tmp_path / "nope"))
+    assert r.returncode == 1 and "unable to open" in r.stderr
+    bad = tmp_path / "bad"
+    bad.write_text("0\t1\t3\nthis is not a rating\n")
+    r = run(cli, "-train", str(bad), "-test", str(bad))
+    assert r.returncode == 1 and "malformed rating line 2" in r.stderr
+    r = run(cli, "-dim", "1,0,8", "-train", str(bad), "-test", str(bad))
+    assert r.returncode == 1 and "k0 and k1 must be 1" in r.stderr
+
+
+def write_triples(path, u, i, r):
+    with open(path, "w") as f:
+        for a, b, c in zip(u, i, r):
+            f.write(f"{a}\t{b}\t{int(c)}\n")
+
+
+def write_libfm(path, u, i, r, offset):
+    with open(path, "w") as f:
+        for a, b, c in zip(u, i, r):
+            f.write(f"{int(c)} {a}:1 {b + offset}:1\n")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["triples", "libfm"])
+def test_cli_matches_binding(cli, tmp_path, ml100k, fmt):
+    import sbmf
+    d = ml100k
+    tr, te = str(tmp_path / "train"), str(tmp_path / "test")
+    if fmt == "triples":
+        write_triples(tr, d["train_user"], d["train_item"], d["train_rating"])
+        write_triples(te, d["test_user"], d["test_item"], d["test_rating"])
+    else:
+        write_libfm(tr, d["train_user"], d["train_item"], d["train_rating"], d["num_users"])
+        write_libfm(te, d["test_user"], d["test_item"], d["test_rating"], d["num_users"])
+    out, rlog = str(tmp_path / "pred"), str(tmp_path / "rlog")
+    r = run(cli, "-task", "r", "-train", tr, "-test", te, "-dim", "1,1,20", "-iter", "6", "-seed", "42", "-out", out, "-rlog", rlog, "-method", "mcmc")
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[:3] == ["number rows =90570", "number of user =943", "number of items =1682"]
+    got = [ln.split()[-1] for ln in lines if ln.startswith("rmse is ")]
+    m = sbmf.SbmfModel(K=20, seed=42)
+    m.set_train(d["train_user"], d["train_item"], d["train_rating"], d["num_users"], d["num_items"])
+    m.set_test(d["test_user"], d["test_item"], d["test_rating"])
+    m.init_factors()
+    m.sweep(6)
+    want = ["%g" % x for x in m.rmse_history(0, 6)[0]]
+    assert got == want
+    pred = np.loadtxt(out)
+    assert pred.shape == (9430,) and np.max(np.abs(pred - m.get_pred())) < 1e-5
+    assert pred.min() >= 0.5 and pred.max() <= 5.0
+    log = open(rlog).read().splitlines()
+    assert log[0].split("\t") == ["rmse", "rmse_sweep", "alpha", "b_0", "time_learn"] and len(log) == 7
+    m.close()
+
+
+@pytest.mark.gpu
+def test_cli_no_arguments_uses_reference_paths(cli, tmp_path, tiny):
+    """[T] opens ../../data/ra.{train,test}_sbpmf relative to its CWD ([T]:32, 98), D=20, T=100."""
+    (tmp_path / "data").mkdir()
+    (tmp_path / "a" / "b").mkdir(parents=True)
+    d = tiny
+    write_triples(tmp_path / "data" / "ra.train_sbpmf", d["train_user"], d["train_item"], d["train_rating"])
+    write_triples(tmp_path / "data" / "ra.test_sbpmf", d["test_user"], d["test_item"], d["test_rating"])
+    r = run(cli, cwd=str(tmp_path / "a" / "b"))
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[1] == "number of user =50" and lines[2] == "number of items =40"
+    assert sum(ln.startswith("rmse is ") for ln in lines) == 100
