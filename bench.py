@@ -223,15 +223,47 @@ def main():
         cb = cpu_reference(sample, K, pairs=pairs, port_steps=max(1, a.steps))
         cfg["n_train_sample"] = int(sample["train_user"].size)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": cb["sweeps_timed"],
-                "warmup": 1, "ms_per_step": cb["s_per_sweep"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": 1, "ms_per_step": cb["s_per_sweep"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
 
-    if a.gpus != 1:
-        raise SystemExit("bench.py: multi-GPU sharding is not wired in yet (single-GPU only in this revision)")
+    dist = None
+    nccl_id = None
+    if world > 1:   # control plane: torch.distributed (gloo) for the id broadcast, barriers and the max over ranks
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
 
+        def new_id():
+            t = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                t = torch.frombuffer(bytearray(sbmf.nccl_unique_id()), dtype=torch.uint8).clone()
+            dist.broadcast(t, 0)
+            return t.numpy().tobytes()
+
+        def max_over_ranks(x):
+            t = torch.tensor([float(x)], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        nccl_id = new_id()
+    else:
+        def max_over_ranks(x):
+            return float(x)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def mk(**kw):
+        if world > 1:
+            kw.update(rank=rank, world_size=world, nccl_id=kw.pop("nccl_id"))
+        else:
+            kw.pop("nccl_id", None)
+        return sbmf.SbmfModel(**kw)
+
+    cfg["parallelism"] = f"{world} GPU(s): users (CSR) and items (CSC) sharded by rating count, factors replicated" if world > 1 else "1 GPU"
     dev = local_rank
     t0 = time.perf_counter()
     d = sbmf.synth_generate(I, J, int(round(NTRAIN / (1 - TEST_FRAC))), test_frac=TEST_FRAC, seed=SEED, device=dev)
@@ -241,7 +273,7 @@ def main():
     fu_per_sweep = float(n_train) * K
 
     # ---- value: K sweeps, everything resident, CUDA events on the library's stream
-    m = sbmf.SbmfModel(K=K, device=dev, sample_mode=sbmf.SAMPLE_REF, seed=1)
+    m = mk(K=K, device=dev, sample_mode=sbmf.SAMPLE_REF, seed=1, nccl_id=nccl_id)
     m.set_train(d["train_user"], d["train_item"], d["train_rating"], I, J)
     m.set_test(d["test_user"], d["test_item"], d["test_rating"])
     m.init_factors()
@@ -249,11 +281,15 @@ def main():
     m.sweep(W)
     m.synchronize()
     m.reset_timing()
+    barrier()
     with ClockSampler(dev) as cs:
         tw0 = time.perf_counter()
         m.sweep(a.steps)
         ms = m.last_sweep_call_ms()     # waits for the K sweeps; device time between two events on the stream
         wall_ms = (time.perf_counter() - tw0) * 1e3
+    barrier()
+    ms = max_over_ranks(ms)             # max over ranks of the device time
+    wall_ms = max_over_ranks(wall_ms)
     launches = m.timing()["kernel_launches"]
     clocks = cs.summary()
     ms_per_step = ms / a.steps
@@ -267,6 +303,7 @@ def main():
     t = m.timing()
     peak, peak_src = peaks()
     roof = None
+    t_local_ratings = t["top_kernel_ratings"]
     if t["top_kernel_launches"]:
         us = t["ms_top_kernel"] / t["top_kernel_launches"] * 1e3
         alg_bytes = 12.0 * 8 * t["top_kernel_ratings"]          # 12 B per (rating, dimension) visit x 8 dimensions per launch
@@ -282,8 +319,8 @@ def main():
         if os.path.exists(prof):
             roof["traffic"] = json.load(open(prof)).get("heavy_accumulate_kernel<2,2>", {}).get("dram_bytes_per_launch")
     phases = {k: round(t[k] / max(t["sweeps"], 1), 3) for k in ("ms_rebuild", "ms_hypers", "ms_user_phase", "ms_exchange", "ms_item_phase", "ms_eval", "ms_total")}
-    sweep_roof = {"algorithmic_bytes_per_sweep": ALG_BYTES_PER_FU * fu_per_sweep, "achieved_gbs": ALG_BYTES_PER_FU * value / 1e9,
-                  "frac_of_peak": ALG_BYTES_PER_FU * value / 1e9 / peak}
+    sweep_roof = {"algorithmic_bytes_per_sweep": ALG_BYTES_PER_FU * fu_per_sweep, "achieved_gbs_per_gpu": ALG_BYTES_PER_FU * value / 1e9 / world,
+                  "frac_of_peak": ALG_BYTES_PER_FU * value / 1e9 / peak / world}
     m.close()
 
     # ---- e2e: the whole job through the C ABI from pinned host buffers
@@ -294,9 +331,10 @@ def main():
             hb[k] = sbmf.pinned_empty(d[k].size, d[k].dtype)
             hb[k][:] = d[k]
         pred = sbmf.pinned_empty(n_test, np.float32)
-        m2 = sbmf.SbmfModel(K=K, device=dev, sample_mode=sbmf.SAMPLE_REF, seed=1)
+        m2 = mk(K=K, device=dev, sample_mode=sbmf.SAMPLE_REF, seed=1, nccl_id=new_id() if world > 1 else None)
         m2.set_timing_enabled(0)
         m2.synchronize()
+        barrier()
         te0 = time.perf_counter()
         m2.set_train(hb["train_user"], hb["train_item"], hb["train_rating"], I, J)
         m2.set_test(hb["test_user"], hb["test_item"], hb["test_rating"])
@@ -307,7 +345,8 @@ def main():
             last = m2.eval()            # D2H read of the step's result (2 doubles), synchronises
         m2._ck(m2.lib.sbmf_cuda_get_pred(m2.h, pred.ctypes.data))
         m2.synchronize()
-        e2e_s = time.perf_counter() - te0
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - te0)
         h2d = 12.0 * (n_train + n_test)
         d2h = 16.0 * a.steps + 8.0 * n_test
         e2e = {"value": fu_per_sweep * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
@@ -315,12 +354,14 @@ def main():
                "what": "set_train(H2D COO + device CSR/CSC build) + set_test + init_factors + steps x (sweep + eval D2H) + get_pred D2H, wall clock"}
         m2.close()
 
+    if rank != 0:
+        return
     cb = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:
         cb = cpu_reference(take_sample(d, a.cpu_sample), K, pairs=1)
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": W, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "sweeps_per_s": 1e3 / ms_per_step, "wall_ms_per_step": wall_ms / a.steps, "rmse_after_timed": rmse, "clocks": clocks,
             "gpu_launches": int(launches), "phases_ms": phases, "roofline": roof, "roofline_sweep": sweep_roof, "e2e": e2e, "cpu_baseline": cb,
             "paper_i5_openmp_fu_per_s": 25.4e6}

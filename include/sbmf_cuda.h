@@ -123,6 +123,20 @@ const char* sbmf_cuda_last_error(const sbmf_handle* h);
 /* rank 0 of a multi-GPU job calls this and ships the 128 bytes to the other ranks (torch.distributed, MPI, ...) */
 int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
 
+/* ---- multi-GPU (one handle per rank = per GPU) --------------------------------------------
+   Every rank passes the SAME full COO to set_train / set_test; the library keeps only the rank's shards: a contiguous
+   user range with its CSR slots and a contiguous item range with its CSC slots (both cut to balance ratings), full
+   replicas of the factors.  Per sweep: all-reduce of (sum e, sum e^2), one residual all-to-all between the phases,
+   all-gather of the rows each rank updated after each phase, all-reduce of the squared test errors.  Draws are keyed
+   by global row id, so the chain does not depend on world_size.
+   The two planning functions are pure host code (no GPU needed) and are what the CPU tests exercise:
+   plan_shards: bounds[0..world], rank r owns rows [bounds[r], bounds[r+1]).
+   plan_exchange: see csrc/plan.cpp; perm[csc slot] = csr slot, csr_bounds / csc_bounds = [world+1] global slot offsets. */
+int sbmf_cuda_plan_shards(const int64_t* ptr, uint32_t n_rows, int world, uint32_t* bounds);
+int sbmf_cuda_plan_exchange(uint64_t n, const uint32_t* perm, int world, int rank, const int64_t* csr_bounds,
+                            const int64_t* csc_bounds, uint32_t* send_idx, int64_t* send_counts, uint32_t* recv_pos,
+                            int64_t* recv_counts);
+
 /* ---- rating storage: replaces the jagged R / R_t build of [T]:32-221 --------------------------------- */
 /* COO in FILE ORDER (rating index n = position), 0-based ids, num_users = 1 + max user id over train U test
    ([T]:151-153).  Builds on device: CSR by user + CSC by item, both STABLE w.r.t. file order ([T]:209-214),

@@ -85,9 +85,9 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
         g_create_err = "create: unknown sample_mode / hyper_mode";
         return SBMF_ERR_INVALID;
     }
-    if (cfg->world_size != 1 || cfg->rank != 0) {
-        g_create_err = "create: world_size > 1 is not implemented in this build";
-        return SBMF_ERR_UNSUPPORTED;
+    if (cfg->world_size < 1 || cfg->world_size > 64 || cfg->rank < 0 || cfg->rank >= cfg->world_size) {
+        g_create_err = "create: need 0 <= rank < world_size <= 64";
+        return SBMF_ERR_INVALID;
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -119,6 +119,8 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
     if (m.cfg.rebuild_every == 0) m.cfg.rebuild_every = 1;
     m.device = cfg->device;
     m.sm_count = prop.multiProcessorCount;
+    m.rank = cfg->rank;
+    m.world = cfg->world_size;
     m.K = cfg->K;
     m.KB = (cfg->K + KBLK - 1) / KBLK;
     m.KP = m.KB * KBLK;
@@ -142,6 +144,14 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
         sbmf_cuda_destroy(h);
         return SBMF_ERR_CUDA;
     }
+    if (m.world > 1) {   // one communicator per rank; the id comes from sbmf_cuda_nccl_unique_id on rank 0
+        std::string err;
+        if (comm_init(m.comm, cfg->nccl_id, m.rank, m.world, err) != 0) {
+            g_create_err = "create: NCCL: " + err;
+            sbmf_cuda_destroy(h);
+            return SBMF_ERR_NCCL;
+        }
+    }
     *out = h;
     return SBMF_OK;
 }
@@ -155,6 +165,7 @@ int sbmf_cuda_destroy(sbmf_handle* h)
     if (m.s_aux) cudaStreamSynchronize(m.s_aux);
     free_storage(m);
     free_test(m);
+    comm_destroy(m.comm);
     cudaFree(m.sc);
     cudaFree(m.rmse_hist);
     for (int i = 0; i < 8; ++i)
@@ -174,9 +185,13 @@ const char* sbmf_cuda_last_error(const sbmf_handle* h) { return h ? h->m.err.c_s
 
 int sbmf_cuda_nccl_unique_id(uint8_t out[128])
 {
-    (void)out;
-    g_create_err = "nccl_unique_id: multi-GPU is not implemented in this build";
-    return SBMF_ERR_UNSUPPORTED;
+    if (!out) return SBMF_ERR_INVALID;
+    std::string err;
+    if (comm_unique_id(out, err) != 0) {
+        g_create_err = "nccl_unique_id: " + err;
+        return SBMF_ERR_NCCL;
+    }
+    return SBMF_OK;
 }
 
 int sbmf_cuda_set_train(sbmf_handle* h, uint64_t n, const uint32_t* user, const uint32_t* item, const float* rating, uint32_t num_users,
@@ -223,6 +238,10 @@ int sbmf_cuda_get_layout(sbmf_handle* h, int64_t* row_ptr, uint32_t* col, uint64
     if (!m.have_train) {
         m.err = "get_layout: no training set";
         return SBMF_ERR_STATE;
+    }
+    if (m.world > 1) {
+        m.err = "get_layout: only the single-GPU handle keeps the global layout";
+        return SBMF_ERR_UNSUPPORTED;
     }
     API_CK(cudaSetDevice(m.device));
     API_CK(cudaStreamSynchronize(m.s_main));
@@ -293,26 +312,33 @@ static int one_sweep(Model& m)
     const bool timing = m.timing_enabled;
     const bool rebuild = (m.sweeps_done % m.cfg.rebuild_every) == 0;
     if (timing) cudaEventRecord(m.ev_t[0], st);
+    int crc = 0;
     if (rebuild) {
         launch_rebuild(m, st);                       // [T]:342-359
     } else {
-        if (m.e_in_csc) launch_permute(m, false, st);
+        if (m.e_in_csc) crc |= launch_permute(m, false, st);
         launch_stats(m, st);
     }
+    crc |= launch_reduce_pair(m, st);                // sum e, sum e^2 (all ranks)
     if (timing) cudaEventRecord(m.ev_t[1], st);
     launch_global_hypers(m, st);                     // [T]:366-410
     launch_dim_hypers(m, st);                        // [T]:415-467
     launch_bias_hypers(m, st);                       // [T]:469-511
     if (timing) cudaEventRecord(m.ev_t[2], st);
     launch_phase(m, m.us, m.it, true);               // [T]:514-558
+    crc |= launch_allgather_side(m, m.us, st);       // multi-GPU: replicate the updated U rows and user biases
     if (timing) cudaEventRecord(m.ev_t[3], st);
-    launch_permute(m, true, st);                     // residual CSR order -> CSC order
+    crc |= launch_permute(m, true, st);              // residual CSR order -> CSC order (all-to-all across GPUs)
     if (timing) cudaEventRecord(m.ev_t[4], st);
     launch_phase(m, m.it, m.us, false);              // [T]:563-606
+    crc |= launch_allgather_side(m, m.it, st);
     m.e_in_csc = true;
     if (timing) cudaEventRecord(m.ev_t[5], st);
     launch_eval(m, st);                              // [T]:610-636
+    crc |= launch_reduce_pair(m, st);
+    launch_eval_final(m, st);
     if (timing) cudaEventRecord(m.ev_t[6], st);
+    if (crc) return SBMF_ERR_NCCL;
     m.sweeps_done++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -462,6 +488,14 @@ int sbmf_cuda_get_pred(sbmf_handle* h, float* pred)
     }
     API_CK(cudaSetDevice(m.device));
     std::vector<double> tmp(m.Nt ? m.Nt : 1);
+    if (m.world > 1) {   // every rank accumulated its own slice of the test set
+        std::vector<size_t> off(m.world), cnt(m.world);
+        for (int q = 0; q < m.world; ++q) {
+            off[q] = m.Nt * (uint64_t)q / (uint64_t)m.world;
+            cnt[q] = m.Nt * (uint64_t)(q + 1) / (uint64_t)m.world - off[q];
+        }
+        if (comm_allgatherv_f64(m.comm, m.t_sum, off.data(), cnt.data(), m.s_main, m.err) != 0) return SBMF_ERR_NCCL;
+    }
     API_CK(cudaMemcpyAsync(tmp.data(), m.t_sum, m.Nt * 8, cudaMemcpyDeviceToHost, m.s_main));
     API_CK(cudaStreamSynchronize(m.s_main));
     const double denom = (double)(m.sweeps_done - m.cfg.burn_in);
@@ -508,11 +542,13 @@ int sbmf_cuda_get_state(sbmf_handle* h, sbmf_state* out)
     if (out->mu_v) API_CK(cudaMemcpy(out->mu_v, m.it.mu_k, (size_t)m.K * 8, cudaMemcpyDeviceToHost));
     if (out->E) {
         // residual in rating (file) order, from whichever layout holds the freshest copy
-        std::vector<float> e(m.N ? m.N : 1);
-        std::vector<uint32_t> id(m.N ? m.N : 1);
-        API_CK(cudaMemcpy(e.data(), m.e_in_csc ? m.it.e : m.us.e, m.N * 4, cudaMemcpyDeviceToHost));
-        API_CK(cudaMemcpy(id.data(), m.e_in_csc ? m.csc_id : m.csr_id, m.N * 4, cudaMemcpyDeviceToHost));
-        for (uint64_t s = 0; s < m.N; ++s) out->E[id[s]] = e[s];
+        // (multi-GPU: only the entries of this rank's shard are written)
+        const uint64_t nl = m.e_in_csc ? m.n_csc : m.n_csr;
+        std::vector<float> e(nl ? nl : 1);
+        std::vector<uint32_t> id(nl ? nl : 1);
+        API_CK(cudaMemcpy(e.data(), m.e_in_csc ? m.it.e : m.us.e, nl * 4, cudaMemcpyDeviceToHost));
+        API_CK(cudaMemcpy(id.data(), m.e_in_csc ? m.csc_id : m.csr_id, nl * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t s = 0; s < nl; ++s) out->E[id[s]] = e[s];
     }
     Scalars sc;
     API_CK(cudaMemcpy(&sc, m.sc, sizeof(Scalars), cudaMemcpyDeviceToHost));

@@ -427,18 +427,21 @@ stats_kernel(const float* __restrict__ e, uint64_t N, double* __restrict__ part)
 
 // final reduce of the statistics + the scalar chain alpha, sigma_b_0, mu_b_0, b_0 of [T]:366-410
 __global__ void __launch_bounds__(RED_THREADS)
-global_hypers_kernel(Scalars* sc, const double* __restrict__ part, uint32_t nparts, uint64_t N, sbmf_priors pr, int mode, uint64_t seed)
+reduce_pair_kernel(const double* __restrict__ part, uint32_t nparts, double* __restrict__ out)
 {
-    __shared__ double out[2];
     double s1 = 0.0, s2 = 0.0;
     for (uint32_t i = threadIdx.x; i < nparts; i += RED_THREADS) {
         s1 += part[(size_t)i * 2];
         s2 += part[(size_t)i * 2 + 1];
     }
     block_reduce2_store(s1, s2, out);
-    __syncthreads();
+}
+
+__global__ void __launch_bounds__(32)
+global_hypers_kernel(Scalars* sc, const double* __restrict__ red2, uint64_t N, sbmf_priors pr, int mode, uint64_t seed)
+{
     if (threadIdx.x != 0) return;
-    const double S1 = out[0], S2 = out[1];
+    const double S1 = red2[0], S2 = red2[1];
     const uint32_t sweep = sc->sweep;
     const double Nd = (double)N;
     sc->sum_e = S1;
@@ -608,17 +611,9 @@ eval_kernel(const uint32_t* __restrict__ tu, const uint32_t* __restrict__ ti, co
     block_reduce2_store(s1, s2, part + (size_t)blockIdx.x * 2);
 }
 
-__global__ void __launch_bounds__(RED_THREADS)
-eval_final_kernel(Scalars* sc, const double* __restrict__ part, uint32_t nparts, uint64_t Nt, double* __restrict__ hist, uint32_t hist_cap)
+__global__ void __launch_bounds__(32)
+eval_final_kernel(Scalars* sc, const double* __restrict__ out, uint64_t Nt, double* __restrict__ hist, uint32_t hist_cap)
 {
-    __shared__ double out[2];
-    double s1 = 0.0, s2 = 0.0;
-    for (uint32_t i = threadIdx.x; i < nparts; i += RED_THREADS) {
-        s1 += part[(size_t)i * 2];
-        s2 += part[(size_t)i * 2 + 1];
-    }
-    block_reduce2_store(s1, s2, out);
-    __syncthreads();
     if (threadIdx.x != 0) return;
     const uint32_t sweep = sc->sweep;
     const double rm = Nt ? sqrt(out[0] / (double)Nt) : 0.0;
@@ -713,19 +708,19 @@ void launch_export_factors(Model& m, const Side& s, float* d_out, bool dim_major
 void launch_rebuild(Model& m, cudaStream_t st)
 {
     rebuild_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.csr_urow, m.us.idx, m.csr_r, m.us.e, m.us.F, m.it.F, m.us.bias, m.it.bias, m.sc, m.I,
-                                                         m.J, m.KB, m.N, m.red_part);
+                                                         m.J, m.KB, m.n_csr, m.red_part);
     m.launches++;
 }
 
 void launch_stats(Model& m, cudaStream_t st)
 {
-    stats_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.us.e, m.N, m.red_part);
+    stats_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.us.e, m.n_csr, m.red_part);
     m.launches++;
 }
 
 void launch_global_hypers(Model& m, cudaStream_t st)
 {
-    global_hypers_kernel<<<1, RED_THREADS, 0, st>>>(m.sc, m.red_part, m.red_blocks, m.N, m.cfg.priors, m.cfg.sample_mode, m.cfg.seed);
+    global_hypers_kernel<<<1, 32, 0, st>>>(m.sc, m.red2, m.N, m.cfg.priors, m.cfg.sample_mode, m.cfg.seed);
     m.launches++;
 }
 
@@ -844,20 +839,70 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift)
     }
 }
 
-void launch_permute(Model& m, bool csr_to_csc, cudaStream_t st)
+// Residual between the two slot orders.  One GPU: a gather through perm.  G GPUs: every value moves from the rank that owns
+// its user to the rank that owns its item -- pack in the destination's CSC order, one grouped NCCL send/recv over NVLink,
+// unpack through recv_pos (plan.cpp).
+int launch_permute(Model& m, bool csr_to_csc, cudaStream_t st)
 {
-    const uint32_t g = grid_for(m.N, 256, m.sm_count * 16);
-    if (csr_to_csc) permute_gather_kernel<<<g, 256, 0, st>>>(m.us.e, m.perm, m.it.e, m.N);
-    else permute_scatter_kernel<<<g, 256, 0, st>>>(m.it.e, m.perm, m.us.e, m.N);
+    if (m.world == 1) {
+        const uint32_t g = grid_for(m.N, 256, m.sm_count * 16);
+        if (csr_to_csc) permute_gather_kernel<<<g, 256, 0, st>>>(m.us.e, m.perm, m.it.e, m.N);
+        else permute_scatter_kernel<<<g, 256, 0, st>>>(m.it.e, m.perm, m.us.e, m.N);
+        m.launches++;
+        return 0;
+    }
+    const uint32_t gs = grid_for(m.n_csr, 256, m.sm_count * 16), gr = grid_for(m.n_csc, 256, m.sm_count * 16);
+    int rc;
+    if (csr_to_csc) {
+        permute_gather_kernel<<<gs, 256, 0, st>>>(m.us.e, m.send_idx, m.sendbuf, m.n_csr);
+        rc = comm_alltoallv_f32(m.comm, m.sendbuf, m.send_off.data(), m.send_cnt.data(), m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), st, m.err);
+        permute_gather_kernel<<<gr, 256, 0, st>>>(m.recvbuf, m.recv_pos, m.it.e, m.n_csc);
+    } else {
+        permute_scatter_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos, m.recvbuf, m.n_csc);
+        rc = comm_alltoallv_f32(m.comm, m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), m.sendbuf, m.send_off.data(), m.send_cnt.data(), st, m.err);
+        permute_scatter_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx, m.us.e, m.n_csr);
+    }
+    m.launches += 2;
+    return rc;
+}
+
+int launch_reduce_pair(Model& m, cudaStream_t st)
+{
+    reduce_pair_kernel<<<1, RED_THREADS, 0, st>>>(m.red_part, m.red_blocks, m.red2);
     m.launches++;
+    if (m.world > 1) return comm_allreduce_sum_f64(m.comm, m.red2, 2, st, m.err);
+    return 0;
+}
+
+int launch_allgather_side(Model& m, Side& s, cudaStream_t st)
+{
+    if (m.world == 1) return 0;
+    const std::vector<uint32_t>& bd = (&s == &m.us) ? m.ub : m.ib;
+    std::vector<size_t> off(m.world), cnt(m.world), off8(m.world), cnt8(m.world);
+    for (int q = 0; q < m.world; ++q) {
+        off[q] = bd[q];
+        cnt[q] = bd[q + 1] - bd[q];
+        off8[q] = off[q] * 8;
+        cnt8[q] = cnt[q] * 8;
+    }
+    int rc = comm_allgatherv_strided_f32(m.comm, s.F, (size_t)s.n * 8, (int)m.KB, off8.data(), cnt8.data(), st, m.err);
+    if (rc) return rc;
+    return comm_allgatherv_f32(m.comm, s.bias, off.data(), cnt.data(), st, m.err);
 }
 
 void launch_eval(Model& m, cudaStream_t st)
 {
-    eval_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.t_user, m.t_item, m.t_r, m.t_sum, m.us.F, m.it.F, m.us.bias, m.it.bias, m.sc, m.I, m.J, m.KB,
-                                                      m.Nt, m.cfg.burn_in, (float)m.cfg.clamp_lo, (float)m.cfg.clamp_hi, m.red_part);
-    eval_final_kernel<<<1, RED_THREADS, 0, st>>>(m.sc, m.red_part, m.red_blocks, m.Nt, m.rmse_hist, m.hist_cap);
-    m.launches += 2;
+    const uint64_t t0 = m.t_begin, nt = m.t_end - m.t_begin;   // this rank's slice of the test set
+    eval_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.t_user + t0, m.t_item + t0, m.t_r + t0, m.t_sum + t0, m.us.F, m.it.F, m.us.bias, m.it.bias,
+                                                      m.sc, m.I, m.J, m.KB, nt, m.cfg.burn_in, (float)m.cfg.clamp_lo, (float)m.cfg.clamp_hi,
+                                                      m.red_part);
+    m.launches++;
+}
+
+void launch_eval_final(Model& m, cudaStream_t st)
+{
+    eval_final_kernel<<<1, 32, 0, st>>>(m.sc, m.red2, m.Nt, m.rmse_hist, m.hist_cap);
+    m.launches++;
 }
 
 }  // namespace sbmf

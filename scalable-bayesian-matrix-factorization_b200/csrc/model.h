@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/sbmf_cuda.h"
+#include "comm.h"
 
 namespace sbmf {
 
@@ -90,6 +91,18 @@ struct Model {
     uint32_t* csc_id = nullptr;       // [N] rating index of each CSC slot
     uint32_t* perm = nullptr;         // [N] CSR slot of each CSC slot
     bool e_in_csc = false;            // where the freshest residual lives
+    // multi-GPU: rank r owns users [ub[r], ub[r+1]) with their CSR slots and items [ib[r], ib[r+1]) with their
+    // CSC slots; every slot array above is then the LOCAL shard, ptr[] is rebased to local slots, factors/biases are replicas
+    Comm comm;
+    int rank = 0, world = 1;
+    uint64_t n_csr = 0, n_csc = 0;    // local slot counts (== N on one GPU)
+    std::vector<uint32_t> ub, ib;     // [world+1] row bounds
+    uint32_t* send_idx = nullptr;     // [n_csr] local CSR slot of each send-buffer position (grouped by destination rank)
+    uint32_t* recv_pos = nullptr;     // [n_csc] receive-buffer position of each local CSC slot (grouped by source rank)
+    float *sendbuf = nullptr, *recvbuf = nullptr;
+    std::vector<size_t> send_off, send_cnt, recv_off, recv_cnt;
+    uint64_t t_begin = 0, t_end = 0;  // this rank's slice of the test set
+    double* red2 = nullptr;           // [2] reduced (and all-reduced) pair of sums: (sum e, sum e^2) or the two squared-error sums
     // test set
     uint32_t *t_user = nullptr, *t_item = nullptr;
     float* t_r = nullptr;
@@ -131,8 +144,11 @@ void launch_global_hypers(Model& m, cudaStream_t st);    // [T]:366-410 (final r
 void launch_dim_hypers(Model& m, cudaStream_t st);       // [T]:415-467
 void launch_bias_hypers(Model& m, cudaStream_t st);      // [T]:469-511
 void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift);   // [T]:514-558 / 563-606
-void launch_permute(Model& m, bool csr_to_csc, cudaStream_t st);
-void launch_eval(Model& m, cudaStream_t st);             // [T]:610-636
+int launch_permute(Model& m, bool csr_to_csc, cudaStream_t st);   // one GPU: gather through perm; else all-to-all over NVLink
+int launch_reduce_pair(Model& m, cudaStream_t st);                // red_part -> red2 (+ all-reduce over ranks)
+int launch_allgather_side(Model& m, Side& s, cudaStream_t st);    // replicate the rows each rank just updated (factors + bias)
+void launch_eval(Model& m, cudaStream_t st);             // [T]:610-636: prediction + partial squared errors of this rank's slice
+void launch_eval_final(Model& m, cudaStream_t st);       // RMSE from the reduced sums, history, sweep counter
 
 }  // namespace sbmf
 

@@ -109,6 +109,10 @@ void free_storage(Model& m)
     cudaFree(m.csr_urow); cudaFree(m.csr_r); cudaFree(m.csr_id); cudaFree(m.csc_id); cudaFree(m.perm);
     m.csr_urow = nullptr; m.csr_r = nullptr; m.csr_id = nullptr; m.csc_id = nullptr; m.perm = nullptr;
     cudaFree(m.red_part); m.red_part = nullptr;
+    cudaFree(m.red2); m.red2 = nullptr;
+    cudaFree(m.send_idx); cudaFree(m.recv_pos); cudaFree(m.sendbuf); cudaFree(m.recvbuf);
+    m.send_idx = m.recv_pos = nullptr; m.sendbuf = m.recvbuf = nullptr;
+    m.n_csr = m.n_csc = 0;
     m.have_train = false;
     m.have_factors = false;
     m.N = 0;
@@ -124,7 +128,7 @@ void free_test(Model& m)
 
 // Row work lists: resident bins by row length, heavy rows cut into slices.  Built on the host from the row
 // pointer (one-time; the order of rows inside a list does not influence any result).
-static int build_worklists(Model& m, Side& s)
+static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
 {
     std::vector<int64_t> ptr((size_t)s.n + 1);
     CK(cudaMemcpy(ptr.data(), s.ptr, ptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -132,7 +136,7 @@ static int build_worklists(Model& m, Side& s)
     std::vector<Slice> slices;
     s.nnz_resident = s.nnz_heavy = 0;
     hsp.push_back(0);
-    for (uint32_t r = 0; r < s.n; ++r) {
+    for (uint32_t r = row0; r < row1; ++r) {
         const int64_t c = ptr[r + 1] - ptr[r];
         if (c <= RESIDENT_MAX) {
             int b = 0;
@@ -167,6 +171,79 @@ static int build_worklists(Model& m, Side& s)
         CK(cudaMemcpy(s.slices, slices.data(), slices.size() * sizeof(Slice), cudaMemcpyHostToDevice));
     }
     CK(cudaMemcpy(s.heavy_slice_ptr, hsp.data(), hsp.size() * 4, cudaMemcpyHostToDevice));
+    return SBMF_OK;
+}
+
+__global__ void rebase_kernel(int64_t* ptr, uint32_t n, int64_t base)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= n) ptr[r] -= base;
+}
+
+template <typename T>
+static cudaError_t slice_inplace(T*& arr, uint64_t off, uint64_t cnt)
+{
+    T* loc = nullptr;
+    cudaError_t e = dmalloc(&loc, cnt);
+    if (e != cudaSuccess) return e;
+    if (cnt) e = cudaMemcpy(loc, arr + off, cnt * sizeof(T), cudaMemcpyDeviceToDevice);
+    cudaFree(arr);
+    arr = loc;
+    return e;
+}
+
+// multi-GPU: cut the global layout into this rank's CSR shard (its users) and CSC shard (its items) and plan the residual
+// all-to-all (plan.cpp).  Every rank built the same global layout from the same COO, so all plans agree.
+extern "C" int sbmf_cuda_plan_shards(const int64_t* ptr, uint32_t n_rows, int world, uint32_t* bounds);
+extern "C" int sbmf_cuda_plan_exchange(uint64_t n, const uint32_t* perm, int world, int rank, const int64_t* csr_bounds, const int64_t* csc_bounds,
+                                       uint32_t* send_idx, int64_t* send_counts, uint32_t* recv_pos, int64_t* recv_counts);
+
+static int shard_storage(Model& m)
+{
+    const int G = m.world, r = m.rank;
+    std::vector<int64_t> up((size_t)m.I + 1), ip((size_t)m.J + 1);
+    CK(cudaMemcpy(up.data(), m.us.ptr, up.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ip.data(), m.it.ptr, ip.size() * 8, cudaMemcpyDeviceToHost));
+    m.ub.assign(G + 1, 0);
+    m.ib.assign(G + 1, 0);
+    sbmf_cuda_plan_shards(up.data(), m.I, G, m.ub.data());
+    sbmf_cuda_plan_shards(ip.data(), m.J, G, m.ib.data());
+    std::vector<int64_t> cb(G + 1), tb(G + 1);
+    for (int q = 0; q <= G; ++q) {
+        cb[q] = up[m.ub[q]];
+        tb[q] = ip[m.ib[q]];
+    }
+    const uint64_t c0 = (uint64_t)cb[r], c1 = (uint64_t)cb[r + 1], t0 = (uint64_t)tb[r], t1 = (uint64_t)tb[r + 1];
+    m.n_csr = c1 - c0;
+    m.n_csc = t1 - t0;
+    {
+        std::vector<uint32_t> perm(m.N ? m.N : 1), sidx(m.n_csr ? m.n_csr : 1), rpos(m.n_csc ? m.n_csc : 1);
+        std::vector<int64_t> sc(G), rc(G);
+        CK(cudaMemcpy(perm.data(), m.perm, m.N * 4, cudaMemcpyDeviceToHost));
+        if (sbmf_cuda_plan_exchange(m.N, perm.data(), G, r, cb.data(), tb.data(), sidx.data(), sc.data(), rpos.data(), rc.data()) != SBMF_OK) {
+            m.err = "set_train: exchange planning failed (internal)";
+            return SBMF_ERR_INVALID;
+        }
+        m.send_off.assign(G, 0); m.send_cnt.assign(G, 0); m.recv_off.assign(G, 0); m.recv_cnt.assign(G, 0);
+        size_t so = 0, ro = 0;
+        for (int q = 0; q < G; ++q) {
+            m.send_off[q] = so; m.send_cnt[q] = (size_t)sc[q]; so += (size_t)sc[q];
+            m.recv_off[q] = ro; m.recv_cnt[q] = (size_t)rc[q]; ro += (size_t)rc[q];
+        }
+        CK(dmalloc(&m.send_idx, m.n_csr)); CK(dmalloc(&m.recv_pos, m.n_csc));
+        CK(dmalloc(&m.sendbuf, m.n_csr)); CK(dmalloc(&m.recvbuf, m.n_csc));
+        CK(cudaMemcpy(m.send_idx, sidx.data(), m.n_csr * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(m.recv_pos, rpos.data(), m.n_csc * 4, cudaMemcpyHostToDevice));
+    }
+    cudaFree(m.perm);
+    m.perm = nullptr;
+    CK(slice_inplace(m.us.idx, c0, m.n_csr)); CK(slice_inplace(m.us.e, c0, m.n_csr)); CK(slice_inplace(m.csr_urow, c0, m.n_csr));
+    CK(slice_inplace(m.csr_r, c0, m.n_csr)); CK(slice_inplace(m.csr_id, c0, m.n_csr));
+    CK(slice_inplace(m.it.idx, t0, m.n_csc)); CK(slice_inplace(m.it.e, t0, m.n_csc)); CK(slice_inplace(m.csc_id, t0, m.n_csc));
+    rebase_kernel<<<(m.I + 256) / 256, 256, 0, m.s_main>>>(m.us.ptr, m.I, (int64_t)c0);
+    rebase_kernel<<<(m.J + 256) / 256, 256, 0, m.s_main>>>(m.it.ptr, m.J, (int64_t)t0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(m.s_main));
     return SBMF_OK;
 }
 
@@ -254,12 +331,17 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
 #undef CKC
 
     int rc;
-    if ((rc = build_worklists(m, m.us)) != SBMF_OK) return rc;
-    if ((rc = build_worklists(m, m.it)) != SBMF_OK) return rc;
+    m.n_csr = m.n_csc = n;
+    m.ub.assign(2, 0); m.ib.assign(2, 0);
+    m.ub[1] = num_users; m.ib[1] = num_items;
+    if (m.world > 1 && (rc = shard_storage(m)) != SBMF_OK) return rc;
+    if ((rc = build_worklists(m, m.us, m.ub[m.rank], m.ub[m.rank + 1])) != SBMF_OK) return rc;
+    if ((rc = build_worklists(m, m.it, m.ib[m.rank], m.ib[m.rank + 1])) != SBMF_OK) return rc;
     if ((rc = alloc_side_state(m, m.us)) != SBMF_OK) return rc;
     if ((rc = alloc_side_state(m, m.it)) != SBMF_OK) return rc;
     m.red_blocks = (uint32_t)m.sm_count * 8;
     CK(dmalloc(&m.red_part, (size_t)m.red_blocks * 2));
+    CK(dmalloc(&m.red2, 2));
     m.have_train = true;
     m.e_in_csc = false;
     return SBMF_OK;
@@ -277,6 +359,8 @@ int build_test(Model& m, uint64_t nt, const uint32_t* user, const uint32_t* item
     }
     CK(cudaMemsetAsync(m.t_sum, 0, (nt ? nt : 1) * 8, m.s_main));
     CK(cudaStreamSynchronize(m.s_main));
+    m.t_begin = nt * (uint64_t)m.rank / (uint64_t)m.world;
+    m.t_end = nt * (uint64_t)(m.rank + 1) / (uint64_t)m.world;
     m.have_test = true;
     return SBMF_OK;
 }

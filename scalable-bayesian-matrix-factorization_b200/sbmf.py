@@ -90,6 +90,8 @@ def load_library(path=None):
     lib.sbmf_cuda_last_sweep_call_ms.argtypes = [C.c_void_p, P(C.c_double)]
     lib.sbmf_cuda_host_alloc.argtypes = [P(C.c_void_p), C.c_size_t]
     lib.sbmf_cuda_host_free.argtypes = [C.c_void_p]
+    lib.sbmf_cuda_plan_shards.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+    lib.sbmf_cuda_plan_exchange.argtypes = [C.c_uint64, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
     lib.sbmf_cuda_synth_generate.argtypes = [P(SynthSpec), P(C.c_uint64), P(C.c_uint64)] + [C.c_void_p] * 6
     lib.sbmf_cuda_synth_last_error.restype = C.c_char_p
     if path is None:
@@ -101,7 +103,10 @@ def default_config(**kw):
     cfg = Config()
     load_library().sbmf_cuda_config_default(C.byref(cfg))
     for k, v in kw.items():
-        setattr(cfg, k, v)
+        if k == "nccl_id":
+            C.memmove(cfg.nccl_id, v, 128)
+        else:
+            setattr(cfg, k, v)
     return cfg
 
 
@@ -226,6 +231,34 @@ class SbmfModel:
 
     def synchronize(self):
         self._ck(self.lib.sbmf_cuda_synchronize(self.h))
+
+
+def nccl_unique_id():
+    """128-byte ncclUniqueId (rank 0 creates it, the host program ships it to the other ranks)."""
+    buf = (C.c_uint8 * 128)()
+    lib = load_library()
+    if lib.sbmf_cuda_nccl_unique_id(buf) != 0:
+        raise SbmfError(-5, lib.sbmf_cuda_last_error(None).decode())
+    return bytes(buf)
+
+
+def plan_shards(ptr, world):
+    ptr = np.ascontiguousarray(ptr, np.int64)
+    b = np.empty(world + 1, np.uint32)
+    rc = load_library().sbmf_cuda_plan_shards(_ptr(ptr), ptr.size - 1, world, _ptr(b))
+    assert rc == 0
+    return b
+
+
+def plan_exchange(perm, world, rank, csr_bounds, csc_bounds):
+    perm = np.ascontiguousarray(perm, np.uint32)
+    cb, tb = np.ascontiguousarray(csr_bounds, np.int64), np.ascontiguousarray(csc_bounds, np.int64)
+    send_idx = np.empty(int(cb[rank + 1] - cb[rank]), np.uint32)
+    recv_pos = np.empty(int(tb[rank + 1] - tb[rank]), np.uint32)
+    sc, rc_ = np.empty(world, np.int64), np.empty(world, np.int64)
+    rc = load_library().sbmf_cuda_plan_exchange(perm.size, _ptr(perm), world, rank, _ptr(cb), _ptr(tb), _ptr(send_idx), _ptr(sc), _ptr(recv_pos), _ptr(rc_))
+    assert rc == 0, rc
+    return send_idx, sc, recv_pos, rc_
 
 
 def pinned_empty(n, dtype):

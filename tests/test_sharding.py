@@ -1,0 +1,124 @@
+"""CPU tests of the multi-GPU host logic (csrc/plan.cpp through the C ABI; no GPU): nnz-balanced shard bounds and the residual
+all-to-all plan, including a real 2-process exchange over torch.distributed/gloo that must reproduce the single-GPU permute."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "scalable-bayesian-matrix-factorization_b200")
+
+
+@pytest.fixture(scope="module")
+def sbmf_mod():
+    subprocess.run(["make", "-C", PKG], check=True, capture_output=True)
+    import sbmf
+    return sbmf
+
+
+def layout_of(d):
+    o = orc.Oracle(d["train_user"], d["train_item"], d["train_rating"], d["test_user"], d["test_item"], d["test_rating"],
+                   d["num_users"], d["num_items"], 4)
+    return o.layout()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_plan_shards_balanced_and_complete(world, ml100k, sbmf_mod):
+    L = layout_of(ml100k)
+    for ptr in (L["row_ptr"], L["col_ptr"]):
+        b = sbmf_mod.plan_shards(ptr, world)
+        assert b[0] == 0 and b[-1] == ptr.size - 1 and np.all(np.diff(b.astype(np.int64)) >= 0)
+        nnz = np.diff(ptr[b.astype(np.int64)])
+        assert nnz.sum() == ptr[-1]
+        maxrow = np.diff(ptr).max()
+        assert nnz.max() <= ptr[-1] / world + maxrow     # no shard exceeds the ideal by more than one row
+
+
+def test_plan_shards_degenerate(sbmf_mod):
+    ptr = np.array([0, 0, 0, 10, 10], np.int64)          # one non-empty row, 4 ranks
+    b = sbmf_mod.plan_shards(ptr, 4)
+    assert b[0] == 0 and b[-1] == 4 and np.diff(ptr[b.astype(np.int64)]).sum() == 10
+    b = sbmf_mod.plan_shards(np.zeros(6, np.int64), 3)   # empty matrix
+    assert b[0] == 0 and b[-1] == 5
+
+
+@pytest.mark.parametrize("case", ["ml100k", "tiny"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_plan_exchange_reproduces_permute(case, world, ml100k, tiny, sbmf_mod):
+    """Simulate all ranks in one process: pack / 'send' / unpack must equal e_csc = e_csr[perm]."""
+    d = ml100k if case == "ml100k" else tiny
+    L = layout_of(d)
+    N = L["perm"].size
+    perm = L["perm"].astype(np.uint32)
+    ub, ib = sbmf_mod.plan_shards(L["row_ptr"], world), sbmf_mod.plan_shards(L["col_ptr"], world)
+    cb, tb = L["row_ptr"][ub.astype(np.int64)], L["col_ptr"][ib.astype(np.int64)]
+    e_csr = np.random.RandomState(0).standard_normal(N).astype(np.float32)
+    plans = [sbmf_mod.plan_exchange(perm, world, r, cb, tb) for r in range(world)]
+    for r in range(world):
+        assert plans[r][1].sum() == cb[r + 1] - cb[r] and plans[r][3].sum() == tb[r + 1] - tb[r]
+        assert sorted(plans[r][0].tolist()) == list(range(int(cb[r + 1] - cb[r])))       # every local slot sent exactly once
+    for r in range(world):           # receiver r
+        recv = []
+        for q in range(world):       # from sender q: q's send buffer segment for destination r
+            send_idx, sc = plans[q][0], plans[q][1]
+            off = int(sc[:r].sum())
+            seg = e_csr[cb[q]:cb[q + 1]][send_idx[off:off + int(sc[r])]]
+            assert seg.size == plans[r][3][q]
+            recv.append(seg)
+        recvbuf = np.concatenate(recv) if recv else np.empty(0, np.float32)
+        e_csc_local = recvbuf[plans[r][2]]
+        assert np.array_equal(e_csc_local, e_csr[perm][tb[r]:tb[r + 1]])
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["SBMF_PKG"]); sys.path.insert(0, os.environ["SBMF_TESTS"])
+import sbmf, oracle_py as orc
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+d = np.load(os.path.join(os.environ["SBMF_TESTS"], "golden", "ml100k.npz"))
+tu, ti, tr = d["train_user"].astype(np.uint32), d["train_item"].astype(np.uint32), d["train_rating"].astype(np.float64)
+o = orc.Oracle(tu, ti, tr, tu[:1], ti[:1], tr[:1], 943, 1682, 4)
+L = o.layout()
+perm = L["perm"].astype(np.uint32)
+ub, ib = sbmf.plan_shards(L["row_ptr"], world), sbmf.plan_shards(L["col_ptr"], world)
+cb, tb = L["row_ptr"][ub.astype(np.int64)], L["col_ptr"][ib.astype(np.int64)]
+send_idx, sc, recv_pos, rc = sbmf.plan_exchange(perm, world, rank, cb, tb)
+e_csr = np.random.RandomState(0).standard_normal(perm.size).astype(np.float32)     # same on every rank
+mine = e_csr[cb[rank]:cb[rank + 1]]
+sendbuf = torch.from_numpy(mine[send_idx].copy())
+recvbuf = torch.empty(int(rc.sum()), dtype=torch.float32)
+ins = list(torch.split(sendbuf, [int(x) for x in sc]))
+outs = list(torch.split(recvbuf, [int(x) for x in rc]))
+reqs = []
+for q in range(world):           # all-to-all-v from send/recv pairs (gloo has no all_to_all)
+    if q == rank:
+        outs[q].copy_(ins[q])
+        continue
+    reqs.append(dist.isend(ins[q].contiguous(), q))
+    reqs.append(dist.irecv(outs[q], q))
+for rq in reqs:
+    rq.wait()
+got = torch.cat(outs).numpy()[recv_pos]
+want = e_csr[perm][tb[rank]:tb[rank + 1]]
+ok = np.array_equal(got, want)
+flag = torch.tensor([1 if ok else 0]); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.barrier(); dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 3)
+'''
+
+
+def test_two_process_gloo_exchange(tmp_path, sbmf_mod):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, SBMF_PKG=PKG, SBMF_TESTS=os.path.join(ROOT, "tests"), MASTER_ADDR="127.0.0.1", MASTER_PORT="29541", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
+    rcs = [p.wait(timeout=240) for p in procs]
+    assert rcs == [0, 0], rcs
