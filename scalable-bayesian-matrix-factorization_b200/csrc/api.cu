@@ -129,6 +129,7 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
     m.it.site_f = SITE_V; m.it.site_b = SITE_BJ; m.it.site_sigma_k = SITE_SIGMA_V; m.it.site_mu_k = SITE_MU_V;
     m.it.site_sigma_b = SITE_SIGMA_BJ; m.it.site_mu_b = SITE_MU_BJ; m.it.prior = 1; m.it.prior_b = 5;
     bool ok = cudaSetDevice(m.device) == cudaSuccess;
+    if (ok) init_constant_tables();
     ok = ok && cudaStreamCreateWithFlags(&m.s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&m.s_aux, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming) == cudaSuccess;

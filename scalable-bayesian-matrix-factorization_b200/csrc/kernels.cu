@@ -29,7 +29,7 @@ struct PhaseArgs {
     float* e;
     float* Fself;
     const float* Fother;
-    uint32_t n_self, n_other;
+    uint32_t ns_self, ns_other;   // rows per factor block INCLUDING the all-zero pad row at index n (gather target of empty slots)
     float* bias;
     const float* mu_b;
     const float* sigma_b;
@@ -98,13 +98,63 @@ __device__ __forceinline__ void solve_block(const float* tot, const f8& uo, cons
 // --------------------------------------------------------------------------------------------------------
 // Resident rows: WARPS warps own one row, each lane keeps RPL (idx, e, f) triples in registers.
 // blocks [b_begin, b_end) are processed in one launch; do_bias runs the bias half-step ([T]:517-534 / 566-582) first.
+//
+// Per block: gather f (empty slots point at the all-zero pad row, so they need no masking), accumulate g/G, transposed
+// warp reduction, sums to shared memory as g[8] + a FULL symmetric G[8][8], then the 8 sequential coordinate updates run
+// lane-parallel: lane k owns dimension k (its row of G, its 1/lambda), and step l broadcasts lane l's delta to the lanes
+// l' > l, which fold it into their B.  The row's noise is drawn 4 blocks at a time (lane -> one of 32 dimensions).
+constexpr int SOLVE_SMEM = 80;   // g[8], G[64], 8 floats of slack for the 4 padding accumulators
+
+// smem offset(s) of packed accumulator p: g[k] -> k; G[k][l] -> 8 + 8k + l and its mirror
+__constant__ uint8_t c_pk_a[NACC];
+__constant__ uint8_t c_pk_b[NACC];
+
+struct SolveOut {
+    float d[8];   // u_old - u_new for the 8 dimensions of the block (all lanes)
+    float mine;   // d[lane & 7]
+};
+
+__device__ __forceinline__ SolveOut solve_lanes(const float* sm, const PhaseArgs& a, int b, uint32_t row, float zq, float alpha, int lane)
+{
+    const int kq = lane & 7;
+    const float4 g0 = *reinterpret_cast<const float4*>(sm + 8 + kq * 8);
+    const float4 g1 = *reinterpret_cast<const float4*>(sm + 8 + kq * 8 + 4);
+    const float Grow[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float A = sm[8 + kq * 9];
+    const float gk = sm[kq];
+    float* Fs = a.Fself + ((size_t)b * a.ns_self + row) * 8;
+    const float uo = Fs[kq];
+    const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
+    const float s = 1.0f / (sig + alpha * A);
+    const float smu = sig * mu;
+    const bool live = (uint32_t)(b * 8 + kq) < a.K;   // padding dimensions of the last block stay exactly zero
+    const float z = __shfl_sync(0xffffffffu, zq, ((b & 3) << 3) + kq);
+    float B = fmaf(A, uo, gk);
+    SolveOut o;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        const float mean = s * fmaf(alpha, B, smu);
+        float cand = live ? uo - draw_f32(a.mode, mean, s, z) : 0.f;
+        const float dl = __shfl_sync(0xffffffffu, cand, l);
+        o.d[l] = dl;
+        if (kq > l) B = fmaf(dl, Grow[l], B);
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) mine = (kq == l) ? o.d[l] : mine;
+    o.mine = mine;
+    if (lane < 8) Fs[kq] = uo - mine;
+    return o;
+}
+
 template <int RPL, int WARPS>
-__global__ void __launch_bounds__(WARPS == 1 ? 256 : WARPS * 32)
+__global__ void __launch_bounds__(WARPS == 1 ? 128 : WARPS * 32)
 row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows, int b_begin, int b_end, int do_bias)
 {
-    constexpr int WPC = (WARPS == 1) ? 8 : WARPS;   // warps per CTA
-    __shared__ __align__(16) float s_tot[(WARPS == 1) ? WPC : 1][NACC];
+    constexpr int WPC = (WARPS == 1) ? 4 : WARPS;   // warps per CTA
+    __shared__ __align__(16) float s_tot[(WARPS == 1) ? WPC : 1][SOLVE_SMEM];
     __shared__ __align__(16) float s_part[(WARPS == 1) ? 1 : WARPS][NACC];
+    __shared__ float s_d[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t r_idx = (WARPS == 1) ? blockIdx.x * WPC + warp : blockIdx.x;
     if (r_idx >= nrows) return;   // WARPS == 1: whole warp leaves; no block-wide barrier is used in that shape
@@ -117,16 +167,16 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 
     const float alpha = a.sc->alpha_f;
     const uint32_t sweep = a.sc->sweep;
+    const uint32_t pad_row = a.ns_other - 1;
 
     uint32_t id[RPL];
     float e[RPL];
-    bool valid[RPL];
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
         const int p = r * TPR + t_in_row;
-        valid[r] = p < c;
-        id[r] = valid[r] ? a.idx[beg + p] : 0u;
-        e[r] = valid[r] ? a.e[beg + p] : 0.f;
+        const bool valid = p < c;
+        id[r] = valid ? a.idx[beg + p] : pad_row;
+        e[r] = valid ? a.e[beg + p] : 0.f;
     }
 
     if (do_bias) {
@@ -134,7 +184,7 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         float t = 0.f;
 #pragma unroll
         for (int r = 0; r < RPL; ++r)
-            if (valid[r]) {
+            if (id[r] != pad_row) {
                 e[r] += shift;
                 t += e[r];
             }
@@ -156,24 +206,19 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         const float d = bo - bn;
 #pragma unroll
         for (int r = 0; r < RPL; ++r)
-            if (valid[r]) e[r] += d;
+            if (id[r] != pad_row) e[r] += d;
         if (t_in_row == 0) a.bias[row] = bn;
     }
 
+    float zq = 0.f;
     for (int b = b_begin; b < b_end; ++b) {
-        // this row's noise for the 8 dimensions of the block: lane k draws dimension 8b+k
-        float zl = 0.f;
-        if (a.mode != SAMPLE_ZERO && lane < 8) zl = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)(b * 8 + lane), sweep));
-        const float* Fo = a.Fother + (size_t)b * a.n_other * 8;
+        // this row's noise, 4 blocks at a time: lane l draws dimension 32*(b/4) + l
+        if (a.mode != SAMPLE_ZERO && (((b & 3) == 0) || b == b_begin))
+            zq = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)((b & ~3) * 8 + lane), sweep));
+        const float* Fo = a.Fother + (size_t)b * a.ns_other * 8;
         f8 f[RPL];
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            if (valid[r]) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
-            else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) f[r].v[k] = 0.f;
-            }
-        }
+        for (int r = 0; r < RPL; ++r) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
         float acc[NACC];
 #pragma unroll
         for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
@@ -183,9 +228,11 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         const int base = reduce_scatter_base(lane);
         if (WARPS == 1) {
             if ((lane & 1) == 0) {
-                tot[base] = acc[0];
-                tot[base + 1] = acc[1];
-                tot[base + 2] = acc[2];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    tot[c_pk_a[base + i]] = acc[i];
+                    tot[c_pk_b[base + i]] = acc[i];
+                }
             }
             __syncwarp();
         } else {
@@ -196,24 +243,28 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
             }
             __syncthreads();
             if (threadIdx.x < NACC) {
-                float s = 0.f;
+                float sum = 0.f;
 #pragma unroll
-                for (int w = 0; w < WARPS; ++w) s += s_part[w][threadIdx.x];
-                tot[threadIdx.x] = s;
+                for (int w = 0; w < WARPS; ++w) sum += s_part[w][threadIdx.x];
+                tot[c_pk_a[threadIdx.x]] = sum;
+                tot[c_pk_b[threadIdx.x]] = sum;
             }
             __syncthreads();
         }
-        float z[8];
+        SolveOut so;
+        if (WARPS == 1) {
+            so = solve_lanes(tot, a, b, row, zq, alpha, lane);
+        } else {   // warp 0 solves and publishes the 8 deltas
+            if (warp == 0) {
+                so = solve_lanes(tot, a, b, row, zq, alpha, lane);
+                if (lane < 8) s_d[lane] = so.mine;
+            }
+            __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) z[k] = __shfl_sync(0xffffffffu, zl, k);
-        float* Fs = a.Fself + ((size_t)b * a.n_self + row) * 8;
-        const f8 uo = ld256(Fs);
-        f8 un;
-        float d[8];
-        solve_block(tot, uo, z, a.sigma_kf + b * 8, a.mu_kf + b * 8, alpha, a.mode, (int)a.K - b * 8, un, d);
+            for (int l = 0; l < 8; ++l) so.d[l] = s_d[l];
+        }
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) e[r] += dot8(f[r], d);
-        if (t_in_row == 0) st256(Fs, un);
+        for (int r = 0; r < RPL; ++r) e[r] += dot8(f[r], so.d);
         if (WARPS == 1) __syncwarp();   // tot is rewritten by the next block
         else __syncthreads();
     }
@@ -221,7 +272,7 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
         const int p = r * TPR + t_in_row;
-        if (valid[r]) a.e[beg + p] = e[r];
+        if (p < c) a.e[beg + p] = e[r];
     }
 }
 
@@ -246,8 +297,8 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
 #pragma unroll
         for (int k = 0; k < 8; ++k) dprev[k] = hdelta[(size_t)sl.hrow * 8 + k];
     }
-    const float* Fp = a.Fother + (size_t)pb * a.n_other * 8;
-    const float* Fc = a.Fother + (size_t)b * a.n_other * 8;
+    const float* Fp = a.Fother + (size_t)pb * a.ns_other * 8;
+    const float* Fc = a.Fother + (size_t)b * a.ns_other * 8;
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
@@ -341,7 +392,7 @@ heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const u
         float z[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) z[k] = __shfl_sync(0xffffffffu, zl, k);
-        float* Fs = a.Fself + ((size_t)b * a.n_self + row) * 8;
+        float* Fs = a.Fself + ((size_t)b * a.ns_self + row) * 8;
         const f8 uo = ld256(Fs);
         f8 un;
         float d[8];
@@ -381,6 +432,7 @@ __device__ __forceinline__ void block_reduce2_store(double s1, double s2, double
     }
 }
 
+// I, J here are the factor strides (rows + 1 pad row)
 __device__ __forceinline__ float dot_blocked(const float* __restrict__ Fu, const float* __restrict__ Fv, uint32_t I, uint32_t J, uint32_t KB,
                                              uint32_t u, uint32_t j)
 {
@@ -475,7 +527,7 @@ global_hypers_kernel(Scalars* sc, const double* __restrict__ red2, uint64_t N, s
 constexpr int HYP_CHUNK = 16384;
 
 __global__ void __launch_bounds__(256)
-dim_hyper_partial_kernel(const float* __restrict__ F, uint32_t n, const double* __restrict__ mu_k, double* __restrict__ part, uint32_t chunks)
+dim_hyper_partial_kernel(const float* __restrict__ F, uint32_t n, uint32_t ns, const double* __restrict__ mu_k, double* __restrict__ part, uint32_t chunks)
 {
     __shared__ double sh[8][16];
     const uint32_t b = blockIdx.y, chunk = blockIdx.x;
@@ -489,7 +541,7 @@ dim_hyper_partial_kernel(const float* __restrict__ F, uint32_t n, const double* 
     const uint32_t r0 = chunk * HYP_CHUNK;
     const uint32_t r1 = min(n, r0 + HYP_CHUNK);
     for (uint32_t r = r0 + threadIdx.x; r < r1; r += 256) {
-        const f8 f = ld256(F + ((size_t)b * n + r) * 8);
+        const f8 f = ld256(F + ((size_t)b * ns + r) * 8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const double u = (double)f.v[k];
@@ -632,19 +684,21 @@ eval_final_kernel(Scalars* sc, const double* __restrict__ out, uint64_t Nt, doub
 __global__ void __launch_bounds__(256)
 init_factors_kernel(float* __restrict__ F, uint32_t n, uint32_t K, uint32_t KB, uint64_t seed, uint32_t site, float stdev)
 {
+    const uint32_t nreal = n - 1;   // n = stride = rows + 1 zero pad row
     const uint64_t total = (uint64_t)KB * n * 8;
     for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
         const uint32_t k8 = (uint32_t)(t & 7);
         const uint64_t br = t >> 3;
         const uint32_t row = (uint32_t)(br % n), b = (uint32_t)(br / n);
         const uint32_t k = b * 8 + k8;
-        F[t] = (k < K) ? stdev * normal_f32(philox_site(seed, site, row, k, 0u)) : 0.f;
+        F[t] = (k < K && row < nreal) ? stdev * normal_f32(philox_site(seed, site, row, k, 0u)) : 0.f;
     }
 }
 
 __global__ void __launch_bounds__(256)
 load_factors_kernel(float* __restrict__ F, const float* __restrict__ src, uint32_t n, uint32_t K, uint32_t KB, int dim_major)
 {
+    const uint32_t nreal = n - 1;   // n = stride = rows + 1 zero pad row
     const uint64_t total = (uint64_t)KB * n * 8;
     for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
         const uint32_t k8 = (uint32_t)(t & 7);
@@ -652,7 +706,7 @@ load_factors_kernel(float* __restrict__ F, const float* __restrict__ src, uint32
         const uint32_t row = (uint32_t)(br % n), b = (uint32_t)(br / n);
         const uint32_t k = b * 8 + k8;
         float v = 0.f;
-        if (k < K) v = dim_major ? src[(size_t)k * n + row] : src[(size_t)row * K + k];
+        if (k < K && row < nreal) v = dim_major ? src[(size_t)k * nreal + row] : src[(size_t)row * K + k];
         F[t] = v;
     }
 }
@@ -670,12 +724,26 @@ export_factors_kernel(const float* __restrict__ F, float* __restrict__ dst, uint
             row = (uint32_t)(t / K);
             k = (uint32_t)(t % K);
         }
-        dst[t] = F[((size_t)(k >> 3) * n + row) * 8 + (k & 7)];
+        dst[t] = F[((size_t)(k >> 3) * (n + 1) + row) * 8 + (k & 7)];
     }
 }
 
 // ========================================================================================================
 // launch wrappers
+void init_constant_tables()
+{
+    uint8_t pa[NACC], pb[NACC];
+    for (int p = 0; p < NACC; ++p) pa[p] = pb[p] = (uint8_t)(72 + (p & 3));   // padding accumulators -> slack
+    for (int k = 0; k < 8; ++k) pa[k] = pb[k] = (uint8_t)k;
+    for (int k = 0; k < 8; ++k)
+        for (int l = k; l < 8; ++l) {
+            pa[gi(k, l)] = (uint8_t)(8 + 8 * k + l);
+            pb[gi(k, l)] = (uint8_t)(8 + 8 * l + k);
+        }
+    cudaMemcpyToSymbol(c_pk_a, pa, NACC);
+    cudaMemcpyToSymbol(c_pk_b, pb, NACC);
+}
+
 static inline uint32_t grid_for(uint64_t n, int threads, int cap)
 {
     uint64_t g = (n + threads - 1) / threads;
@@ -686,15 +754,15 @@ static inline uint32_t grid_for(uint64_t n, int threads, int cap)
 
 void launch_init_factors(Model& m, Side& s, uint32_t site, cudaStream_t st)
 {
-    const uint64_t total = (uint64_t)m.KB * s.n * 8;
-    init_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, s.n, m.K, m.KB, m.cfg.seed, site, (float)m.cfg.init_stdev);
+    const uint64_t total = (uint64_t)m.KB * (s.n + 1) * 8;
+    init_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, s.n + 1, m.K, m.KB, m.cfg.seed, site, (float)m.cfg.init_stdev);
     m.launches++;
 }
 
 void launch_load_factors(Model& m, Side& s, const float* d_src, bool dim_major, cudaStream_t st)
 {
-    const uint64_t total = (uint64_t)m.KB * s.n * 8;
-    load_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, d_src, s.n, m.K, m.KB, dim_major ? 1 : 0);
+    const uint64_t total = (uint64_t)m.KB * (s.n + 1) * 8;
+    load_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, d_src, s.n + 1, m.K, m.KB, dim_major ? 1 : 0);
     m.launches++;
 }
 
@@ -707,8 +775,8 @@ void launch_export_factors(Model& m, const Side& s, float* d_out, bool dim_major
 
 void launch_rebuild(Model& m, cudaStream_t st)
 {
-    rebuild_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.csr_urow, m.us.idx, m.csr_r, m.us.e, m.us.F, m.it.F, m.us.bias, m.it.bias, m.sc, m.I,
-                                                         m.J, m.KB, m.n_csr, m.red_part);
+    rebuild_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.csr_urow, m.us.idx, m.csr_r, m.us.e, m.us.F, m.it.F, m.us.bias, m.it.bias, m.sc, m.I + 1,
+                                                         m.J + 1, m.KB, m.n_csr, m.red_part);
     m.launches++;
 }
 
@@ -727,7 +795,7 @@ void launch_global_hypers(Model& m, cudaStream_t st)
 static void dim_hypers_side(Model& m, Side& s, cudaStream_t st)
 {
     const sbmf_priors& p = m.cfg.priors;
-    dim_hyper_partial_kernel<<<dim3(s.hyp_chunks, m.KB), 256, 0, st>>>(s.F, s.n, s.mu_k, s.hyp_part, s.hyp_chunks);
+    dim_hyper_partial_kernel<<<dim3(s.hyp_chunks, m.KB), 256, 0, st>>>(s.F, s.n, s.n + 1, s.mu_k, s.hyp_part, s.hyp_chunks);
     dim_hyper_final_kernel<<<m.KB, 32, 0, st>>>(s.hyp_part, s.hyp_chunks, s.n, m.K, s.sigma_k, s.mu_k, s.sigma_kf, s.mu_kf, m.sc, p.alpha[s.prior],
                                                 p.beta[s.prior], p.mu[s.prior], p.sigma[s.prior], m.cfg.sample_mode, m.cfg.seed, s.site_sigma_k,
                                                 s.site_mu_k);
@@ -757,7 +825,7 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
     constexpr int RPL = kBins[BIN].rpl, WARPS = kBins[BIN].warps;
     const uint32_t n = self.bin_count[BIN];
     if (!n) return;
-    if (WARPS == 1) row_resident_kernel<RPL, WARPS><<<(n + 7) / 8, 256, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+    if (WARPS == 1) row_resident_kernel<RPL, WARPS><<<(n + 3) / 4, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
     else row_resident_kernel<RPL, WARPS><<<n, WARPS * 32, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
     m.launches++;
 }
@@ -771,8 +839,8 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift)
     a.e = self.e;
     a.Fself = self.F;
     a.Fother = other.F;
-    a.n_self = self.n;
-    a.n_other = other.n;
+    a.ns_self = self.n + 1;
+    a.ns_other = other.n + 1;
     a.bias = self.bias;
     a.mu_b = self.mu_b;
     a.sigma_b = self.sigma_b;
@@ -885,7 +953,7 @@ int launch_allgather_side(Model& m, Side& s, cudaStream_t st)
         off8[q] = off[q] * 8;
         cnt8[q] = cnt[q] * 8;
     }
-    int rc = comm_allgatherv_strided_f32(m.comm, s.F, (size_t)s.n * 8, (int)m.KB, off8.data(), cnt8.data(), st, m.err);
+    int rc = comm_allgatherv_strided_f32(m.comm, s.F, (size_t)(s.n + 1) * 8, (int)m.KB, off8.data(), cnt8.data(), st, m.err);
     if (rc) return rc;
     return comm_allgatherv_f32(m.comm, s.bias, off.data(), cnt.data(), st, m.err);
 }
@@ -894,7 +962,7 @@ void launch_eval(Model& m, cudaStream_t st)
 {
     const uint64_t t0 = m.t_begin, nt = m.t_end - m.t_begin;   // this rank's slice of the test set
     eval_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.t_user + t0, m.t_item + t0, m.t_r + t0, m.t_sum + t0, m.us.F, m.it.F, m.us.bias, m.it.bias,
-                                                      m.sc, m.I, m.J, m.KB, nt, m.cfg.burn_in, (float)m.cfg.clamp_lo, (float)m.cfg.clamp_hi,
+                                                      m.sc, m.I + 1, m.J + 1, m.KB, nt, m.cfg.burn_in, (float)m.cfg.clamp_lo, (float)m.cfg.clamp_hi,
                                                       m.red_part);
     m.launches++;
 }

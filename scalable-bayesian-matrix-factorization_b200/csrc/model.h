@@ -134,6 +134,7 @@ void free_storage(Model& m);
 void free_test(Model& m);
 
 // ---- kernels.cu: launch wrappers (all asynchronous on the given stream)
+void init_constant_tables();   // once per device, after cudaSetDevice
 void launch_init_factors(Model& m, Side& s, uint32_t site, cudaStream_t st);
 // host layout -> K8-blocked.  dim_major: src is [K][n] (V of [T]:234-237), else [n][K] (U of [T]:229-232)
 void launch_load_factors(Model& m, Side& s, const float* d_src, bool dim_major, cudaStream_t st);

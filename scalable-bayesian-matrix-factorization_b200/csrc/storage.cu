@@ -249,7 +249,7 @@ static int shard_storage(Model& m)
 
 static int alloc_side_state(Model& m, Side& s)
 {
-    CK(dmalloc(&s.F, (size_t)m.KB * s.n * 8));
+    CK(dmalloc(&s.F, (size_t)m.KB * (s.n + 1) * 8));   // + the all-zero pad row
     CK(dmalloc(&s.bias, s.n)); CK(dmalloc(&s.mu_b, s.n)); CK(dmalloc(&s.sigma_b, s.n));
     CK(dmalloc(&s.sigma_k, m.KP)); CK(dmalloc(&s.mu_k, m.KP)); CK(dmalloc(&s.sigma_kf, m.KP)); CK(dmalloc(&s.mu_kf, m.KP));
     s.hyp_chunks = (s.n + 16383) / 16384;
