@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "model.h"
@@ -103,9 +104,10 @@ __device__ __forceinline__ void solve_block(const float* tot, const f8& uo, cons
 // warp reduction, sums to shared memory as g[8] + a FULL symmetric G[8][8], then the 8 sequential coordinate updates run
 // lane-parallel: lane k owns dimension k (its row of G, its 1/lambda), and step l broadcasts lane l's delta to the lanes
 // l' > l, which fold it into their B.  The row's noise is drawn 4 blocks at a time (lane -> one of 32 dimensions).
-constexpr int SOLVE_SMEM = 80;   // g[8], G[64], 8 floats of slack for the 4 padding accumulators
+constexpr int G_STRIDE = 12;                      // row stride of the symmetric G in shared memory: LDS.128-aligned and bank-conflict-free
+constexpr int SOLVE_SMEM = 8 + 8 * G_STRIDE + 8;  // g[8], G[8][12], 8 floats of slack for the 4 padding accumulators
 
-// smem offset(s) of packed accumulator p: g[k] -> k; G[k][l] -> 8 + 8k + l and its mirror
+// smem offset(s) of packed accumulator p: g[k] -> k; G[k][l] -> 8 + 12k + l and its mirror
 __constant__ uint8_t c_pk_a[NACC];
 __constant__ uint8_t c_pk_b[NACC];
 
@@ -114,27 +116,33 @@ struct SolveOut {
     float mine;   // d[lane & 7]
 };
 
-__device__ __forceinline__ SolveOut solve_lanes(const float* sm, const PhaseArgs& a, int b, uint32_t row, float zq, float alpha, int lane)
+// uo / sig / mu are this lane's (dimension kq = lane & 7) old factor value and hyper-parameters, loaded by the caller
+// early enough to hide their latency; lanes of padding dimensions pass uo = 0 and get delta 0.
+__device__ __forceinline__ SolveOut solve_lanes(const float* sm, float* Fs, float uo, float sig, float mu, bool live, int mode, float z,
+                                                float alpha, int lane)
 {
     const int kq = lane & 7;
-    const float4 g0 = *reinterpret_cast<const float4*>(sm + 8 + kq * 8);
-    const float4 g1 = *reinterpret_cast<const float4*>(sm + 8 + kq * 8 + 4);
+    const float4 g0 = *reinterpret_cast<const float4*>(sm + 8 + kq * G_STRIDE);
+    const float4 g1 = *reinterpret_cast<const float4*>(sm + 8 + kq * G_STRIDE + 4);
     const float Grow[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float A = sm[8 + kq * 9];
+    const float A = sm[8 + kq * (G_STRIDE + 1)];
     const float gk = sm[kq];
-    float* Fs = a.Fself + ((size_t)b * a.ns_self + row) * 8;
-    const float uo = Fs[kq];
-    const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
-    const float s = 1.0f / (sig + alpha * A);
-    const float smu = sig * mu;
-    const bool live = (uint32_t)(b * 8 + kq) < a.K;   // padding dimensions of the last block stay exactly zero
-    const float z = __shfl_sync(0xffffffffu, zq, ((b & 3) << 3) + kq);
+    float s = 1.0f / (sig + alpha * A);
+    // ran_gaussian(mean, stdev) of random.h:166-172: stdev := 1/lambda or its sqrt; stdev == 0 or NaN -> mean
+    float sd = (mode == SAMPLE_ZERO) ? 0.f : ((mode == SAMPLE_SQRT) ? sqrtf(s) : s);
+    if (isnan(sd)) sd = 0.f;
+    float smu = sig * mu;
+    if (!live) {   // padding dimension: mean = 0, no noise, delta = 0
+        s = 0.f;
+        sd = 0.f;
+        smu = 0.f;
+    }
     float B = fmaf(A, uo, gk);
     SolveOut o;
 #pragma unroll
     for (int l = 0; l < 8; ++l) {
         const float mean = s * fmaf(alpha, B, smu);
-        float cand = live ? uo - draw_f32(a.mode, mean, s, z) : 0.f;
+        const float cand = uo - fmaf(sd, z, mean);
         const float dl = __shfl_sync(0xffffffffu, cand, l);
         o.d[l] = dl;
         if (kq > l) B = fmaf(dl, Grow[l], B);
@@ -147,7 +155,7 @@ __device__ __forceinline__ SolveOut solve_lanes(const float* sm, const PhaseArgs
     return o;
 }
 
-template <int RPL, int WARPS>
+template <int RPL, int WARPS, bool PF>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : WARPS * 32)
 row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows, int b_begin, int b_end, int do_bias)
 {
@@ -165,9 +173,28 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
     constexpr int TPR = WARPS * 32;   // threads per row
     float* tot = (WARPS == 1) ? s_tot[warp] : s_tot[0];
 
+    const int mode = a.mode;
+    const uint32_t K = a.K;
     const float alpha = a.sc->alpha_f;
     const uint32_t sweep = a.sc->sweep;
-    const uint32_t pad_row = a.ns_other - 1;
+    const uint32_t ns_other = a.ns_other, ns_self = a.ns_self;
+    const uint32_t pad_row = ns_other - 1;
+    const float* __restrict__ Fother = a.Fother;
+    const int kq = lane & 7;
+
+    // where this lane's (or, WARPS > 1, this thread's) reduced sums go in shared memory
+    const int base = (WARPS == 1) ? reduce_scatter_base(lane) : (int)threadIdx.x;
+    uint32_t off_a = 0, off_b = 0;   // 3 x 8-bit offsets each
+    if (WARPS == 1) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            off_a |= (uint32_t)c_pk_a[base + i] << (8 * i);
+            off_b |= (uint32_t)c_pk_b[base + i] << (8 * i);
+        }
+    } else if (threadIdx.x < NACC) {
+        off_a = c_pk_a[base];
+        off_b = c_pk_b[base];
+    }
 
     uint32_t id[RPL];
     float e[RPL];
@@ -177,6 +204,13 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         const bool valid = p < c;
         id[r] = valid ? a.idx[beg + p] : pad_row;
         e[r] = valid ? a.e[beg + p] : 0.f;
+    }
+    // first block's gathers go out before the bias half-step
+    f8 f[RPL];
+    {
+        const float* Fo = Fother + (size_t)b_begin * ns_other * 8;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
     }
 
     if (do_bias) {
@@ -201,8 +235,8 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         const float s = 1.0f / (sb + alpha * (float)c);
         const float mean = s * (sb * mb + alpha * (t + (float)c * bo));
         float z = 0.f;
-        if (a.mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
-        const float bn = draw_f32(a.mode, mean, s, z);
+        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        const float bn = draw_f32(mode, mean, s, z);
         const float d = bo - bn;
 #pragma unroll
         for (int r = 0; r < RPL; ++r)
@@ -212,51 +246,64 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 
     float zq = 0.f;
     for (int b = b_begin; b < b_end; ++b) {
+        // this lane's dimension of the block: old value and hyper-parameters (latency hidden behind the accumulation)
+        float* Fs = a.Fself + ((size_t)b * ns_self + row) * 8;
+        const bool live = (uint32_t)(b * 8 + kq) < K;
+        const float uo = live ? Fs[kq] : 0.f;
+        const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
         // this row's noise, 4 blocks at a time: lane l draws dimension 32*(b/4) + l
-        if (a.mode != SAMPLE_ZERO && (((b & 3) == 0) || b == b_begin))
+        if (mode != SAMPLE_ZERO && (((b & 3) == 0) || b == b_begin))
             zq = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)((b & ~3) * 8 + lane), sweep));
-        const float* Fo = a.Fother + (size_t)b * a.ns_other * 8;
-        f8 f[RPL];
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
         float acc[NACC];
 #pragma unroll
         for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
 #pragma unroll
         for (int r = 0; r < RPL; ++r) accumulate(acc, f[r], e[r]);
+        // PF: keep this block's factors for the residual update; the next block's gathers fly during reduce + solve
+        f8 fcur[PF ? RPL : 1];
+        if (PF) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) fcur[r] = f[r];
+            if (b + 1 < b_end) {
+                const float* Fo = Fother + (size_t)(b + 1) * ns_other * 8;
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
+            }
+        }
         warp_reduce_scatter48(acc, lane);
-        const int base = reduce_scatter_base(lane);
         if (WARPS == 1) {
             if ((lane & 1) == 0) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    tot[c_pk_a[base + i]] = acc[i];
-                    tot[c_pk_b[base + i]] = acc[i];
+                    tot[(off_a >> (8 * i)) & 0xff] = acc[i];
+                    tot[(off_b >> (8 * i)) & 0xff] = acc[i];
                 }
             }
             __syncwarp();
         } else {
+            const int rb = reduce_scatter_base(lane);
             if ((lane & 1) == 0) {
-                s_part[warp][base] = acc[0];
-                s_part[warp][base + 1] = acc[1];
-                s_part[warp][base + 2] = acc[2];
+                s_part[warp][rb] = acc[0];
+                s_part[warp][rb + 1] = acc[1];
+                s_part[warp][rb + 2] = acc[2];
             }
             __syncthreads();
             if (threadIdx.x < NACC) {
                 float sum = 0.f;
 #pragma unroll
                 for (int w = 0; w < WARPS; ++w) sum += s_part[w][threadIdx.x];
-                tot[c_pk_a[threadIdx.x]] = sum;
-                tot[c_pk_b[threadIdx.x]] = sum;
+                tot[off_a] = sum;
+                tot[off_b] = sum;
             }
             __syncthreads();
         }
+        const float z = __shfl_sync(0xffffffffu, zq, ((b & 3) << 3) + kq);
         SolveOut so;
         if (WARPS == 1) {
-            so = solve_lanes(tot, a, b, row, zq, alpha, lane);
+            so = solve_lanes(tot, Fs, uo, sig, mu, live, mode, z, alpha, lane);
         } else {   // warp 0 solves and publishes the 8 deltas
             if (warp == 0) {
-                so = solve_lanes(tot, a, b, row, zq, alpha, lane);
+                so = solve_lanes(tot, Fs, uo, sig, mu, live, mode, z, alpha, lane);
                 if (lane < 8) s_d[lane] = so.mine;
             }
             __syncthreads();
@@ -264,7 +311,12 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
             for (int l = 0; l < 8; ++l) so.d[l] = s_d[l];
         }
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) e[r] += dot8(f[r], so.d);
+        for (int r = 0; r < RPL; ++r) e[r] += dot8(PF ? fcur[r] : f[r], so.d);
+        if (!PF && b + 1 < b_end) {
+            const float* Fo = Fother + (size_t)(b + 1) * ns_other * 8;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
+        }
         if (WARPS == 1) __syncwarp();   // tot is rewritten by the next block
         else __syncthreads();
     }
@@ -281,12 +333,12 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 // to e (PREV: 0 = only the global shift, 1 = bias delta, 2 = delta of block pb, re-gathering f) and accumulates
 // the partial sums of the current step (CUR: 0 = nothing, 1 = bias: sum e, 2 = block b: g, G) per slice;
 // heavy_solve<CUR> combines a row's slices in slice order and performs the update(s).
-template <int PREV, int CUR>
-__global__ void __launch_bounds__(SLICE_THREADS)
+template <int PREV, int CUR, int UNR, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const float* __restrict__ hdelta, const float* __restrict__ hbias_delta,
                         float* __restrict__ hpart, int pb, int b)
 {
-    __shared__ float s_part[SLICE_THREADS / 32][NACC];
+    __shared__ float s_part[THREADS / 32][NACC];
     const Slice sl = slices[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float dprev[8];
@@ -299,26 +351,41 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
     }
     const float* Fp = a.Fother + (size_t)pb * a.ns_other * 8;
     const float* Fc = a.Fother + (size_t)b * a.ns_other * 8;
+    const uint32_t pad_row = a.ns_other - 1;
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
     const uint32_t* idx = a.idx + sl.start;
     float* ep = a.e + sl.start;
-#pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < sl.len; i += SLICE_THREADS) {
-        float e = ep[i];
-        const uint32_t id = idx[i];
-        if (PREV == 2) {
-            const f8 fp = ld256_nc(Fp + (size_t)id * 8);
-            e += dot8(fp, dprev);
-        } else {
-            e += dscalar;
+    // batches of UNR ratings per thread: all index/residual loads, then all gathers, then the math, so that
+    // 2*UNR sector gathers per thread are in flight (the kernel is bound by gather latency, not by arithmetic)
+    for (uint32_t base = threadIdx.x; base < sl.len; base += THREADS * UNR) {
+        uint32_t id[UNR];
+        float e[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const uint32_t i = base + u * THREADS;
+            const bool ok = i < sl.len;
+            id[u] = ok ? idx[i] : pad_row;
+            e[u] = ok ? ep[i] : 0.f;
         }
-        ep[i] = e;
-        if (CUR == 1) acc[0] += e;
+        f8 fp[PREV == 2 ? UNR : 1], fc[CUR == 2 ? UNR : 1];
+        if (PREV == 2) {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) fp[u] = ld256_nc(Fp + (size_t)id[u] * 8);
+        }
         if (CUR == 2) {
-            const f8 f = ld256_nc(Fc + (size_t)id * 8);
-            accumulate(acc, f, e);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) fc[u] = ld256_nc(Fc + (size_t)id[u] * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const uint32_t i = base + u * THREADS;
+            if (PREV == 2) e[u] += dot8(fp[u], dprev);
+            else e[u] += dscalar;
+            if (i < sl.len) ep[i] = e[u];
+            if (CUR == 1 && i < sl.len) acc[0] += e[u];
+            if (CUR == 2) accumulate(acc, fc[u], e[u]);
         }
     }
     if (CUR == 1) {
@@ -328,7 +395,7 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
         if (threadIdx.x == 0) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < SLICE_THREADS / 32; ++w) s += s_part[w][0];
+            for (int w = 0; w < THREADS / 32; ++w) s += s_part[w][0];
             hpart[(size_t)blockIdx.x * NACC] = s;
         }
     }
@@ -344,7 +411,7 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
         if (threadIdx.x < NACC) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < SLICE_THREADS / 32; ++w) s += s_part[w][threadIdx.x];
+            for (int w = 0; w < THREADS / 32; ++w) s += s_part[w][threadIdx.x];
             hpart[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
         }
     }
@@ -733,12 +800,12 @@ export_factors_kernel(const float* __restrict__ F, float* __restrict__ dst, uint
 void init_constant_tables()
 {
     uint8_t pa[NACC], pb[NACC];
-    for (int p = 0; p < NACC; ++p) pa[p] = pb[p] = (uint8_t)(72 + (p & 3));   // padding accumulators -> slack
+    for (int p = 0; p < NACC; ++p) pa[p] = pb[p] = (uint8_t)(8 + 8 * G_STRIDE + (p & 3));   // padding accumulators -> slack
     for (int k = 0; k < 8; ++k) pa[k] = pb[k] = (uint8_t)k;
     for (int k = 0; k < 8; ++k)
         for (int l = k; l < 8; ++l) {
-            pa[gi(k, l)] = (uint8_t)(8 + 8 * k + l);
-            pb[gi(k, l)] = (uint8_t)(8 + 8 * l + k);
+            pa[gi(k, l)] = (uint8_t)(8 + G_STRIDE * k + l);
+            pb[gi(k, l)] = (uint8_t)(8 + G_STRIDE * l + k);
         }
     cudaMemcpyToSymbol(c_pk_a, pa, NACC);
     cudaMemcpyToSymbol(c_pk_b, pb, NACC);
@@ -825,8 +892,15 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
     constexpr int RPL = kBins[BIN].rpl, WARPS = kBins[BIN].warps;
     const uint32_t n = self.bin_count[BIN];
     if (!n) return;
-    if (WARPS == 1) row_resident_kernel<RPL, WARPS><<<(n + 3) / 4, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-    else row_resident_kernel<RPL, WARPS><<<n, WARPS * 32, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+    static const int pf_mask = getenv("SBMF_PREFETCH") ? atoi(getenv("SBMF_PREFETCH")) : 0;   // tuning knob: bit BIN = prefetch in that bin
+    const bool pf = (pf_mask >> BIN) & 1;
+    if (WARPS == 1) {
+        if (pf) row_resident_kernel<RPL, WARPS, true><<<(n + 3) / 4, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else row_resident_kernel<RPL, WARPS, false><<<(n + 3) / 4, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+    } else {
+        if (pf) row_resident_kernel<RPL, WARPS, true><<<n, WARPS * 32, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else row_resident_kernel<RPL, WARPS, false><<<n, WARPS * 32, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+    }
     m.launches++;
 }
 
@@ -881,9 +955,21 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift)
         const uint32_t ns = self.n_slices, nh = self.n_heavy;
         const uint32_t gs = (nh + 3) / 4;
         float* hbias = self.hdelta + (size_t)nh * 8;
-        heavy_accumulate_kernel<0, 1><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, 0, 0);
+        static const int variant = getenv("SBMF_HEAVY_VARIANT") ? atoi(getenv("SBMF_HEAVY_VARIANT")) : 4;   // tuning knob; 4 = 2 ratings x 64 threads
+#define HEAVY_ACC(PREV, CUR, PB, B)                                                                                                          \
+    do {                                                                                                                                     \
+        if (variant == 1) heavy_accumulate_kernel<PREV, CUR, 2, 128><<<ns, 128, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
+        else if (variant == 2) heavy_accumulate_kernel<PREV, CUR, 4, 128><<<ns, 128, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
+        else if (variant == 3) heavy_accumulate_kernel<PREV, CUR, 2, 256><<<ns, 256, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
+        else if (variant == 4) heavy_accumulate_kernel<PREV, CUR, 2, 64><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
+        else if (variant == 5) heavy_accumulate_kernel<PREV, CUR, 4, 64><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
+        else if (variant == 6) heavy_accumulate_kernel<PREV, CUR, 1, 128><<<ns, 128, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
+        else if (variant == 7) heavy_accumulate_kernel<PREV, CUR, 1, 64><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
+        else heavy_accumulate_kernel<PREV, CUR, 4, 256><<<ns, 256, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);       \
+    } while (0)
+        HEAVY_ACC(0, 1, 0, 0);
         heavy_solve_kernel<1><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
-        heavy_accumulate_kernel<1, 2><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, 0, 0);
+        HEAVY_ACC(1, 2, 0, 0);
         heavy_solve_kernel<2><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
         const bool detail = m.timing_detail && !apply_shift;   // item phase only
         if (detail && m.ev_top.size() < (size_t)2 * KB) {
@@ -896,11 +982,12 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift)
         if (detail) m.ev_top_used = 0;
         for (int b = 1; b < KB; ++b) {
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
-            heavy_accumulate_kernel<2, 2><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, b - 1, b);
+            HEAVY_ACC(2, 2, b - 1, b);
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
             heavy_solve_kernel<2><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, b);
         }
-        heavy_accumulate_kernel<2, 0><<<ns, SLICE_THREADS, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, KB - 1, 0);
+        HEAVY_ACC(2, 0, KB - 1, 0);
+#undef HEAVY_ACC
         m.launches += 2 * KB + 3;
         cudaEventRecord(m.ev_join, sh);
         cudaStreamWaitEvent(sr, m.ev_join, 0);

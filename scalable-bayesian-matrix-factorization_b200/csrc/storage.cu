@@ -8,6 +8,7 @@
 // permutation perm[csc slot] = csr slot that moves the residual between the two orders.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cub/cub.cuh>
@@ -147,7 +148,8 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
             const uint32_t h = (uint32_t)heavy.size();
             heavy.push_back(r);
             // equal-length slices (the last one is not a short tail)
-            const int64_t ns = (c + SLICE_LEN - 1) / SLICE_LEN;
+            static const int64_t slice_len = getenv("SBMF_SLICE_LEN") ? atol(getenv("SBMF_SLICE_LEN")) : SLICE_LEN;
+            const int64_t ns = (c + slice_len - 1) / slice_len;
             const int64_t len = (c + ns - 1) / ns;
             for (int64_t o = 0; o < c; o += len) slices.push_back(Slice{ptr[r] + o, (uint32_t)std::min<int64_t>(len, c - o), h});
             hsp.push_back((uint32_t)slices.size());
