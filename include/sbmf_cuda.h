@@ -67,7 +67,10 @@ typedef struct sbmf_config {
     int32_t hyper_mode;          /* sbmf_hyper_mode */
     uint32_t rebuild_every;      /* rebuild the residual from scratch every n-th sweep; 1 = every sweep = [T]:342-359 */
     uint32_t burn_in;            /* sweeps before test predictions are accumulated; 0 = [T]:323 */
-    uint32_t reserved0;
+    uint32_t residual_mode;      /* how the per-sweep residual rebuild of [T]:342-359 is done: 0 = fused into the user phase
+                                    (the fresh residual r - prediction replaces the incrementally updated one at the end of the
+                                    user phase; this sweep's sum e / sum e^2 come from the incremental residual of the previous
+                                    sweep, equal up to fp32 rounding); 1 = stand-alone rebuild kernel at the start of every sweep */
     uint64_t seed;               /* Philox key.  ([T] never seeds rand(); libFM parses -seed and ignores it) */
     double init_stdev;           /* 0.1 = [T]:242, 248 */
     double clamp_lo, clamp_hi;   /* 0.5 / 5.0 = [T]:627-628 */

@@ -48,6 +48,7 @@ int sbmf_cuda_config_default(sbmf_config* cfg)
     cfg->sample_mode = SBMF_SAMPLE_REF_VAR_AS_STDEV;
     cfg->hyper_mode = SBMF_HYPER_REF_T;
     cfg->rebuild_every = 1;                        // [T]:342-359 rebuilds E every sweep
+    cfg->residual_mode = 0;                        // ... fused into the user phase; 1 = stand-alone rebuild kernel
     cfg->burn_in = 0;                              // [T]:323
     cfg->seed = 1;
     cfg->init_stdev = 0.1;                         // [T]:242, 248
@@ -311,10 +312,16 @@ static int one_sweep(Model& m)
 {
     cudaStream_t st = m.s_main;
     const bool timing = m.timing_enabled;
-    const bool rebuild = (m.sweeps_done % m.cfg.rebuild_every) == 0;
+    // Residual hygiene ([T]:342-359 rebuilds E from scratch every sweep).  residual_mode 0 (default): the same rebuild, but
+    // fused into the user phase (its kernels already gather every factor the prediction needs), so the statistics of this
+    // sweep come from the incrementally updated residual of the previous one; residual_mode 1: the stand-alone rebuild kernel
+    // at the start of the sweep, literally as in [T].  Sweep 0 always rebuilds stand-alone (nothing to update yet).
+    const bool due = (m.sweeps_done % m.cfg.rebuild_every) == 0;
+    const bool standalone = due && (m.sweeps_done == 0 || m.cfg.residual_mode == 1);
+    const bool fused = due && !standalone;
     if (timing) cudaEventRecord(m.ev_t[0], st);
     int crc = 0;
-    if (rebuild) {
+    if (standalone) {
         launch_rebuild(m, st);                       // [T]:342-359
     } else {
         if (m.e_in_csc) crc |= launch_permute(m, false, st);
@@ -326,12 +333,12 @@ static int one_sweep(Model& m)
     launch_dim_hypers(m, st);                        // [T]:415-467
     launch_bias_hypers(m, st);                       // [T]:469-511
     if (timing) cudaEventRecord(m.ev_t[2], st);
-    launch_phase(m, m.us, m.it, true);               // [T]:514-558
+    launch_phase(m, m.us, m.it, true, fused);        // [T]:514-558 (+ the fused residual refresh)
     crc |= launch_allgather_side(m, m.us, st);       // multi-GPU: replicate the updated U rows and user biases
     if (timing) cudaEventRecord(m.ev_t[3], st);
     crc |= launch_permute(m, true, st);              // residual CSR order -> CSC order (all-to-all across GPUs)
     if (timing) cudaEventRecord(m.ev_t[4], st);
-    launch_phase(m, m.it, m.us, false);              // [T]:563-606
+    launch_phase(m, m.it, m.us, false, false);       // [T]:563-606
     crc |= launch_allgather_side(m, m.it, st);
     m.e_in_csc = true;
     if (timing) cudaEventRecord(m.ev_t[5], st);

@@ -40,8 +40,16 @@ struct PhaseArgs {
     uint32_t K;
     uint64_t seed;
     uint32_t site_f, site_b;
+    const uint32_t* rows_of_hrow;   // heavy_rows of this side
     int mode;          // SampleMode
     int apply_shift;   // user phase: add sc->shift_f on the first touch of e ([T]:407-410)
+    // residual refresh fused into this phase (REFRESH kernels): while the blocks are processed the prediction
+    // p = sum_b <f_b, u_new_b> is accumulated from the factors already in registers, and the phase ends with
+    // e = r - (b_0 + b_self + b_other + p): the rebuild of [T]:342-359 at the cost of one extra 4-byte gather per rating
+    const float* r;           // rating per slot (this side's order)
+    const float* bias_other;  // [n_other + 1] opposite-side biases (pad row -> 0 is never read)
+    float* pacc;              // [slots] partial predictions carried between launches / streaming passes
+    int KBtot;                // total number of blocks (to know the last one)
 };
 
 __host__ __device__ constexpr int gi(int k, int l) { return 8 + k * 8 - (k * (k - 1)) / 2 + (l - k); }   // k <= l
@@ -155,7 +163,7 @@ __device__ __forceinline__ SolveOut solve_lanes(const float* sm, float* Fs, floa
     return o;
 }
 
-template <int RPL, int WARPS, bool PF>
+template <int RPL, int WARPS, bool PF, bool REFRESH>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : WARPS * 32)
 row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows, int b_begin, int b_end, int do_bias)
 {
@@ -198,13 +206,17 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 
     uint32_t id[RPL];
     float e[RPL];
+    float pr[REFRESH ? RPL : 1];   // partial prediction sum_b <f_b, u_new_b>
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
         const int p = r * TPR + t_in_row;
         const bool valid = p < c;
         id[r] = valid ? a.idx[beg + p] : pad_row;
         e[r] = valid ? a.e[beg + p] : 0.f;
+        if (REFRESH) pr[r] = (valid && b_begin > 0) ? a.pacc[beg + p] : 0.f;
     }
+    float bias_new = 0.f;
+    if (REFRESH && !do_bias) bias_new = a.bias[row];
     // first block's gathers go out before the bias half-step
     f8 f[RPL];
     {
@@ -242,6 +254,7 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         for (int r = 0; r < RPL; ++r)
             if (id[r] != pad_row) e[r] += d;
         if (t_in_row == 0) a.bias[row] = bn;
+        bias_new = bn;
     }
 
     float zq = 0.f;
@@ -298,6 +311,11 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
             __syncthreads();
         }
         const float z = __shfl_sync(0xffffffffu, zq, ((b & 3) << 3) + kq);
+        float uo8[8];
+        if (REFRESH) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) uo8[k] = __shfl_sync(0xffffffffu, uo, k);
+        }
         SolveOut so;
         if (WARPS == 1) {
             so = solve_lanes(tot, Fs, uo, sig, mu, live, mode, z, alpha, lane);
@@ -311,7 +329,16 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
             for (int l = 0; l < 8; ++l) so.d[l] = s_d[l];
         }
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) e[r] += dot8(PF ? fcur[r] : f[r], so.d);
+        for (int r = 0; r < RPL; ++r) {
+            const float fd = dot8(PF ? fcur[r] : f[r], so.d);
+            e[r] += fd;
+            if (REFRESH) {   // <f, u_new> = <f, u_old> - <f, d>; u_old broadcast from the 8 lanes that hold it
+                float fu = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) fu = fmaf((PF ? fcur[r] : f[r]).v[k], uo8[k], fu);
+                pr[r] += fu - fd;
+            }
+        }
         if (!PF && b + 1 < b_end) {
             const float* Fo = Fother + (size_t)(b + 1) * ns_other * 8;
 #pragma unroll
@@ -321,10 +348,22 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         else __syncthreads();
     }
 
+    if (REFRESH && b_end == a.KBtot) {   // the phase is complete for this row: fresh residual instead of the incremental one
+        const float b0 = a.sc->b_0_f;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const int p = r * TPR + t_in_row;
+            if (p < c) a.e[beg + p] = a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]);
+        }
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
         const int p = r * TPR + t_in_row;
-        if (p < c) a.e[beg + p] = e[r];
+        if (p < c) {
+            a.e[beg + p] = e[r];
+            if (REFRESH) a.pacc[beg + p] = pr[r];
+        }
     }
 }
 
@@ -333,7 +372,7 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 // to e (PREV: 0 = only the global shift, 1 = bias delta, 2 = delta of block pb, re-gathering f) and accumulates
 // the partial sums of the current step (CUR: 0 = nothing, 1 = bias: sum e, 2 = block b: g, G) per slice;
 // heavy_solve<CUR> combines a row's slices in slice order and performs the update(s).
-template <int PREV, int CUR, int UNR, int THREADS>
+template <int PREV, int CUR, int UNR, int THREADS, bool REFRESH>
 __global__ void __launch_bounds__(THREADS)
 heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const float* __restrict__ hdelta, const float* __restrict__ hbias_delta,
                         float* __restrict__ hpart, int pb, int b)
@@ -349,6 +388,18 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
 #pragma unroll
         for (int k = 0; k < 8; ++k) dprev[k] = hdelta[(size_t)sl.hrow * 8 + k];
     }
+    // REFRESH: the previous block's NEW factor values of this row (the solve kernel has stored them), for p += <f_prev, u_new_prev>
+    float unprev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float row_const = 0.f;
+    if (REFRESH && PREV == 2) {
+        const uint32_t row = a.rows_of_hrow[sl.hrow];
+        const float* Fsp = a.Fself + ((size_t)pb * a.ns_self + row) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) unprev[k] = Fsp[k];
+        if (CUR == 0) row_const = a.sc->b_0_f + a.bias[row];
+    }
+    float* pp = a.pacc + sl.start;
+    const float* rp = a.r + sl.start;
     const float* Fp = a.Fother + (size_t)pb * a.ns_other * 8;
     const float* Fc = a.Fother + (size_t)b * a.ns_other * 8;
     const uint32_t pad_row = a.ns_other - 1;
@@ -362,12 +413,14 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
     for (uint32_t base = threadIdx.x; base < sl.len; base += THREADS * UNR) {
         uint32_t id[UNR];
         float e[UNR];
+        float pr[REFRESH ? UNR : 1];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const uint32_t i = base + u * THREADS;
             const bool ok = i < sl.len;
             id[u] = ok ? idx[i] : pad_row;
             e[u] = ok ? ep[i] : 0.f;
+            if (REFRESH && PREV == 2) pr[u] = (ok && pb > 0) ? pp[i] : 0.f;
         }
         f8 fp[PREV == 2 ? UNR : 1], fc[CUR == 2 ? UNR : 1];
         if (PREV == 2) {
@@ -383,6 +436,11 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
             const uint32_t i = base + u * THREADS;
             if (PREV == 2) e[u] += dot8(fp[u], dprev);
             else e[u] += dscalar;
+            if (REFRESH && PREV == 2) {
+                pr[u] += dot8(fp[u], unprev);
+                if (CUR == 0) e[u] = (i < sl.len) ? rp[i] - (row_const + a.bias_other[id[u]] + pr[u]) : 0.f;   // phase done: fresh residual
+                else if (i < sl.len) pp[i] = pr[u];
+            }
             if (i < sl.len) ep[i] = e[u];
             if (CUR == 1 && i < sl.len) acc[0] += e[u];
             if (CUR == 2) accumulate(acc, fc[u], e[u]);
@@ -887,27 +945,26 @@ void launch_bias_hypers(Model& m, cudaStream_t st)
 }
 
 template <int BIN>
-static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, int b1, int do_bias, cudaStream_t st)
+static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, int b1, int do_bias, bool refresh, cudaStream_t st)
 {
     constexpr int RPL = kBins[BIN].rpl, WARPS = kBins[BIN].warps;
     const uint32_t n = self.bin_count[BIN];
     if (!n) return;
-    static const int pf_mask = getenv("SBMF_PREFETCH") ? atoi(getenv("SBMF_PREFETCH")) : 0;   // tuning knob: bit BIN = prefetch in that bin
-    const bool pf = (pf_mask >> BIN) & 1;
-    if (WARPS == 1) {
-        if (pf) row_resident_kernel<RPL, WARPS, true><<<(n + 3) / 4, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-        else row_resident_kernel<RPL, WARPS, false><<<(n + 3) / 4, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-    } else {
-        if (pf) row_resident_kernel<RPL, WARPS, true><<<n, WARPS * 32, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-        else row_resident_kernel<RPL, WARPS, false><<<n, WARPS * 32, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-    }
+    const dim3 grid(WARPS == 1 ? (n + 3) / 4 : n), block(WARPS == 1 ? 128 : WARPS * 32);
+    if (refresh) row_resident_kernel<RPL, WARPS, false, true><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+    else row_resident_kernel<RPL, WARPS, false, false><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
     m.launches++;
 }
 
 // One half-sweep: bias then all factor blocks of every row of `self` ([T]:514-558 users / 563-606 items).
-void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift)
+void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh)
 {
     PhaseArgs a;
+    a.r = m.csr_r;              // only the user phase refreshes (refresh == false on the item side)
+    a.bias_other = other.bias;
+    a.pacc = m.pacc;
+    a.KBtot = (int)m.KB;
+    a.rows_of_hrow = self.heavy_rows;
     a.ptr = self.ptr;
     a.idx = self.idx;
     a.e = self.e;
@@ -943,29 +1000,23 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift)
     for (int b0 = 0; b0 < KB; b0 += nb) {
         const int b1 = (b0 + nb < KB) ? b0 + nb : KB;
         const int do_bias = (b0 == 0) ? 1 : 0;
-        launch_bin<0>(m, a, self, b0, b1, do_bias, sr);
-        launch_bin<1>(m, a, self, b0, b1, do_bias, sr);
-        launch_bin<2>(m, a, self, b0, b1, do_bias, sr);
-        launch_bin<3>(m, a, self, b0, b1, do_bias, sr);
-        launch_bin<4>(m, a, self, b0, b1, do_bias, sr);
-        launch_bin<5>(m, a, self, b0, b1, do_bias, sr);
-        launch_bin<6>(m, a, self, b0, b1, do_bias, sr);
+        launch_bin<0>(m, a, self, b0, b1, do_bias, refresh, sr);
+        launch_bin<1>(m, a, self, b0, b1, do_bias, refresh, sr);
+        launch_bin<2>(m, a, self, b0, b1, do_bias, refresh, sr);
+        launch_bin<3>(m, a, self, b0, b1, do_bias, refresh, sr);
+        launch_bin<4>(m, a, self, b0, b1, do_bias, refresh, sr);
+        launch_bin<5>(m, a, self, b0, b1, do_bias, refresh, sr);
+        launch_bin<6>(m, a, self, b0, b1, do_bias, refresh, sr);
     }
     if (heavy) {
         const uint32_t ns = self.n_slices, nh = self.n_heavy;
         const uint32_t gs = (nh + 3) / 4;
         float* hbias = self.hdelta + (size_t)nh * 8;
-        static const int variant = getenv("SBMF_HEAVY_VARIANT") ? atoi(getenv("SBMF_HEAVY_VARIANT")) : 4;   // tuning knob; 4 = 2 ratings x 64 threads
-#define HEAVY_ACC(PREV, CUR, PB, B)                                                                                                          \
-    do {                                                                                                                                     \
-        if (variant == 1) heavy_accumulate_kernel<PREV, CUR, 2, 128><<<ns, 128, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
-        else if (variant == 2) heavy_accumulate_kernel<PREV, CUR, 4, 128><<<ns, 128, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
-        else if (variant == 3) heavy_accumulate_kernel<PREV, CUR, 2, 256><<<ns, 256, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
-        else if (variant == 4) heavy_accumulate_kernel<PREV, CUR, 2, 64><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
-        else if (variant == 5) heavy_accumulate_kernel<PREV, CUR, 4, 64><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
-        else if (variant == 6) heavy_accumulate_kernel<PREV, CUR, 1, 128><<<ns, 128, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
-        else if (variant == 7) heavy_accumulate_kernel<PREV, CUR, 1, 64><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B); \
-        else heavy_accumulate_kernel<PREV, CUR, 4, 256><<<ns, 256, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);       \
+    // 2 ratings per thread x 64 threads per slice CTA measured best on B200 (profiles/): small CTAs, ~20 warps per SM
+#define HEAVY_ACC(PREV, CUR, PB, B)                                                                                                              \
+    do {                                                                                                                                         \
+        if (refresh) heavy_accumulate_kernel<PREV, CUR, 2, 64, true><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);  \
+        else heavy_accumulate_kernel<PREV, CUR, 2, 64, false><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);         \
     } while (0)
         HEAVY_ACC(0, 1, 0, 0);
         heavy_solve_kernel<1><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
@@ -997,11 +1048,32 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift)
 // Residual between the two slot orders.  One GPU: a gather through perm.  G GPUs: every value moves from the rank that owns
 // its user to the rank that owns its item -- pack in the destination's CSC order, one grouped NCCL send/recv over NVLink,
 // unpack through recv_pos (plan.cpp).
+__global__ void __launch_bounds__(256)
+invert_perm_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ inv, uint64_t n)
+{
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (uint64_t)gridDim.x * 256) inv[perm[t]] = (uint32_t)t;
+}
+
+// the reverse direction (CSC order -> CSR order) as GATHERS through inverse maps, built on first use: random 4-byte
+// reads are ~4x cheaper than random 4-byte writes
+static bool ensure_inverse(Model& m, const uint32_t* perm, uint32_t** inv, uint64_t n, cudaStream_t st)
+{
+    if (*inv) return true;
+    if (cudaMalloc((void**)inv, (n ? n : 1) * 4) != cudaSuccess) {
+        *inv = nullptr;
+        cudaGetLastError();
+        return false;   // fall back to the scatter form
+    }
+    invert_perm_kernel<<<grid_for(n, 256, m.sm_count * 16), 256, 0, st>>>(perm, *inv, n);
+    return true;
+}
+
 int launch_permute(Model& m, bool csr_to_csc, cudaStream_t st)
 {
     if (m.world == 1) {
         const uint32_t g = grid_for(m.N, 256, m.sm_count * 16);
         if (csr_to_csc) permute_gather_kernel<<<g, 256, 0, st>>>(m.us.e, m.perm, m.it.e, m.N);
+        else if (ensure_inverse(m, m.perm, &m.perm_inv, m.N, st)) permute_gather_kernel<<<g, 256, 0, st>>>(m.it.e, m.perm_inv, m.us.e, m.N);
         else permute_scatter_kernel<<<g, 256, 0, st>>>(m.it.e, m.perm, m.us.e, m.N);
         m.launches++;
         return 0;
@@ -1013,9 +1085,11 @@ int launch_permute(Model& m, bool csr_to_csc, cudaStream_t st)
         rc = comm_alltoallv_f32(m.comm, m.sendbuf, m.send_off.data(), m.send_cnt.data(), m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), st, m.err);
         permute_gather_kernel<<<gr, 256, 0, st>>>(m.recvbuf, m.recv_pos, m.it.e, m.n_csc);
     } else {
-        permute_scatter_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos, m.recvbuf, m.n_csc);
+        if (ensure_inverse(m, m.recv_pos, &m.recv_pos_inv, m.n_csc, st)) permute_gather_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos_inv, m.recvbuf, m.n_csc);
+        else permute_scatter_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos, m.recvbuf, m.n_csc);
         rc = comm_alltoallv_f32(m.comm, m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), m.sendbuf, m.send_off.data(), m.send_cnt.data(), st, m.err);
-        permute_scatter_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx, m.us.e, m.n_csr);
+        if (ensure_inverse(m, m.send_idx, &m.send_idx_inv, m.n_csr, st)) permute_gather_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx_inv, m.us.e, m.n_csr);
+        else permute_scatter_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx, m.us.e, m.n_csr);
     }
     m.launches += 2;
     return rc;

@@ -87,9 +87,11 @@ struct Model {
     Side us, it;                      // user side (CSR), item side (CSC)
     uint32_t* csr_urow = nullptr;     // [N] user of each CSR slot (COO row index for the flat rebuild)
     float* csr_r = nullptr;           // [N] rating per CSR slot
+    float* pacc = nullptr;            // [N] partial predictions of the fused residual refresh (CSR slot order)
     uint32_t* csr_id = nullptr;       // [N] rating (file) index of each CSR slot
     uint32_t* csc_id = nullptr;       // [N] rating index of each CSC slot
     uint32_t* perm = nullptr;         // [N] CSR slot of each CSC slot
+    uint32_t *perm_inv = nullptr, *recv_pos_inv = nullptr, *send_idx_inv = nullptr;   // inverse maps for the reverse direction, built on first use
     bool e_in_csc = false;            // where the freshest residual lives
     // multi-GPU: rank r owns users [ub[r], ub[r+1]) with their CSR slots and items [ib[r], ib[r+1]) with their
     // CSC slots; every slot array above is then the LOCAL shard, ptr[] is rebased to local slots, factors/biases are replicas
@@ -144,7 +146,7 @@ void launch_stats(Model& m, cudaStream_t st);            // partial stats of the
 void launch_global_hypers(Model& m, cudaStream_t st);    // [T]:366-410 (final reduce of the stats + 4 scalar draws)
 void launch_dim_hypers(Model& m, cudaStream_t st);       // [T]:415-467
 void launch_bias_hypers(Model& m, cudaStream_t st);      // [T]:469-511
-void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift);   // [T]:514-558 / 563-606
+void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh);   // [T]:514-558 / 563-606
 int launch_permute(Model& m, bool csr_to_csc, cudaStream_t st);   // one GPU: gather through perm; else all-to-all over NVLink
 int launch_reduce_pair(Model& m, cudaStream_t st);                // red_part -> red2 (+ all-reduce over ranks)
 int launch_allgather_side(Model& m, Side& s, cudaStream_t st);    // replicate the rows each rank just updated (factors + bias)

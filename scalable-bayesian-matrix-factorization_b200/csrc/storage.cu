@@ -107,11 +107,14 @@ void free_storage(Model& m)
 {
     free_side(m.us);
     free_side(m.it);
-    cudaFree(m.csr_urow); cudaFree(m.csr_r); cudaFree(m.csr_id); cudaFree(m.csc_id); cudaFree(m.perm);
+    cudaFree(m.csr_urow); cudaFree(m.csr_r); cudaFree(m.csr_id); cudaFree(m.csc_id); cudaFree(m.perm); cudaFree(m.pacc);
+    m.pacc = nullptr;
     m.csr_urow = nullptr; m.csr_r = nullptr; m.csr_id = nullptr; m.csc_id = nullptr; m.perm = nullptr;
     cudaFree(m.red_part); m.red_part = nullptr;
     cudaFree(m.red2); m.red2 = nullptr;
     cudaFree(m.send_idx); cudaFree(m.recv_pos); cudaFree(m.sendbuf); cudaFree(m.recvbuf);
+    cudaFree(m.perm_inv); cudaFree(m.recv_pos_inv); cudaFree(m.send_idx_inv);
+    m.perm_inv = m.recv_pos_inv = m.send_idx_inv = nullptr;
     m.send_idx = m.recv_pos = nullptr; m.sendbuf = m.recvbuf = nullptr;
     m.n_csr = m.n_csc = 0;
     m.have_train = false;
@@ -344,6 +347,7 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     m.red_blocks = (uint32_t)m.sm_count * 8;
     CK(dmalloc(&m.red_part, (size_t)m.red_blocks * 2));
     CK(dmalloc(&m.red2, 2));
+    CK(dmalloc(&m.pacc, m.n_csr));
     m.have_train = true;
     m.e_in_csc = false;
     return SBMF_OK;

@@ -23,7 +23,7 @@ class Priors(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("K", C.c_uint32), ("device", C.c_int32), ("sample_mode", C.c_int32),
-                ("hyper_mode", C.c_int32), ("rebuild_every", C.c_uint32), ("burn_in", C.c_uint32), ("reserved0", C.c_uint32),
+                ("hyper_mode", C.c_int32), ("rebuild_every", C.c_uint32), ("burn_in", C.c_uint32), ("residual_mode", C.c_uint32),
                 ("seed", C.c_uint64), ("init_stdev", C.c_double), ("clamp_lo", C.c_double), ("clamp_hi", C.c_double),
                 ("priors", Priors), ("rank", C.c_int32), ("world_size", C.c_int32), ("nccl_id", C.c_uint8 * 128)]
 

@@ -63,10 +63,11 @@ def check_state(gs, os_, tol, what=("U", "V", "b_i", "b_j", "mu_b_i", "sigma_b_i
     return worst
 
 
+@pytest.mark.parametrize("residual_mode", [0, 1])   # 0: rebuild fused into the user phase, 1: stand-alone rebuild kernel ([T] literal)
 @pytest.mark.parametrize("case,K", [("ml100k", 20), ("ml100k", 50), ("tiny", 20), ("tiny", 3)])
-def test_zero_noise_10_sweeps(case, K, ml100k, tiny):
+def test_zero_noise_10_sweeps(case, K, residual_mode, ml100k, tiny):
     d = ml100k if case == "ml100k" else tiny
-    m, o = make_pair(d, K, 2)
+    m, o = make_pair(d, K, 2, residual_mode=residual_mode)
     init_both(m, o, d, K)
     m.sweep(10)
     r_o, rs_o = o.sweep(10)
@@ -165,14 +166,15 @@ def skewed_case(seed=3, I=40, J=6000, dense_users=3):
             "test_rating": r[:nt], "num_users": I, "num_items": J}
 
 
+@pytest.mark.parametrize("residual_mode", [0, 1])
 @pytest.mark.parametrize("transpose", [False, True])
 @pytest.mark.parametrize("K", [8, 20])
-def test_zero_noise_heavy_rows(transpose, K):
+def test_zero_noise_heavy_rows(transpose, K, residual_mode):
     d = skewed_case()
     if transpose:   # heavy ITEMS instead of heavy users
         d = dict(d, train_user=d["train_item"], train_item=d["train_user"], test_user=d["test_item"], test_item=d["test_user"],
                  num_users=d["num_items"], num_items=d["num_users"])
-    m, o = make_pair(d, K, 2)
+    m, o = make_pair(d, K, 2, residual_mode=residual_mode)
     init_both(m, o, d, K)
     t = m.timing()
     assert (t["nnz_heavy_item"] if transpose else t["nnz_heavy_user"]) > 0
