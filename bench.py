@@ -209,7 +209,8 @@ def main():
     W = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     cfg = {"workload": f"{a.workload}: synthetic Netflix/MovieLens-shaped Zipf rating matrix {I}x{J}, ~{NTRAIN} train ratings (+{int(TEST_FRAC * 100)}% test), K={K}",
            "users": I, "items": J, "K": K, "l2_policy": "working set per sweep (>2 GB) far exceeds the 126 MB L2; no flush needed",
-           "rebuild_every": 1, "sample_mode": "reference (x = mu + (1/lambda) z)"}
+           "rebuild_every": 1, "residual_mode": "0: per-sweep residual rebuild of gibbs_sbpmf2.cpp:342-359 fused into the user phase",
+           "sample_mode": "reference (x = mu + (1/lambda) z)"}
 
     import sbmf
     if a.impl == "reference":
@@ -337,20 +338,26 @@ def main():
         barrier()
         te0 = time.perf_counter()
         m2.set_train(hb["train_user"], hb["train_item"], hb["train_rating"], I, J)
+        te1 = time.perf_counter()
         m2.set_test(hb["test_user"], hb["test_item"], hb["test_rating"])
         m2.init_factors()
+        te2 = time.perf_counter()
         last = None
         for _ in range(a.steps):
             m2.sweep(1)
             last = m2.eval()            # D2H read of the step's result (2 doubles), synchronises
+        te3 = time.perf_counter()
         m2._ck(m2.lib.sbmf_cuda_get_pred(m2.h, pred.ctypes.data))
         m2.synchronize()
         barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - te0)
+        te4 = time.perf_counter()
+        e2e_s = max_over_ranks(te4 - te0)
+        breakdown = {"set_train_s": round(te1 - te0, 4), "set_test_init_s": round(te2 - te1, 4), "sweeps_s": round(te3 - te2, 4),
+                     "get_pred_s": round(te4 - te3, 4)}
         h2d = 12.0 * (n_train + n_test)
         d2h = 16.0 * a.steps + 8.0 * n_test
         e2e = {"value": fu_per_sweep * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
-               "seconds_total": e2e_s, "sweeps": a.steps, "final_rmse": last[0],
+               "seconds_total": e2e_s, "sweeps": a.steps, "final_rmse": last[0], "breakdown_rank0": breakdown,
                "what": "set_train(H2D COO + device CSR/CSC build) + set_test + init_factors + steps x (sweep + eval D2H) + get_pred D2H, wall clock"}
         m2.close()
 

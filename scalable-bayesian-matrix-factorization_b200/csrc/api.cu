@@ -131,6 +131,14 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
     m.it.site_sigma_b = SITE_SIGMA_BJ; m.it.site_mu_b = SITE_MU_BJ; m.it.prior = 1; m.it.prior_b = 5;
     bool ok = cudaSetDevice(m.device) == cudaSuccess;
     if (ok) init_constant_tables();
+    if (ok) {   // keep freed stream-ordered allocations (set_train temporaries) in the pool instead of returning them to the OS
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, m.device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     ok = ok && cudaStreamCreateWithFlags(&m.s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&m.s_aux, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming) == cudaSuccess;

@@ -163,8 +163,9 @@ __device__ __forceinline__ SolveOut solve_lanes(const float* sm, float* Fs, floa
     return o;
 }
 
+// register caps (min CTAs per SM): 8 ratings per lane -> 128 registers, 4 -> 102, fewer -> 80
 template <int RPL, int WARPS, bool PF, bool REFRESH>
-__global__ void __launch_bounds__(WARPS == 1 ? 128 : WARPS * 32)
+__global__ void __launch_bounds__(WARPS == 1 ? 128 : WARPS * 32, (RPL == 8 ? 512 : RPL == 4 ? 640 : 768) / (WARPS == 1 ? 128 : WARPS * 32))
 row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows, int b_begin, int b_end, int do_bias)
 {
     constexpr int WPC = (WARPS == 1) ? 4 : WARPS;   // warps per CTA

@@ -10,7 +10,10 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <stdio.h>
+
 #include <algorithm>
+#include <chrono>
 #include <cub/cub.cuh>
 #include <vector>
 
@@ -263,10 +266,25 @@ static int alloc_side_state(Model& m, Side& s)
     return SBMF_OK;
 }
 
+struct Trace {   // SBMF_TRACE=1: wall-clock of the set_train stages on stderr
+    bool on = getenv("SBMF_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what)
+    {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sbmf trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* item, const float* rating, uint32_t num_users,
                   uint32_t num_items)
 {
+    Trace tr;
     free_storage(m);
+    tr.lap("free previous");
     if (n >= (1ull << 31)) {
         m.err = "set_train: more than 2^31-1 ratings per GPU are not supported (shard across GPUs)";
         return SBMF_ERR_UNSUPPORTED;
@@ -280,8 +298,12 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     uint32_t *d_user = nullptr, *d_item = nullptr, *d_iota = nullptr, *d_keys = nullptr, *d_inv = nullptr, *d_max = nullptr;
     float* d_rating = nullptr;
     void* d_tmp = nullptr;
+    // temporaries come from the device's stream-ordered pool (release threshold raised in sbmf_cuda_create): a plain
+    // cudaFree of a few GB can take hundreds of milliseconds
+    auto talloc = [&](void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, st); };
     auto cleanup = [&]() {
-        cudaFree(d_user); cudaFree(d_item); cudaFree(d_iota); cudaFree(d_keys); cudaFree(d_inv); cudaFree(d_max); cudaFree(d_rating); cudaFree(d_tmp);
+        for (void* p : {(void*)d_user, (void*)d_item, (void*)d_iota, (void*)d_keys, (void*)d_inv, (void*)d_max, (void*)d_rating, d_tmp})
+            if (p) cudaFreeAsync(p, st);
     };
 #define CKC(call)                                                                                  \
     do {                                                                                           \
@@ -293,11 +315,12 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
         }                                                                                          \
     } while (0)
 
-    CKC(dmalloc(&d_user, n)); CKC(dmalloc(&d_item, n)); CKC(dmalloc(&d_rating, n)); CKC(dmalloc(&d_iota, n)); CKC(dmalloc(&d_keys, n));
-    CKC(dmalloc(&d_inv, n)); CKC(dmalloc(&d_max, 2));
+    CKC(talloc((void**)&d_user, n * 4)); CKC(talloc((void**)&d_item, n * 4)); CKC(talloc((void**)&d_rating, n * 4));
+    CKC(talloc((void**)&d_iota, n * 4)); CKC(talloc((void**)&d_keys, n * 4)); CKC(talloc((void**)&d_inv, n * 4)); CKC(talloc((void**)&d_max, 8));
     CKC(cudaMemcpyAsync(d_user, user, n * 4, cudaMemcpyHostToDevice, st));
     CKC(cudaMemcpyAsync(d_item, item, n * 4, cudaMemcpyHostToDevice, st));
     CKC(cudaMemcpyAsync(d_rating, rating, n * 4, cudaMemcpyHostToDevice, st));
+    tr.lap("alloc + H2D");
     CKC(cudaMemsetAsync(d_max, 0, 8, st));
     if (n) max_id_kernel<<<G, T, 0, st>>>(d_user, d_item, n, d_max);
     uint32_t h_max[2] = {0, 0};
@@ -313,9 +336,10 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     CKC(dmalloc(&m.us.idx, n)); CKC(dmalloc(&m.it.idx, n)); CKC(dmalloc(&m.us.e, n)); CKC(dmalloc(&m.it.e, n));
     CKC(dmalloc(&m.csr_urow, n)); CKC(dmalloc(&m.csr_r, n)); CKC(dmalloc(&m.csr_id, n)); CKC(dmalloc(&m.csc_id, n)); CKC(dmalloc(&m.perm, n));
 
+    tr.lap("id check + alloc layout");
     size_t tmp_bytes = 0;
     CKC(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_user, d_keys, d_iota, m.csr_id, (int)n, 0, 32, st));
-    CKC(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+    CKC(talloc(&d_tmp, tmp_bytes));
     iota_kernel<<<G, T, 0, st>>>(d_iota, n);
     // CSR: stable sort of the rating index by user
     CKC(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_user, m.csr_urow, d_iota, m.csr_id, (int)n, 0, bits_for(num_users), st));
@@ -332,7 +356,9 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     CKC(cudaMemsetAsync(m.it.e, 0, (n ? n : 1) * 4, st));
     CKC(cudaGetLastError());
     CKC(cudaStreamSynchronize(st));
+    tr.lap("sorts + gathers");
     cleanup();
+    tr.lap("free temporaries");
 #undef CKC
 
     int rc;
@@ -342,12 +368,14 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     if (m.world > 1 && (rc = shard_storage(m)) != SBMF_OK) return rc;
     if ((rc = build_worklists(m, m.us, m.ub[m.rank], m.ub[m.rank + 1])) != SBMF_OK) return rc;
     if ((rc = build_worklists(m, m.it, m.ib[m.rank], m.ib[m.rank + 1])) != SBMF_OK) return rc;
+    tr.lap("shard + work lists");
     if ((rc = alloc_side_state(m, m.us)) != SBMF_OK) return rc;
     if ((rc = alloc_side_state(m, m.it)) != SBMF_OK) return rc;
     m.red_blocks = (uint32_t)m.sm_count * 8;
     CK(dmalloc(&m.red_part, (size_t)m.red_blocks * 2));
     CK(dmalloc(&m.red2, 2));
     CK(dmalloc(&m.pacc, m.n_csr));
+    tr.lap("alloc state");
     m.have_train = true;
     m.e_in_csc = false;
     return SBMF_OK;
