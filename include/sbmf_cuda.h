@@ -113,6 +113,7 @@ typedef struct sbmf_timing {
     double ms_top_kernel;        /* sum of its launch durations */
     uint64_t top_kernel_launches;
     uint64_t top_kernel_ratings; /* ratings one launch streams (each for 8 latent dimensions) */
+    double ms_allgather;         /* multi-GPU: the factor/bias all-gathers after the two phases (part of ms_user_phase / ms_item_phase) */
 } sbmf_timing;
 
 /* ---- life cycle ------------------------------------------------------------------------------------ */

@@ -145,6 +145,7 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
     ok = ok && cudaEventCreateWithFlags(&m.ev_join, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&m.ev_t[i]) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreate(&m.ev_call[i]) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreate(&m.ev_c[i]) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&m.sc, sizeof(Scalars)) == cudaSuccess;
     ok = ok && cudaMemset(m.sc, 0, sizeof(Scalars)) == cudaSuccess;
     m.hist_cap = 4096;
@@ -160,6 +161,30 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
             g_create_err = "create: NCCL: " + err;
             sbmf_cuda_destroy(h);
             return SBMF_ERR_NCCL;
+        }
+        // NCCL connects peers lazily on the first collective that needs them; do that here, once, with one small instance of
+        // every pattern the sweep uses (all-reduce, broadcast from every root, all-to-all), not inside the first sweep
+        {
+            float* wf = nullptr;
+            double* wd = nullptr;
+            const int G = m.world;
+            bool wok = cudaMalloc((void**)&wf, (size_t)G * 2 * 256 * 4) == cudaSuccess && cudaMalloc((void**)&wd, 16) == cudaSuccess;
+            wok = wok && cudaMemset(wf, 0, (size_t)G * 2 * 256 * 4) == cudaSuccess && cudaMemset(wd, 0, 16) == cudaSuccess;
+            if (wok) {
+                std::vector<size_t> off(G), cnt(G, 256);
+                for (int q = 0; q < G; ++q) off[q] = (size_t)q * 256;
+                wok = comm_allreduce_sum_f64(m.comm, wd, 2, m.s_main, err) == 0;
+                wok = wok && comm_allgatherv_f32(m.comm, wf, off.data(), cnt.data(), m.s_main, err) == 0;
+                wok = wok && comm_alltoallv_f32(m.comm, wf, off.data(), cnt.data(), wf + (size_t)G * 256, off.data(), cnt.data(), m.s_main, err) == 0;
+                wok = wok && cudaStreamSynchronize(m.s_main) == cudaSuccess;
+            }
+            cudaFree(wf);
+            cudaFree(wd);
+            if (!wok) {
+                g_create_err = "create: NCCL warm-up failed: " + err;
+                sbmf_cuda_destroy(h);
+                return SBMF_ERR_NCCL;
+            }
         }
     }
     *out = h;
@@ -182,6 +207,8 @@ int sbmf_cuda_destroy(sbmf_handle* h)
         if (m.ev_t[i]) cudaEventDestroy(m.ev_t[i]);
     for (int i = 0; i < 2; ++i)
         if (m.ev_call[i]) cudaEventDestroy(m.ev_call[i]);
+    for (int i = 0; i < 2; ++i)
+        if (m.ev_c[i]) cudaEventDestroy(m.ev_c[i]);
     for (cudaEvent_t ev : m.ev_top) cudaEventDestroy(ev);
     if (m.ev_fork) cudaEventDestroy(m.ev_fork);
     if (m.ev_join) cudaEventDestroy(m.ev_join);
@@ -342,11 +369,13 @@ static int one_sweep(Model& m)
     launch_bias_hypers(m, st);                       // [T]:469-511
     if (timing) cudaEventRecord(m.ev_t[2], st);
     launch_phase(m, m.us, m.it, true, fused);        // [T]:514-558 (+ the fused residual refresh)
+    if (timing) cudaEventRecord(m.ev_c[0], st);
     crc |= launch_allgather_side(m, m.us, st);       // multi-GPU: replicate the updated U rows and user biases
     if (timing) cudaEventRecord(m.ev_t[3], st);
     crc |= launch_permute(m, true, st);              // residual CSR order -> CSC order (all-to-all across GPUs)
     if (timing) cudaEventRecord(m.ev_t[4], st);
     launch_phase(m, m.it, m.us, false, false);       // [T]:563-606
+    if (timing) cudaEventRecord(m.ev_c[1], st);
     crc |= launch_allgather_side(m, m.it, st);
     m.e_in_csc = true;
     if (timing) cudaEventRecord(m.ev_t[5], st);
@@ -379,6 +408,11 @@ static int one_sweep(Model& m)
         cudaEventElapsedTime(&tot, m.ev_t[0], m.ev_t[6]);
         m.timing.ms_total += tot;
         m.timing.sweeps++;
+        float ag = 0.f;
+        cudaEventElapsedTime(&ag, m.ev_c[0], m.ev_t[3]);
+        m.timing.ms_allgather += ag;
+        cudaEventElapsedTime(&ag, m.ev_c[1], m.ev_t[5]);
+        m.timing.ms_allgather += ag;
         if (m.timing_detail && m.ev_top_used) {
             for (uint32_t i = 0; i + 1 < m.ev_top_used; i += 2) {
                 float t = 0.f;

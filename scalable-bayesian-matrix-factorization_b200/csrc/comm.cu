@@ -3,6 +3,7 @@
 #include "comm.h"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace sbmf {
@@ -100,10 +101,26 @@ int comm_allreduce_sum_f64(Comm& c, double* buf, size_t count, cudaStream_t st, 
     return 0;
 }
 
+// In-place all-gather-v of nseg strided segments.  Default: point-to-point -- every rank sends its own part of every
+// segment straight to every peer (one grouped NCCL launch, all NVLink links busy at once); SBMF_AGV=bcast selects one
+// broadcast per (segment, root) instead.
 template <typename T>
 static int allgatherv(Comm& c, T* base, size_t stride, int nseg, const size_t* offsets, const size_t* counts, int dtype, cudaStream_t st,
                       std::string& err)
 {
+    static const bool use_bcast = getenv("SBMF_AGV") && !strcmp(getenv("SBMF_AGV"), "bcast");
+    if (!use_bcast) {
+        NC(g_api.GroupStart());
+        for (int q = 0; q < c.world; ++q) {
+            if (q == c.rank) continue;
+            for (int s = 0; s < nseg; ++s) {
+                if (counts[c.rank]) NC(g_api.Send(base + (size_t)s * stride + offsets[c.rank], counts[c.rank], dtype, q, (ncclComm_t)c.nccl, st));
+                if (counts[q]) NC(g_api.Recv(base + (size_t)s * stride + offsets[q], counts[q], dtype, q, (ncclComm_t)c.nccl, st));
+            }
+        }
+        NC(g_api.GroupEnd());
+        return 0;
+    }
     NC(g_api.GroupStart());
     for (int s = 0; s < nseg; ++s)
         for (int q = 0; q < c.world; ++q) {

@@ -119,6 +119,7 @@ struct Model {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_t[8] = {};
     cudaEvent_t ev_call[2] = {};
+    cudaEvent_t ev_c[2] = {};          // start of the post-phase all-gathers (multi-GPU)
     std::vector<cudaEvent_t> ev_top;   // 2 per launch of the dominant kernel in one phase
     uint32_t ev_top_used = 0;
     bool timing_enabled = true;

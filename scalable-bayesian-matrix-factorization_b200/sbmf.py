@@ -42,7 +42,7 @@ class Timing(C.Structure):
                 ("ms_item_phase", C.c_double), ("ms_eval", C.c_double), ("ms_total", C.c_double), ("sweeps", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("nnz_light_user", C.c_uint64), ("nnz_heavy_user", C.c_uint64),
                 ("nnz_light_item", C.c_uint64), ("nnz_heavy_item", C.c_uint64), ("ms_top_kernel", C.c_double),
-                ("top_kernel_launches", C.c_uint64), ("top_kernel_ratings", C.c_uint64)]
+                ("top_kernel_launches", C.c_uint64), ("top_kernel_ratings", C.c_uint64), ("ms_allgather", C.c_double)]
 
 
 class SynthSpec(C.Structure):
