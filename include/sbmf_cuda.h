@@ -113,7 +113,7 @@ typedef struct sbmf_timing {
     double ms_top_kernel;        /* sum of its launch durations */
     uint64_t top_kernel_launches;
     uint64_t top_kernel_ratings; /* ratings one launch streams (each for 8 latent dimensions) */
-    double ms_allgather;         /* multi-GPU: the factor/bias all-gathers after the two phases (part of ms_user_phase / ms_item_phase) */
+    double ms_allgather;         /* multi-GPU: grouped V all-gather + reverse residual all-to-all after the item phase (the U all-gather rides in ms_exchange) */
 } sbmf_timing;
 
 /* ---- life cycle ------------------------------------------------------------------------------------ */

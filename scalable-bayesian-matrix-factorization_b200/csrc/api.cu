@@ -359,7 +359,7 @@ static int one_sweep(Model& m)
     if (standalone) {
         launch_rebuild(m, st);                       // [T]:342-359
     } else {
-        if (m.e_in_csc) crc |= launch_permute(m, false, st);
+        if (m.e_in_csc) crc |= launch_permute(m, false, nullptr, st);   // (single GPU, or first use; multi-GPU sweeps do it at their end)
         launch_stats(m, st);
     }
     crc |= launch_reduce_pair(m, st);                // sum e, sum e^2 (all ranks)
@@ -367,18 +367,29 @@ static int one_sweep(Model& m)
     launch_global_hypers(m, st);                     // [T]:366-410
     launch_dim_hypers(m, st);                        // [T]:415-467
     launch_bias_hypers(m, st);                       // [T]:469-511
+    // peer-mapped replicas: the user phase writes U rows into every replica, so every rank must be done reading U first
+    if (m.peer_ok) crc |= launch_barrier(m, st);
     if (timing) cudaEventRecord(m.ev_t[2], st);
     launch_phase(m, m.us, m.it, true, fused);        // [T]:514-558 (+ the fused residual refresh)
-    if (timing) cudaEventRecord(m.ev_c[0], st);
-    crc |= launch_allgather_side(m, m.us, st);       // multi-GPU: replicate the updated U rows and user biases
     if (timing) cudaEventRecord(m.ev_t[3], st);
-    crc |= launch_permute(m, true, st);              // residual CSR order -> CSC order (all-to-all across GPUs)
+    // residual CSR order -> CSC order; multi-GPU: all-to-all grouped with the all-gather of the updated U rows and user biases
+    crc |= launch_permute(m, true, &m.us, st);
     if (timing) cudaEventRecord(m.ev_t[4], st);
     launch_phase(m, m.it, m.us, false, false);       // [T]:563-606
-    if (timing) cudaEventRecord(m.ev_c[1], st);
-    crc |= launch_allgather_side(m, m.it, st);
     m.e_in_csc = true;
     if (timing) cudaEventRecord(m.ev_t[5], st);
+    if (m.world > 1) {
+        // replicate the updated V rows / item biases; if the next sweep starts from the incremental residual, its CSC -> CSR
+        // all-to-all rides in the same grouped launch
+        const bool next_standalone = ((m.sweeps_done + 1) % m.cfg.rebuild_every) == 0 && m.cfg.residual_mode == 1;
+        if (!next_standalone) {
+            crc |= launch_permute(m, false, &m.it, st);
+            m.e_in_csc = false;
+        } else {
+            crc |= launch_allgather_side(m, m.it, st);
+        }
+    }
+    if (timing) cudaEventRecord(m.ev_c[0], st);
     launch_eval(m, st);                              // [T]:610-636
     crc |= launch_reduce_pair(m, st);
     launch_eval_final(m, st);
@@ -398,20 +409,20 @@ static int one_sweep(Model& m)
         }
         float ms[6];
         for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms[i], m.ev_t[i], m.ev_t[i + 1]);
+        float ag_pre = 0.f;
+        cudaEventElapsedTime(&ag_pre, m.ev_t[5], m.ev_c[0]);
         m.timing.ms_rebuild += ms[0];
         m.timing.ms_hypers += ms[1];
         m.timing.ms_user_phase += ms[2];
         m.timing.ms_exchange += ms[3];
         m.timing.ms_item_phase += ms[4];
-        m.timing.ms_eval += ms[5];
+        m.timing.ms_eval += ms[5] - ag_pre;
         float tot = 0.f;
         cudaEventElapsedTime(&tot, m.ev_t[0], m.ev_t[6]);
         m.timing.ms_total += tot;
         m.timing.sweeps++;
-        float ag = 0.f;
-        cudaEventElapsedTime(&ag, m.ev_c[0], m.ev_t[3]);
-        m.timing.ms_allgather += ag;
-        cudaEventElapsedTime(&ag, m.ev_c[1], m.ev_t[5]);
+        float ag = 0.f;   // multi-GPU: the grouped V all-gather (+ reverse residual all-to-all) between item phase and evaluation
+        cudaEventElapsedTime(&ag, m.ev_t[5], m.ev_c[0]);
         m.timing.ms_allgather += ag;
         if (m.timing_detail && m.ev_top_used) {
             for (uint32_t i = 0; i + 1 < m.ev_top_used; i += 2) {

@@ -146,6 +146,18 @@ int comm_allgatherv_strided_f32(Comm& c, float* base, size_t stride, int nseg, c
     return allgatherv<float>(c, base, stride, nseg, offsets, counts, ncclFloat32, st, err);
 }
 
+int comm_group_begin(std::string& err)
+{
+    if (!load(err)) return -1;
+    NC(g_api.GroupStart());
+    return 0;
+}
+int comm_group_end(std::string& err)
+{
+    NC(g_api.GroupEnd());
+    return 0;
+}
+
 int comm_alltoallv_f32(Comm& c, const float* send, const size_t* send_off, const size_t* send_cnt, float* recv, const size_t* recv_off,
                        const size_t* recv_cnt, cudaStream_t st, std::string& err)
 {

@@ -25,6 +25,10 @@ int comm_allgatherv_f64(Comm& c, double* buf, const size_t* offsets, const size_
 // several in-place allgatherv's (same counts/offsets pattern, `nseg` base pointers with stride) fused in one NCCL group
 int comm_allgatherv_strided_f32(Comm& c, float* base, size_t stride, int nseg, const size_t* offsets, const size_t* counts, cudaStream_t st,
                                 std::string& err);
+// NCCL groups nest: everything enqueued between begin and end (including the calls above) becomes ONE grouped launch, so
+// independent exchanges share the links instead of running back to back
+int comm_group_begin(std::string& err);
+int comm_group_end(std::string& err);
 int comm_alltoallv_f32(Comm& c, const float* send, const size_t* send_off, const size_t* send_cnt, float* recv, const size_t* recv_off,
                        const size_t* recv_cnt, cudaStream_t st, std::string& err);
 

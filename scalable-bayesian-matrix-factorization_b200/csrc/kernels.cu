@@ -29,6 +29,11 @@ struct PhaseArgs {
     const uint32_t* idx;
     float* e;
     float* Fself;
+    // replicas of Fself / bias to write updated rows to: [0, nrep).  One GPU: just the local arrays.  G GPUs with peer access:
+    // every rank's replica (peer-mapped over NVLink) -- the all-gather is fused into the update
+    float* Frep[MAX_PEERS];
+    float* brep[MAX_PEERS];
+    int nrep;
     const float* Fother;
     uint32_t ns_self, ns_other;   // rows per factor block INCLUDING the all-zero pad row at index n (gather target of empty slots)
     float* bias;
@@ -126,8 +131,8 @@ struct SolveOut {
 
 // uo / sig / mu are this lane's (dimension kq = lane & 7) old factor value and hyper-parameters, loaded by the caller
 // early enough to hide their latency; lanes of padding dimensions pass uo = 0 and get delta 0.
-__device__ __forceinline__ SolveOut solve_lanes(const float* sm, float* Fs, float uo, float sig, float mu, bool live, int mode, float z,
-                                                float alpha, int lane)
+__device__ __forceinline__ SolveOut solve_lanes(const float* sm, const PhaseArgs& a, size_t foff, float uo, float sig, float mu, bool live,
+                                                int mode, float z, float alpha, int lane)
 {
     const int kq = lane & 7;
     const float4 g0 = *reinterpret_cast<const float4*>(sm + 8 + kq * G_STRIDE);
@@ -159,7 +164,10 @@ __device__ __forceinline__ SolveOut solve_lanes(const float* sm, float* Fs, floa
 #pragma unroll
     for (int l = 0; l < 8; ++l) mine = (kq == l) ? o.d[l] : mine;
     o.mine = mine;
-    if (lane < 8) Fs[kq] = uo - mine;
+    if (lane < 8) {
+        const float un = uo - mine;
+        for (int q = 0; q < a.nrep; ++q) a.Frep[q][foff + kq] = un;   // 8 lanes x 4 B = one sector per replica
+    }
     return o;
 }
 
@@ -254,16 +262,17 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 #pragma unroll
         for (int r = 0; r < RPL; ++r)
             if (id[r] != pad_row) e[r] += d;
-        if (t_in_row == 0) a.bias[row] = bn;
+        if (t_in_row == 0)
+            for (int q = 0; q < a.nrep; ++q) a.brep[q][row] = bn;
         bias_new = bn;
     }
 
     float zq = 0.f;
     for (int b = b_begin; b < b_end; ++b) {
         // this lane's dimension of the block: old value and hyper-parameters (latency hidden behind the accumulation)
-        float* Fs = a.Fself + ((size_t)b * ns_self + row) * 8;
+        const size_t foff = ((size_t)b * ns_self + row) * 8;
         const bool live = (uint32_t)(b * 8 + kq) < K;
-        const float uo = live ? Fs[kq] : 0.f;
+        const float uo = live ? a.Fself[foff + kq] : 0.f;
         const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
         // this row's noise, 4 blocks at a time: lane l draws dimension 32*(b/4) + l
         if (mode != SAMPLE_ZERO && (((b & 3) == 0) || b == b_begin))
@@ -319,10 +328,10 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         }
         SolveOut so;
         if (WARPS == 1) {
-            so = solve_lanes(tot, Fs, uo, sig, mu, live, mode, z, alpha, lane);
+            so = solve_lanes(tot, a, foff, uo, sig, mu, live, mode, z, alpha, lane);
         } else {   // warp 0 solves and publishes the 8 deltas
             if (warp == 0) {
-                so = solve_lanes(tot, Fs, uo, sig, mu, live, mode, z, alpha, lane);
+                so = solve_lanes(tot, a, foff, uo, sig, mu, live, mode, z, alpha, lane);
                 if (lane < 8) s_d[lane] = so.mine;
             }
             __syncthreads();
@@ -501,7 +510,7 @@ heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const u
         if (a.mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
         const float bn = draw_f32(a.mode, mean, s, z);
         if (lane == 0) {
-            a.bias[row] = bn;
+            for (int q = 0; q < a.nrep; ++q) a.brep[q][row] = bn;
             hbias_delta[hrow] = bo - bn;
         }
     } else {
@@ -518,13 +527,13 @@ heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const u
         float z[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) z[k] = __shfl_sync(0xffffffffu, zl, k);
-        float* Fs = a.Fself + ((size_t)b * a.ns_self + row) * 8;
-        const f8 uo = ld256(Fs);
+        const size_t foff = ((size_t)b * a.ns_self + row) * 8;
+        const f8 uo = ld256(a.Fself + foff);
         f8 un;
         float d[8];
         solve_block(s_tot[warp], uo, z, a.sigma_kf + b * 8, a.mu_kf + b * 8, alpha, a.mode, (int)a.K - b * 8, un, d);
         if (lane == 0) {
-            st256(Fs, un);
+            for (int q = 0; q < a.nrep; ++q) st256(a.Frep[q] + foff, un);
 #pragma unroll
             for (int k = 0; k < 8; ++k) hdelta[(size_t)hrow * 8 + k] = d[k];
         }
@@ -970,6 +979,14 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     a.idx = self.idx;
     a.e = self.e;
     a.Fself = self.F;
+    {
+        const int side = (&self == &m.us) ? 0 : 1;
+        a.nrep = m.peer_ok ? m.world : 1;
+        for (int q = 0; q < MAX_PEERS; ++q) {
+            a.Frep[q] = (m.peer_ok && q < m.world) ? m.pF[side][q] : self.F;
+            a.brep[q] = (m.peer_ok && q < m.world) ? m.pbias[side][q] : self.bias;
+        }
+    }
     a.Fother = other.F;
     a.ns_self = self.n + 1;
     a.ns_other = other.n + 1;
@@ -1049,6 +1066,9 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
 // Residual between the two slot orders.  One GPU: a gather through perm.  G GPUs: every value moves from the rank that owns
 // its user to the rank that owns its item -- pack in the destination's CSC order, one grouped NCCL send/recv over NVLink,
 // unpack through recv_pos (plan.cpp).
+int launch_allgather_side(Model& m, Side& s, cudaStream_t st);
+static int permute_peer(Model& m, bool csr_to_csc, cudaStream_t st);
+
 __global__ void __launch_bounds__(256)
 invert_perm_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ inv, uint64_t n)
 {
@@ -1069,7 +1089,7 @@ static bool ensure_inverse(Model& m, const uint32_t* perm, uint32_t** inv, uint6
     return true;
 }
 
-int launch_permute(Model& m, bool csr_to_csc, cudaStream_t st)
+int launch_permute(Model& m, bool csr_to_csc, Side* gather_side, cudaStream_t st)
 {
     if (m.world == 1) {
         const uint32_t g = grid_for(m.N, 256, m.sm_count * 16);
@@ -1079,19 +1099,91 @@ int launch_permute(Model& m, bool csr_to_csc, cudaStream_t st)
         m.launches++;
         return 0;
     }
+    if (m.peer_ok) return permute_peer(m, csr_to_csc, st);   // updated rows were already written into every replica by the phase kernels
+    // G GPUs: one grouped NCCL launch carries the residual all-to-all AND the all-gather of the rows this rank just updated
+    // (both needed before the next phase; together they keep all NVLink links busy instead of running back to back)
     const uint32_t gs = grid_for(m.n_csr, 256, m.sm_count * 16), gr = grid_for(m.n_csc, 256, m.sm_count * 16);
-    int rc;
+    int rc = 0;
     if (csr_to_csc) {
         permute_gather_kernel<<<gs, 256, 0, st>>>(m.us.e, m.send_idx, m.sendbuf, m.n_csr);
-        rc = comm_alltoallv_f32(m.comm, m.sendbuf, m.send_off.data(), m.send_cnt.data(), m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), st, m.err);
+        rc |= comm_group_begin(m.err);
+        rc |= comm_alltoallv_f32(m.comm, m.sendbuf, m.send_off.data(), m.send_cnt.data(), m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), st, m.err);
+        if (gather_side) rc |= launch_allgather_side(m, *gather_side, st);
+        rc |= comm_group_end(m.err);
         permute_gather_kernel<<<gr, 256, 0, st>>>(m.recvbuf, m.recv_pos, m.it.e, m.n_csc);
     } else {
         if (ensure_inverse(m, m.recv_pos, &m.recv_pos_inv, m.n_csc, st)) permute_gather_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos_inv, m.recvbuf, m.n_csc);
         else permute_scatter_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos, m.recvbuf, m.n_csc);
-        rc = comm_alltoallv_f32(m.comm, m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), m.sendbuf, m.send_off.data(), m.send_cnt.data(), st, m.err);
+        rc |= comm_group_begin(m.err);
+        rc |= comm_alltoallv_f32(m.comm, m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), m.sendbuf, m.send_off.data(), m.send_cnt.data(), st, m.err);
+        if (gather_side) rc |= launch_allgather_side(m, *gather_side, st);
+        rc |= comm_group_end(m.err);
         if (ensure_inverse(m, m.send_idx, &m.send_idx_inv, m.n_csr, st)) permute_gather_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx_inv, m.us.e, m.n_csr);
         else permute_scatter_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx, m.us.e, m.n_csr);
     }
+    m.launches += 2;
+    return rc;
+}
+
+// Residual exchange as direct NVLink stores: position i of my send order belongs to destination rank q = segment of i, and goes
+// to dst[q][dst_off[q] + (i - seg_off[q])] in q's receive buffer.  src_idx[i] = local slot to read.
+struct PushArgs {
+    float* dst[MAX_PEERS];
+    uint64_t seg_off[MAX_PEERS + 1];
+    uint64_t dst_off[MAX_PEERS];
+    int world;
+};
+__global__ void __launch_bounds__(256)
+push_kernel(const float* __restrict__ e, const uint32_t* __restrict__ src_idx, PushArgs pa, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        int q = 0;
+#pragma unroll
+        for (int k = 1; k < MAX_PEERS; ++k) q += (k < pa.world && i >= pa.seg_off[k]) ? 1 : 0;
+        pa.dst[q][pa.dst_off[q] + (i - pa.seg_off[q])] = e[src_idx[i]];
+    }
+    __threadfence_system();
+}
+
+int launch_barrier(Model& m, cudaStream_t st)
+{
+    if (m.world == 1) return 0;
+    return comm_allreduce_sum_f64(m.comm, m.bar, 1, st, m.err);
+}
+
+// forward (CSR -> CSC) / reverse exchange with peer pushes: pack+send in one kernel, barrier, unpack
+static int permute_peer(Model& m, bool csr_to_csc, cudaStream_t st)
+{
+    PushArgs pa;
+    pa.world = m.world;
+    const uint32_t gs = grid_for(m.n_csr, 256, m.sm_count * 16), gr = grid_for(m.n_csc, 256, m.sm_count * 16);
+    if (csr_to_csc) {
+        for (int q = 0; q < m.world; ++q) {
+            pa.dst[q] = m.precv[q];
+            pa.seg_off[q] = m.send_off[q];
+            pa.dst_off[q] = m.fwd_dst_off[q];
+        }
+        pa.seg_off[m.world] = m.n_csr;
+        push_kernel<<<gs, 256, 0, st>>>(m.us.e, m.send_idx, pa, m.n_csr);
+        int rc = launch_barrier(m, st);   // also: every peer has finished its user phase, so all U rows / biases have landed here
+        permute_gather_kernel<<<gr, 256, 0, st>>>(m.recvbuf, m.recv_pos, m.it.e, m.n_csc);
+        m.launches += 2;
+        return rc;
+    }
+    if (!ensure_inverse(m, m.recv_pos, &m.recv_pos_inv, m.n_csc, st) || !ensure_inverse(m, m.send_idx, &m.send_idx_inv, m.n_csr, st)) {
+        m.err = "out of device memory for the inverse exchange maps";
+        return -1;
+    }
+    for (int q = 0; q < m.world; ++q) {
+        pa.dst[q] = m.psend[q];
+        pa.seg_off[q] = m.recv_off[q];
+        pa.dst_off[q] = m.rev_dst_off[q];
+    }
+    pa.seg_off[m.world] = m.n_csc;
+    // position i of my receive order holds local CSC slot recv_pos_inv[i]; it returns to the rank it came from
+    push_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos_inv, pa, m.n_csc);
+    int rc = launch_barrier(m, st);       // also: all V rows / item biases have landed
+    permute_gather_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx_inv, m.us.e, m.n_csr);
     m.launches += 2;
     return rc;
 }
@@ -1107,6 +1199,7 @@ int launch_reduce_pair(Model& m, cudaStream_t st)
 int launch_allgather_side(Model& m, Side& s, cudaStream_t st)
 {
     if (m.world == 1) return 0;
+    if (m.peer_ok) return launch_barrier(m, st);   // rows were pushed by the phase kernels; only make sure every peer is done
     const std::vector<uint32_t>& bd = (&s == &m.us) ? m.ub : m.ib;
     std::vector<size_t> off(m.world), cnt(m.world), off8(m.world), cnt8(m.world);
     for (int q = 0; q < m.world; ++q) {

@@ -25,6 +25,7 @@ constexpr int NBINS = 7;            // resident-row bins, see kBin* below
 constexpr int RESIDENT_MAX = 2048;  // longer rows go through the streaming ("heavy") pipeline
 constexpr int SLICE_LEN = 4096;     // ratings per heavy-row slice (one CTA)
 constexpr int SLICE_THREADS = 256;
+constexpr int MAX_PEERS = 8;         // replicas a phase kernel can write directly (one NVSwitch domain)
 
 // resident bins: a row of c ratings is handled by WARPS warps holding RPL ratings per lane in registers
 struct BinShape { int rpl, warps, cap; };
@@ -103,6 +104,17 @@ struct Model {
     uint32_t* recv_pos = nullptr;     // [n_csc] receive-buffer position of each local CSC slot (grouped by source rank)
     float *sendbuf = nullptr, *recvbuf = nullptr;
     std::vector<size_t> send_off, send_cnt, recv_off, recv_cnt;
+    // peer-mapped replicas (CUDA IPC over NVLink, world <= MAX_PEERS): every rank writes the rows it updates straight into all
+    // replicas from inside the phase kernels, and pushes its residual segments into the peers' exchange buffers; NCCL then only
+    // carries two 16-byte all-reduces per sweep plus tiny barriers.  Falls back to the NCCL exchanges if IPC is unavailable.
+    bool peer_ok = false;
+    float* pF[2][8] = {};             // [side: 0 users, 1 items][rank] factor replica of that rank (own entry = local pointer)
+    float* pbias[2][8] = {};
+    float* precv[8] = {};             // peers' recvbuf (forward exchange target)
+    float* psend[8] = {};             // peers' sendbuf (reverse exchange target)
+    std::vector<void*> ipc_opened;
+    std::vector<size_t> fwd_dst_off, rev_dst_off;   // start of MY segment in rank q's recvbuf / sendbuf
+    double* bar = nullptr;            // 1 double: payload of the barrier all-reduce
     uint64_t t_begin = 0, t_end = 0;  // this rank's slice of the test set
     double* red2 = nullptr;           // [2] reduced (and all-reduced) pair of sums: (sum e, sum e^2) or the two squared-error sums
     // test set
@@ -148,7 +160,11 @@ void launch_global_hypers(Model& m, cudaStream_t st);    // [T]:366-410 (final r
 void launch_dim_hypers(Model& m, cudaStream_t st);       // [T]:415-467
 void launch_bias_hypers(Model& m, cudaStream_t st);      // [T]:469-511
 void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh);   // [T]:514-558 / 563-606
-int launch_permute(Model& m, bool csr_to_csc, cudaStream_t st);   // one GPU: gather through perm; else all-to-all over NVLink
+// one GPU: gather through perm.  G GPUs: all-to-all over NVLink, grouped with the all-gather of gather_side's updated rows (may be null)
+int launch_permute(Model& m, bool csr_to_csc, Side* gather_side, cudaStream_t st);
+int setup_peer_access(Model& m);                                  // storage.cu: exchange IPC handles, map the peers' buffers
+void close_peer_access(Model& m);
+int launch_barrier(Model& m, cudaStream_t st);                    // cross-GPU barrier on the stream (1-element all-reduce)
 int launch_reduce_pair(Model& m, cudaStream_t st);                // red_part -> red2 (+ all-reduce over ranks)
 int launch_allgather_side(Model& m, Side& s, cudaStream_t st);    // replicate the rows each rank just updated (factors + bias)
 void launch_eval(Model& m, cudaStream_t st);             // [T]:610-636: prediction + partial squared errors of this rank's slice

@@ -87,4 +87,26 @@ int sbmf_cuda_plan_exchange(uint64_t n, const uint32_t* perm, int world, int ran
     return SBMF_OK;
 }
 
+// counts[src * world + dst] = number of residuals whose user lives on rank src (CSR owner) and whose item lives on rank dst
+// (CSC owner): the full traffic matrix of the residual exchange, from which every rank derives where its segments start in
+// its peers' receive buffers (direct NVLink pushes need no handshake).
+int sbmf_cuda_plan_pair_counts(uint64_t n, const uint32_t* perm, int world, const int64_t* csr_bounds, const int64_t* csc_bounds, int64_t* counts)
+{
+    if (!perm || !csr_bounds || !csc_bounds || !counts || world < 1) return SBMF_ERR_INVALID;
+    if ((uint64_t)csr_bounds[world] != n || (uint64_t)csc_bounds[world] != n) return SBMF_ERR_INVALID;
+    for (int i = 0; i < world * world; ++i) counts[i] = 0;
+    for (int dst = 0; dst < world; ++dst)
+        for (int64_t t = csc_bounds[dst]; t < csc_bounds[dst + 1]; ++t) {
+            const int64_t s = perm[t];
+            int lo = 0, hi = world - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) / 2;
+                if (csr_bounds[mid] <= s) lo = mid;
+                else hi = mid - 1;
+            }
+            counts[lo * world + dst]++;
+        }
+    return SBMF_OK;
+}
+
 }  // extern "C"

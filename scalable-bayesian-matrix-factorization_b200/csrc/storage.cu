@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include <stdio.h>
+#include <string.h>
 
 #include <algorithm>
 #include <chrono>
@@ -106,8 +107,117 @@ static void free_side(Side& s)
     s.prior = pr; s.prior_b = prb;
 }
 
+// Map every peer's factor / bias replicas and exchange buffers into this process (CUDA IPC; NVLink peer access is enabled
+// lazily by cudaIpcOpenMemHandle).  The 64-byte handles travel through one NCCL all-gather, so no extra host channel is needed.
+// Any failure leaves peer_ok = false: the NCCL exchanges are used instead.
+int setup_peer_access(Model& m)
+{
+    m.peer_ok = false;
+    const int G = m.world;
+    if (G > MAX_PEERS || getenv("SBMF_NO_PEER")) return SBMF_OK;
+    void* mine[6] = {m.us.F, m.it.F, m.us.bias, m.it.bias, m.recvbuf, m.sendbuf};
+    constexpr int HW = 6 * 64 / 4;   // floats per rank
+    std::vector<float> host((size_t)G * HW, 0.f);
+    float ok_flag = 1.f;
+    for (int i = 0; i < 6; ++i) {
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, mine[i]) != cudaSuccess) {
+            cudaGetLastError();
+            ok_flag = 0.f;
+            memset(&h, 0, sizeof(h));
+        }
+        memcpy(&host[(size_t)m.rank * HW + i * 16], &h, 64);
+    }
+    float* d = nullptr;
+    CK(cudaMalloc((void**)&d, ((size_t)G * HW + G) * 4));
+    CK(cudaMemset(d, 0, ((size_t)G * HW + G) * 4));
+    CK(cudaMemcpy(d + (size_t)m.rank * HW, &host[(size_t)m.rank * HW], HW * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d + (size_t)G * HW + m.rank, &ok_flag, 4, cudaMemcpyHostToDevice));
+    std::vector<size_t> off(G), cnt(G, HW), off1(G), cnt1(G, 1);
+    for (int q = 0; q < G; ++q) {
+        off[q] = (size_t)q * HW;
+        off1[q] = (size_t)G * HW + q;
+    }
+    if (comm_allgatherv_f32(m.comm, d, off.data(), cnt.data(), m.s_main, m.err) != 0 ||
+        comm_allgatherv_f32(m.comm, d, off1.data(), cnt1.data(), m.s_main, m.err) != 0) {
+        cudaFree(d);
+        return SBMF_ERR_NCCL;
+    }
+    std::vector<float> flags(G);
+    CK(cudaMemcpyAsync(host.data(), d, (size_t)G * HW * 4, cudaMemcpyDeviceToHost, m.s_main));
+    CK(cudaMemcpyAsync(flags.data(), d + (size_t)G * HW, (size_t)G * 4, cudaMemcpyDeviceToHost, m.s_main));
+    CK(cudaStreamSynchronize(m.s_main));
+    cudaFree(d);
+    bool all_ok = true;
+    for (int q = 0; q < G; ++q) all_ok = all_ok && flags[q] == 1.f;
+    // every rank must reach the same verdict: open, then agree through a second all-reduce-like exchange (sum of failures)
+    double fails = 0.0;
+    void* opened[MAX_PEERS][6] = {};
+    if (all_ok) {
+        for (int q = 0; q < G && fails == 0.0; ++q) {
+            for (int i = 0; i < 6; ++i) {
+                if (q == m.rank) {
+                    opened[q][i] = mine[i];
+                    continue;
+                }
+                cudaIpcMemHandle_t h;
+                memcpy(&h, &host[(size_t)q * HW + i * 16], 64);
+                void* p = nullptr;
+                if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    fails = 1.0;
+                    break;
+                }
+                opened[q][i] = p;
+                m.ipc_opened.push_back(p);
+            }
+        }
+    } else {
+        fails = 1.0;
+    }
+    CK(cudaMemcpy(m.bar, &fails, 8, cudaMemcpyHostToDevice));
+    if (comm_allreduce_sum_f64(m.comm, m.bar, 1, m.s_main, m.err) != 0) return SBMF_ERR_NCCL;
+    CK(cudaMemcpyAsync(&fails, m.bar, 8, cudaMemcpyDeviceToHost, m.s_main));
+    CK(cudaStreamSynchronize(m.s_main));
+    CK(cudaMemset(m.bar, 0, 8));
+    if (fails != 0.0) {
+        close_peer_access(m);
+        return SBMF_OK;   // NCCL fallback
+    }
+    for (int q = 0; q < G; ++q) {
+        m.pF[0][q] = (float*)opened[q][0];
+        m.pF[1][q] = (float*)opened[q][1];
+        m.pbias[0][q] = (float*)opened[q][2];
+        m.pbias[1][q] = (float*)opened[q][3];
+        m.precv[q] = (float*)opened[q][4];
+        m.psend[q] = (float*)opened[q][5];
+    }
+    m.peer_ok = true;
+    return SBMF_OK;
+}
+
+void close_peer_access(Model& m)
+{
+    for (void* p : m.ipc_opened) cudaIpcCloseMemHandle(p);
+    m.ipc_opened.clear();
+    m.peer_ok = false;
+}
+
 void free_storage(Model& m)
 {
+    if (m.world > 1 && m.comm.nccl && m.have_train) {
+        // peers may still be writing into / reading from our buffers: meet them before anything is unmapped or freed
+        cudaStreamSynchronize(m.s_main);
+        cudaStreamSynchronize(m.s_aux);
+        if (m.bar) {
+            std::string err;
+            comm_allreduce_sum_f64(m.comm, m.bar, 1, m.s_main, err);
+            cudaStreamSynchronize(m.s_main);
+        }
+    }
+    close_peer_access(m);
+    cudaFree(m.bar);
+    m.bar = nullptr;
     free_side(m.us);
     free_side(m.it);
     cudaFree(m.csr_urow); cudaFree(m.csr_r); cudaFree(m.csr_id); cudaFree(m.csc_id); cudaFree(m.perm); cudaFree(m.pacc);
@@ -203,6 +313,8 @@ static cudaError_t slice_inplace(T*& arr, uint64_t off, uint64_t cnt)
 // multi-GPU: cut the global layout into this rank's CSR shard (its users) and CSC shard (its items) and plan the residual
 // all-to-all (plan.cpp).  Every rank built the same global layout from the same COO, so all plans agree.
 extern "C" int sbmf_cuda_plan_shards(const int64_t* ptr, uint32_t n_rows, int world, uint32_t* bounds);
+extern "C" int sbmf_cuda_plan_pair_counts(uint64_t n, const uint32_t* perm, int world, const int64_t* csr_bounds, const int64_t* csc_bounds,
+                                          int64_t* counts);
 extern "C" int sbmf_cuda_plan_exchange(uint64_t n, const uint32_t* perm, int world, int rank, const int64_t* csr_bounds, const int64_t* csc_bounds,
                                        uint32_t* send_idx, int64_t* send_counts, uint32_t* recv_pos, int64_t* recv_counts);
 
@@ -231,6 +343,21 @@ static int shard_storage(Model& m)
         if (sbmf_cuda_plan_exchange(m.N, perm.data(), G, r, cb.data(), tb.data(), sidx.data(), sc.data(), rpos.data(), rc.data()) != SBMF_OK) {
             m.err = "set_train: exchange planning failed (internal)";
             return SBMF_ERR_INVALID;
+        }
+        {   // where my segments start in every peer's buffers (for the direct-push exchange)
+            std::vector<int64_t> pc((size_t)G * G);
+            sbmf_cuda_plan_pair_counts(m.N, perm.data(), G, cb.data(), tb.data(), pc.data());
+            m.fwd_dst_off.assign(G, 0);
+            m.rev_dst_off.assign(G, 0);
+            for (int q = 0; q < G; ++q) {
+                size_t f = 0, b = 0;
+                for (int x = 0; x < r; ++x) {
+                    f += (size_t)pc[(size_t)x * G + q];   // residuals rank x sends to q precede mine in q's recvbuf
+                    b += (size_t)pc[(size_t)q * G + x];   // residuals q originally sent to x precede mine in q's sendbuf
+                }
+                m.fwd_dst_off[q] = f;
+                m.rev_dst_off[q] = b;
+            }
         }
         m.send_off.assign(G, 0); m.send_cnt.assign(G, 0); m.recv_off.assign(G, 0); m.recv_cnt.assign(G, 0);
         size_t so = 0, ro = 0;
@@ -375,6 +502,9 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     CK(dmalloc(&m.red_part, (size_t)m.red_blocks * 2));
     CK(dmalloc(&m.red2, 2));
     CK(dmalloc(&m.pacc, m.n_csr));
+    CK(dmalloc(&m.bar, 1));
+    CK(cudaMemset(m.bar, 0, 8));
+    if (m.world > 1 && (rc = setup_peer_access(m)) != SBMF_OK) return rc;
     tr.lap("alloc state");
     m.have_train = true;
     m.e_in_csc = false;

@@ -238,3 +238,101 @@ def test_synth_properties():
     assert all(np.array_equal(s[k], s2[k]) for k in ("train_user", "train_item", "train_rating", "test_user", "test_item"))
     deg = np.bincount(s["train_item"], minlength=3706)
     assert deg.max() > 20 * np.median(deg[deg > 0])       # Zipf-skewed popularity
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def tiny_case(I, J, pairs, ratings, test_pairs=((0, 0),), test_ratings=(3.0,)):
+    u = np.array([p[0] for p in pairs], np.uint32); i = np.array([p[1] for p in pairs], np.uint32)
+    tu = np.array([p[0] for p in test_pairs], np.uint32); ti = np.array([p[1] for p in test_pairs], np.uint32)
+    return {"train_user": u, "train_item": i, "train_rating": np.array(ratings, np.float32), "test_user": tu, "test_item": ti,
+            "test_rating": np.array(test_ratings, np.float32), "num_users": I, "num_items": J}
+
+
+@pytest.mark.parametrize("K", [1, 7, 8, 9, 64, 256])
+def test_edge_latent_dimensions(K, tiny):
+    """K not a multiple of the 8-wide factor block, K = 1 and K = SBMF_MAX_K."""
+    m, o = make_pair(tiny, K, 2)
+    init_both(m, o, tiny, K)
+    m.sweep(4)
+    o.sweep(4)
+    check_state(m.get_state(), o.state(), 1e-4, what=("U", "V", "b_i", "b_j", "sigma_u", "mu_u", "sigma_v", "mu_v"))
+    m.close()
+
+
+def test_edge_single_rating_and_empty_rows():
+    d = tiny_case(5, 4, [(2, 1)], [4.0], test_pairs=[(2, 1), (0, 3), (4, 0)], test_ratings=[4.0, 3.0, 1.0])
+    for mode in (2, 0):
+        m, o = make_pair(d, 8, mode, seed=5)
+        init_both(m, o, d, 8)
+        m.sweep(6)
+        r_o, _ = o.sweep(6)
+        r_g, _ = m.rmse_history(0, 6)
+        assert np.all(np.isfinite(r_g))
+        if mode == 2:
+            check_state(m.get_state(), o.state(), 1e-4, what=("U", "V", "b_i", "b_j"))
+            assert np.max(np.abs(r_g - r_o)) <= 1e-5
+        m.close()
+
+
+def test_edge_empty_training_set():
+    """[T] with a missing train file runs on 0 ratings; here: prior-only updates, finite output."""
+    import sbmf
+    m = sbmf.SbmfModel(K=8, sample_mode=2)
+    e = np.empty(0, np.uint32)
+    m.set_train(e, e, np.empty(0, np.float32), 3, 3)
+    m.set_test(np.array([0, 2], np.uint32), np.array([1, 2], np.uint32), np.array([3.0, 4.0], np.float32))
+    m.init_factors()
+    m.sweep(3)
+    r, _ = m.rmse_history(0, 3)
+    s = m.get_state()
+    assert np.all(np.isfinite(r)) and np.all(np.isfinite(s["U"])) and np.all(np.isfinite(s["V"]))
+    m.close()
+
+
+def test_error_behaviour(ml100k):
+    import sbmf
+    d = ml100k
+    m = sbmf.SbmfModel(K=8)
+    with pytest.raises(sbmf.SbmfError) as e:
+        m.sweep(1)                                             # call order: no training set yet
+    assert e.value.code == -4
+    with pytest.raises(sbmf.SbmfError) as e:
+        m.set_train(d["train_user"], d["train_item"], d["train_rating"], 10, d["num_items"])   # ids out of range
+    assert e.value.code == -1 and "out of range" in str(e.value)
+    m.set_train(d["train_user"], d["train_item"], d["train_rating"], d["num_users"], d["num_items"])
+    with pytest.raises(sbmf.SbmfError) as e:
+        m.set_test(np.array([99999], np.uint32), np.array([0], np.uint32), np.array([1.0], np.float32))
+    assert e.value.code == -1
+    with pytest.raises(sbmf.SbmfError):
+        sbmf.SbmfModel(K=0)
+    with pytest.raises(sbmf.SbmfError):
+        sbmf.SbmfModel(K=257)
+    m.close()
+
+
+def test_reset_by_init_factors(ml100k):
+    """init_factors restarts the chain: same seed -> the same trajectory again, prediction sums cleared ([T]:145, 268-281)."""
+    import sbmf
+    d = ml100k
+    m = sbmf.SbmfModel(K=20, seed=3)
+    m.set_train(d["train_user"], d["train_item"], d["train_rating"], d["num_users"], d["num_items"])
+    m.set_test(d["test_user"], d["test_item"], d["test_rating"])
+    m.init_factors(); m.sweep(4); a = m.rmse_history(0, 4)[0].copy(); pa = m.get_pred().copy()
+    m.init_factors(); m.sweep(4); b = m.rmse_history(0, 4)[0]; pb = m.get_pred()
+    assert np.array_equal(a, b) and np.array_equal(pa, pb)
+    m.close()
+
+
+def test_burn_in_and_sqrt_mode(ml100k):
+    import sbmf
+    d = ml100k
+    m = sbmf.SbmfModel(K=20, seed=3, burn_in=3, sample_mode=1)
+    m.set_train(d["train_user"], d["train_item"], d["train_rating"], d["num_users"], d["num_items"])
+    m.set_test(d["test_user"], d["test_item"], d["test_rating"])
+    m.init_factors(); m.sweep(6)
+    mean, sweep = m.rmse_history(0, 6)
+    assert np.allclose(mean[:4], sweep[:4])                   # before / at the first collected sweep the mean IS the sweep's prediction
+    assert mean[5] < sweep[5] + 1e-3                          # averaging does not hurt
+    p = m.get_pred()
+    assert p.min() >= 0.5 - 1e-6 and p.max() <= 5.0 + 1e-6
+    m.close()
