@@ -141,6 +141,10 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
     }
     ok = ok && cudaStreamCreateWithFlags(&m.s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&m.s_aux, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = cudaStreamCreateWithFlags(&m.s_res[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&m.ev_join_res[i], cudaEventDisableTiming) == cudaSuccess;
+    }
     ok = ok && cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&m.ev_join, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&m.ev_t[i]) == cudaSuccess;
@@ -214,6 +218,10 @@ int sbmf_cuda_destroy(sbmf_handle* h)
     if (m.ev_join) cudaEventDestroy(m.ev_join);
     if (m.s_main) cudaStreamDestroy(m.s_main);
     if (m.s_aux) cudaStreamDestroy(m.s_aux);
+    for (int i = 0; i < 2; ++i) {
+        if (m.ev_join_res[i]) cudaEventDestroy(m.ev_join_res[i]);
+        if (m.s_res[i]) cudaStreamDestroy(m.s_res[i]);
+    }
     delete h;
     return SBMF_OK;
 }

@@ -1005,11 +1005,14 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
 
     const int KB = (int)m.KB;
     const bool heavy = self.n_heavy > 0;
+    // row classes are independent (disjoint rows, slots and factor rows): the streaming pipeline runs on its own stream and the
+    // resident bins are spread over three, so the tail of one launch overlaps the head of another
     cudaStream_t sr = m.s_main, sh = m.s_aux;
-    if (heavy) {
-        cudaEventRecord(m.ev_fork, sr);
-        cudaStreamWaitEvent(sh, m.ev_fork, 0);
-    }
+    cudaStream_t sb[3] = {m.s_main, m.s_res[0], m.s_res[1]};
+    cudaEventRecord(m.ev_fork, sr);
+    if (heavy) cudaStreamWaitEvent(sh, m.ev_fork, 0);
+    cudaStreamWaitEvent(sb[1], m.ev_fork, 0);
+    cudaStreamWaitEvent(sb[2], m.ev_fork, 0);
     // resident rows: as many blocks per launch as keep the gathered factor blocks L2-resident
     const size_t block_bytes = (size_t)other.n * 32;
     int nb = (int)((size_t)(48u << 20) / (block_bytes ? block_bytes : 1));
@@ -1018,14 +1021,18 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     for (int b0 = 0; b0 < KB; b0 += nb) {
         const int b1 = (b0 + nb < KB) ? b0 + nb : KB;
         const int do_bias = (b0 == 0) ? 1 : 0;
-        launch_bin<0>(m, a, self, b0, b1, do_bias, refresh, sr);
-        launch_bin<1>(m, a, self, b0, b1, do_bias, refresh, sr);
-        launch_bin<2>(m, a, self, b0, b1, do_bias, refresh, sr);
-        launch_bin<3>(m, a, self, b0, b1, do_bias, refresh, sr);
-        launch_bin<4>(m, a, self, b0, b1, do_bias, refresh, sr);
-        launch_bin<5>(m, a, self, b0, b1, do_bias, refresh, sr);
-        launch_bin<6>(m, a, self, b0, b1, do_bias, refresh, sr);
+        launch_bin<6>(m, a, self, b0, b1, do_bias, refresh, sb[0]);   // longest rows first
+        launch_bin<5>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
+        launch_bin<4>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
+        launch_bin<3>(m, a, self, b0, b1, do_bias, refresh, sb[0]);
+        launch_bin<2>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
+        launch_bin<1>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
+        launch_bin<0>(m, a, self, b0, b1, do_bias, refresh, sb[0]);
     }
+    cudaEventRecord(m.ev_join_res[0], sb[1]);
+    cudaEventRecord(m.ev_join_res[1], sb[2]);
+    cudaStreamWaitEvent(sr, m.ev_join_res[0], 0);
+    cudaStreamWaitEvent(sr, m.ev_join_res[1], 0);
     if (heavy) {
         const uint32_t ns = self.n_slices, nh = self.n_heavy;
         const uint32_t gs = (nh + 3) / 4;

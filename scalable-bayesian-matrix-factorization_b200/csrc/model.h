@@ -128,6 +128,8 @@ struct Model {
     uint32_t hist_cap = 0;
 
     cudaStream_t s_main = nullptr, s_aux = nullptr;
+    cudaStream_t s_res[2] = {};        // extra streams for the resident bins
+    cudaEvent_t ev_join_res[2] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_t[8] = {};
     cudaEvent_t ev_call[2] = {};

@@ -253,6 +253,19 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
     std::vector<Slice> slices;
     s.nnz_resident = s.nnz_heavy = 0;
     hsp.push_back(0);
+    // slice length: at most SLICE_LEN, but short enough that one streaming launch is >= ~8 waves of CTAs on this GPU
+    // (a multi-GPU shard or a thin heavy tail would otherwise run 2-3 ragged waves per launch)
+    uint64_t nnz_heavy_total = 0;
+    for (uint32_t r = row0; r < row1; ++r) {
+        const int64_t c = ptr[r + 1] - ptr[r];
+        if (c > RESIDENT_MAX) nnz_heavy_total += (uint64_t)c;
+    }
+    int64_t slice_len = SLICE_LEN;
+    {
+        const int64_t want = (int64_t)(nnz_heavy_total / ((uint64_t)m.sm_count * 80u));
+        slice_len = std::min<int64_t>(SLICE_LEN, std::max<int64_t>(1024, (want + 255) / 256 * 256));
+        if (const char* ev = getenv("SBMF_SLICE_LEN")) slice_len = atol(ev);   // tuning knob
+    }
     for (uint32_t r = row0; r < row1; ++r) {
         const int64_t c = ptr[r + 1] - ptr[r];
         if (c <= RESIDENT_MAX) {
@@ -264,7 +277,6 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
             const uint32_t h = (uint32_t)heavy.size();
             heavy.push_back(r);
             // equal-length slices (the last one is not a short tail)
-            static const int64_t slice_len = getenv("SBMF_SLICE_LEN") ? atol(getenv("SBMF_SLICE_LEN")) : SLICE_LEN;
             const int64_t ns = (c + slice_len - 1) / slice_len;
             const int64_t len = (c + ns - 1) / ns;
             for (int64_t o = 0; o < c; o += len) slices.push_back(Slice{ptr[r] + o, (uint32_t)std::min<int64_t>(len, c - o), h});
