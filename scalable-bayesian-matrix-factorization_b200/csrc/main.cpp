@@ -7,7 +7,9 @@
 //     "rmse is <v>" per sweep ([T]:635).
 //   * libFM's flag syntax and names (src/util/cmdline.h:29-120, src/libfm/libfm.cpp:86-110): -name value | --name value,
 //     ',' or ';' list delimiter, duplicate or unknown flag => "ERROR: ..." like libFM's main (libfm.cpp:636-640).
-//       -train F -test F     rating files: `user SEP item SEP rating` triples ([T]:35-73) or libFM text `y u:1 i:1` (auto-detected)
+//       -train F -test F     rating files: `user SEP item SEP rating` triples ([T]:35-73), libFM text `y u:1 i:1` (auto-detected), or
+//                            libFM binary F.x + F.y as written by the reference's tools/convert (fmatrix.h:34-52, convert.cpp:147-187;
+//                            chosen like Data::load does, Data.h:113-117: when F.x and F.y exist)
 //       -dim 'k0,k1,K'       K = latent dimension (third field, libFM's k2); k0/k1 are accepted and must be 1 (biases are part of SBMF)
 //       -iter T              sweeps (default 100)        -init_stdev s   (default 0.1, [T]:242)
 //       -out F               posterior-mean clamped test predictions, one per line (libfm.cpp:629-634, DVector::save)
@@ -15,7 +17,8 @@
 //       -seed n              Philox key (libFM parses -seed and ignores it, libfm.cpp:124; [T] never seeds)
 //       -method mcmc|sbmf    accepted for libFM command lines; -task r; -verbosity n; -help
 //     extensions: -do_sampling 0 (conditional-mean updates; libFM's do_sample=false), -stdev_mode ref|sqrt,
-//       -burn_in n, -rebuild_every n, -device n, -item_offset n|auto (libFM text: item feature id - offset = item id)
+//       -burn_in n, -rebuild_every n, -device n, -item_offset n|auto (libFM text/binary: item feature id - offset = item id),
+//       -dump_triples F (write the parsed train triples), -dry_run 1 (parse, print the header lines, stop before touching a GPU)
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -111,8 +114,60 @@ struct Ratings {
 // [T]:35-73: sscanf("%u%c%u%c%lf"), a line counts iff all 5 conversions succeed.  libFM text lines ("y u:1 i:1") fail the
 // third conversion's separator test (':' then a digit is read as the item id of a triple only if there is no ':' form),
 // so the format is detected on the first non-empty line by looking for ':'.
+bool file_exists(const std::string& p)
+{
+    std::ifstream f(p.c_str(), std::ios::binary);
+    return f.is_open();
+}
+
+// libFM binary design matrix: file_header{u32 id = 2; u32 float_size = 4; u64 num_values; u32 num_rows; u32 num_cols} then per row
+// u32 size + size x {u32 id; f32 value} (fmatrix.h:34-52, convert.cpp:147-153, 186-187); targets: {u32 1; u32 4; u32 num_rows} + f32s
+// (convert.cpp:159-163, 177).  A matrix-factorisation row has exactly two entries: the user feature and the item feature.
+void read_binary(const std::string& path, Ratings& out)
+{
+    std::ifstream fx((path + ".x").c_str(), std::ios::binary), fy((path + ".y").c_str(), std::ios::binary);
+    if (!fx.is_open() || !fy.is_open()) throw "unable to open " + path + ".x / .y";
+    struct { uint32_t id, float_size; uint64_t num_values; uint32_t num_rows, num_cols; } fh;
+    static_assert(sizeof(fh) == 24, "file_header layout");
+    fx.read(reinterpret_cast<char*>(&fh), sizeof(fh));
+    if (!fx || fh.id != 2) throw "" + path + ".x: not a libFM binary matrix (file id != 2)";
+    if (fh.float_size != 4) throw "" + path + ".x: float size " + std::to_string(fh.float_size) + " is not supported";
+    uint32_t yh[3];
+    fy.read(reinterpret_cast<char*>(yh), sizeof(yh));
+    if (!fy || yh[0] != 1 || yh[1] != 4) throw "" + path + ".y: not a libFM binary target vector";
+    if (yh[2] != fh.num_rows) throw "" + path + ": .x and .y disagree on the number of rows";
+    if (fh.num_values != 2ull * fh.num_rows) throw "" + path + ".x: every row must hold exactly user:1 item:1";
+    out.user.resize(fh.num_rows);
+    out.item.resize(fh.num_rows);
+    out.rating.resize(fh.num_rows);
+    fy.read(reinterpret_cast<char*>(out.rating.data()), (std::streamsize)fh.num_rows * 4);
+    if (!fy) throw "" + path + ".y: truncated";
+    for (uint32_t r = 0; r < fh.num_rows; ++r) {
+        struct { uint32_t size; uint32_t id0; float v0; uint32_t id1; float v1; } row;
+        static_assert(sizeof(row) == 20, "row layout");
+        fx.read(reinterpret_cast<char*>(&row), sizeof(row));
+        if (!fx || row.size != 2) throw "" + path + ".x: row " + std::to_string(r) + " does not have exactly two entries";
+        out.user[r] = row.id0;
+        out.item[r] = row.id1;
+    }
+}
+
 void read_ratings(const std::string& path, Ratings& out, long item_offset, bool& was_libfm)
 {
+    if (file_exists(path + ".x") && file_exists(path + ".y")) {   // Data.h:113-117
+        read_binary(path, out);
+        was_libfm = true;
+        if (item_offset > 0)
+            for (auto& m : out.item) {
+                if ((long)m < item_offset) throw std::string("libFM binary: item feature id below -item_offset in ") + path;
+                m -= (uint32_t)item_offset;
+            }
+        for (size_t n = 0; n < out.user.size(); ++n) {
+            if (out.user[n] > out.user_max) out.user_max = out.user[n];
+            if (out.item[n] > out.item_max) out.item_max = out.item[n];
+        }
+        return;
+    }
     std::ifstream f(path.c_str());
     if (!f.is_open()) throw "unable to open " + path;
     std::string line;
@@ -189,7 +244,9 @@ int main(int argc, char** argv)
         const std::string p_burn = cmd.reg("burn_in", "sweeps before predictions are averaged; default=0");
         const std::string p_reb = cmd.reg("rebuild_every", "rebuild the residual every n sweeps; default=1");
         const std::string p_dev = cmd.reg("device", "CUDA device ordinal; default=0");
-        const std::string p_off = cmd.reg("item_offset", "libFM text input: item id = item feature id - offset; default=auto");
+        const std::string p_off = cmd.reg("item_offset", "libFM text/binary input: item id = item feature id - offset; default=auto");
+        const std::string p_dump = cmd.reg("dump_triples", "write the parsed training triples (user item rating) to this file");
+        const std::string p_dry = cmd.reg("dry_run", "1 = parse the inputs, print the header lines and stop (no GPU needed)");
         if (cmd.has(p_help)) {
             cmd.print_help();
             return 0;
@@ -232,6 +289,13 @@ int main(int argc, char** argv)
         std::cout << "number rows =" << tr.user.size() << "\n";                             // [T]:225-227
         std::cout << "number of user =" << num_users << "\n";
         std::cout << "number of items =" << num_items << "\n";
+
+        if (cmd.has(p_dump)) {
+            std::ofstream o(cmd.get(p_dump, "").c_str());
+            if (!o.is_open()) throw "unable to open " + cmd.get(p_dump, "");
+            for (size_t n = 0; n < tr.user.size(); ++n) o << tr.user[n] << "\t" << tr.item[n] << "\t" << tr.rating[n] << "\n";
+        }
+        if (cmd.geti(p_dry, 0) != 0) return 0;
 
         sbmf_config cfg;
         sbmf_cuda_config_default(&cfg);

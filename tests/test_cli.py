@@ -106,3 +106,29 @@ def test_cli_no_arguments_uses_reference_paths(cli, tmp_path, tiny):
     lines = r.stdout.splitlines()
     assert lines[1] == "number of user =50" and lines[2] == "number of items =40"
     assert sum(ln.startswith("rmse is ") for ln in lines) == 100
+
+
+def test_three_input_formats_parse_to_the_same_triples(cli, tmp_path):
+    """triples, libFM text and libFM binary (bytes written by the reference's own convert tool) -> identical (user, item, rating)."""
+    G = os.path.join(ROOT, "tests", "golden")
+    want = open(os.path.join(G, "tiny_unsorted.train")).read().split()
+    want = [(int(want[i]), int(want[i + 1]), float(want[i + 2])) for i in range(0, len(want), 3)]
+    outs = {}
+    for name, tr, te in (("triples", "tiny_unsorted.train", "tiny_unsorted.test"), ("text", "tiny_libfm.train", "tiny_libfm.test"),
+                         ("binary", "tiny_libfm.train_bin", "tiny_libfm.test_bin")):
+        dump = str(tmp_path / f"dump_{name}")
+        r = run(cli, "-train", os.path.join(G, tr), "-test", os.path.join(G, te), "-dry_run", "1", "-dump_triples", dump)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.splitlines()[:3] == ["number rows =560", "number of user =50", "number of items =40"], r.stdout
+        got = open(dump).read().split()
+        outs[name] = [(int(got[i]), int(got[i + 1]), float(got[i + 2])) for i in range(0, len(got), 3)]
+    assert outs["triples"] == want and outs["text"] == want and outs["binary"] == want
+
+
+def test_binary_header_checks(cli, tmp_path):
+    import struct
+    p = str(tmp_path / "bad")
+    open(p + ".x", "wb").write(struct.pack("<IIQII", 3, 4, 2, 1, 2))
+    open(p + ".y", "wb").write(struct.pack("<III", 1, 4, 1))
+    r = run(cli, "-train", p, "-test", p, "-dry_run", "1")
+    assert r.returncode == 1 and "file id != 2" in r.stderr

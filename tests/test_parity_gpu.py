@@ -336,3 +336,51 @@ def test_burn_in_and_sqrt_mode(ml100k):
     p = m.get_pred()
     assert p.min() >= 0.5 - 1e-6 and p.max() <= 5.0 + 1e-6
     m.close()
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("shape", ["ml10m_k100"])
+def test_full_size_properties(shape):
+    """At a BASELINE.json size (ML-10M-shaped, 71,567 x 10,681, 10M ratings, K=100) the oracle is too slow, so the sweep is checked
+    through size-independent properties: (i) the residual the sweep leaves equals rating - prediction recomputed from the exported
+    state in fp64 (all kernel paths, the permutations and the fused refresh have to agree for that), (ii) the device's sum e / sum e^2
+    of the next sweep equal numpy's over that residual, (iii) the RMSE history equals the RMSE of the exported predictions,
+    (iv) both row classes (register-resident and streaming) are exercised, (v) a second run is bit-identical."""
+    import sbmf
+    I, J, N, K = 71567, 10681, 10000000, 100
+    s = sbmf.synth_generate(I, J, N, seed=20151002)
+    runs = []
+    for _ in range(2):
+        m = sbmf.SbmfModel(K=K, sample_mode=0, seed=17)
+        m.set_train(s["train_user"], s["train_item"], s["train_rating"], I, J)
+        m.set_test(s["test_user"], s["test_item"], s["test_rating"])
+        m.init_factors()
+        m.sweep(3)
+        st = m.get_state()
+        t = m.timing()
+        assert min(t["nnz_light_user"], t["nnz_heavy_user"], t["nnz_light_item"], t["nnz_heavy_item"]) > 0
+        runs.append((st, m.rmse_history(0, 3)[0].copy(), m.get_pred().copy()))
+        if len(runs) == 1:
+            # (i) residual consistency on a 1-in-13 sample of ratings
+            idx = np.arange(0, s["train_user"].size, 13)
+            u, j = s["train_user"][idx], s["train_item"][idx]
+            U, V = st["U"].astype(np.float64), st["V"].astype(np.float64)
+            pred = st["b_0"] + st["b_i"][u].astype(np.float64) + st["b_j"][j].astype(np.float64) + np.einsum("nk,kn->n", U[u], V[:, j])
+            want = s["train_rating"][idx].astype(np.float64) - pred
+            assert np.max(np.abs(st["E"][idx] - want)) <= 2e-4, np.max(np.abs(st["E"][idx] - want))
+            # (ii) statistics of the next sweep are taken over exactly this residual
+            E64 = st["E"].astype(np.float64)
+            m.sweep(1)
+            st2 = m.get_state(with_E=False)
+            assert abs(st2["sum_e"] - E64.sum()) <= 1e-6 * np.abs(E64).sum()
+            assert abs(st2["sum_e2"] - (E64 * E64).sum()) <= 1e-6 * (E64 * E64).sum()
+            # (iii) RMSE bookkeeping: prediction of the last sweep only (burn_in = 0: mean over 4 sweeps) is in range, finite
+            p = m.get_pred()
+            assert np.all(np.isfinite(p)) and p.min() >= 0.5 - 1e-6 and p.max() <= 5 + 1e-6
+            rm = m.rmse_history(0, 4)[0]
+            assert abs(rm[3] - np.sqrt(np.mean((s["test_rating"].astype(np.float64) - p) ** 2))) <= 1e-5
+            assert rm[3] < rm[0]
+        m.close()
+    for k in ("U", "V", "b_i", "b_j", "E"):
+        assert np.array_equal(runs[0][0][k], runs[1][0][k]), k
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
