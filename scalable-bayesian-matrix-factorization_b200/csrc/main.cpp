@@ -272,17 +272,22 @@ int main(int argc, char** argv)
         const std::string offs = cmd.get(p_off, "auto");
         if (offs != "auto") off = atol(offs.c_str());
         read_ratings(train_file, tr, off, libfm_tr);
-        if (libfm_tr && offs == "auto") {
-            // libFM MF files number items after the users (scripts/triple_format_to_libfm.pl): offset = 1 + max user id
+        read_ratings(test_file, te, off, libfm_te);
+        if ((libfm_tr || libfm_te) && offs == "auto") {
+            // libFM MF files number items after the users (scripts/triple_format_to_libfm.pl): offset = 1 + max user id over
+            // train U test, applied when every item feature id lies beyond it
+            const uint32_t umax = tr.user_max > te.user_max ? tr.user_max : te.user_max;
             uint32_t min_item = UINT32_MAX;
             for (uint32_t m : tr.item) min_item = m < min_item ? m : min_item;
-            off = (min_item > tr.user_max) ? (long)tr.user_max + 1 : 0;
+            for (uint32_t m : te.item) min_item = m < min_item ? m : min_item;
+            off = (min_item != UINT32_MAX && min_item > umax) ? (long)umax + 1 : 0;
             if (off) {
                 for (auto& m : tr.item) m -= (uint32_t)off;
-                tr.item_max -= (uint32_t)off;
+                for (auto& m : te.item) m -= (uint32_t)off;
+                if (!tr.item.empty()) tr.item_max -= (uint32_t)off;
+                if (!te.item.empty()) te.item_max -= (uint32_t)off;
             }
         }
-        read_ratings(test_file, te, libfm_tr ? off : 0, libfm_te);
         const uint32_t user_max = tr.user_max > te.user_max ? tr.user_max : te.user_max;   // [T]:45-52, 112-119
         const uint32_t item_max = tr.item_max > te.item_max ? tr.item_max : te.item_max;
         const uint32_t num_users = user_max + 1, num_items = item_max + 1;                  // [T]:151-153
