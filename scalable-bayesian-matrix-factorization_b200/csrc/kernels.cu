@@ -172,8 +172,8 @@ __device__ __forceinline__ SolveOut solve_lanes(const float* sm, const PhaseArgs
 }
 
 // register caps (min CTAs per SM): 8 ratings per lane -> 128 registers, 4 -> 102, fewer -> 80
-template <int RPL, int WARPS, bool PF, bool REFRESH>
-__global__ void __launch_bounds__(WARPS == 1 ? 128 : WARPS * 32, (RPL == 8 ? 512 : RPL == 4 ? 640 : 768) / (WARPS == 1 ? 128 : WARPS * 32))
+template <int RPL, int WARPS, bool REFRESH>
+__global__ void __launch_bounds__(WARPS == 1 ? 128 : WARPS * 32, (RPL >= 7 ? 512 : RPL >= 4 ? 640 : 768) / (WARPS == 1 ? 128 : WARPS * 32))
 row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows, int b_begin, int b_end, int do_bias)
 {
     constexpr int WPC = (WARPS == 1) ? 4 : WARPS;   // warps per CTA
@@ -282,17 +282,6 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
 #pragma unroll
         for (int r = 0; r < RPL; ++r) accumulate(acc, f[r], e[r]);
-        // PF: keep this block's factors for the residual update; the next block's gathers fly during reduce + solve
-        f8 fcur[PF ? RPL : 1];
-        if (PF) {
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) fcur[r] = f[r];
-            if (b + 1 < b_end) {
-                const float* Fo = Fother + (size_t)(b + 1) * ns_other * 8;
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
-            }
-        }
         warp_reduce_scatter48(acc, lane);
         if (WARPS == 1) {
             if ((lane & 1) == 0) {
@@ -340,16 +329,16 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         }
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
-            const float fd = dot8(PF ? fcur[r] : f[r], so.d);
+            const float fd = dot8(f[r], so.d);
             e[r] += fd;
             if (REFRESH) {   // <f, u_new> = <f, u_old> - <f, d>; u_old broadcast from the 8 lanes that hold it
                 float fu = 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) fu = fmaf((PF ? fcur[r] : f[r]).v[k], uo8[k], fu);
+                for (int k = 0; k < 8; ++k) fu = fmaf(f[r].v[k], uo8[k], fu);
                 pr[r] += fu - fd;
             }
         }
-        if (!PF && b + 1 < b_end) {
+        if (b + 1 < b_end) {   // next block's gathers (a register double buffer for them costs more occupancy than it hides latency)
             const float* Fo = Fother + (size_t)(b + 1) * ns_other * 8;
 #pragma unroll
             for (int r = 0; r < RPL; ++r) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
@@ -961,8 +950,8 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
     const uint32_t n = self.bin_count[BIN];
     if (!n) return;
     const dim3 grid(WARPS == 1 ? (n + 3) / 4 : n), block(WARPS == 1 ? 128 : WARPS * 32);
-    if (refresh) row_resident_kernel<RPL, WARPS, false, true><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-    else row_resident_kernel<RPL, WARPS, false, false><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+    if (refresh) row_resident_kernel<RPL, WARPS, true><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+    else row_resident_kernel<RPL, WARPS, false><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
     m.launches++;
 }
 
@@ -1021,13 +1010,18 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     for (int b0 = 0; b0 < KB; b0 += nb) {
         const int b1 = (b0 + nb < KB) ? b0 + nb : KB;
         const int do_bias = (b0 == 0) ? 1 : 0;
-        launch_bin<6>(m, a, self, b0, b1, do_bias, refresh, sb[0]);   // longest rows first
-        launch_bin<5>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
-        launch_bin<4>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
-        launch_bin<3>(m, a, self, b0, b1, do_bias, refresh, sb[0]);
-        launch_bin<2>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
-        launch_bin<1>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
-        launch_bin<0>(m, a, self, b0, b1, do_bias, refresh, sb[0]);
+        launch_bin<11>(m, a, self, b0, b1, do_bias, refresh, sb[0]);   // longest rows first
+        launch_bin<10>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
+        launch_bin<9>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
+        launch_bin<8>(m, a, self, b0, b1, do_bias, refresh, sb[0]);
+        launch_bin<7>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
+        launch_bin<6>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
+        launch_bin<5>(m, a, self, b0, b1, do_bias, refresh, sb[0]);
+        launch_bin<4>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
+        launch_bin<3>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
+        launch_bin<2>(m, a, self, b0, b1, do_bias, refresh, sb[0]);
+        launch_bin<1>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
+        launch_bin<0>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
     }
     cudaEventRecord(m.ev_join_res[0], sb[1]);
     cudaEventRecord(m.ev_join_res[1], sb[2]);

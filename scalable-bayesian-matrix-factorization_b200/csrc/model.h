@@ -21,7 +21,7 @@ namespace sbmf {
 
 constexpr int KBLK = 8;             // latent dimensions per factor block (one 32-byte sector per row)
 constexpr int NACC = 48;            // g[8] + upper-triangular G[36] = 44 accumulators, padded to 48
-constexpr int NBINS = 7;            // resident-row bins, see kBin* below
+constexpr int NBINS = 12;            // resident-row bins, see kBin* below
 constexpr int RESIDENT_MAX = 2048;  // longer rows go through the streaming ("heavy") pipeline
 constexpr int SLICE_LEN = 4096;     // ratings per heavy-row slice (one CTA)
 constexpr int SLICE_THREADS = 256;
@@ -29,7 +29,8 @@ constexpr int MAX_PEERS = 8;         // replicas a phase kernel can write direct
 
 // resident bins: a row of c ratings is handled by WARPS warps holding RPL ratings per lane in registers
 struct BinShape { int rpl, warps, cap; };
-constexpr BinShape kBins[NBINS] = {{1, 1, 32}, {2, 1, 64}, {4, 1, 128}, {8, 1, 256}, {4, 4, 512}, {8, 4, 1024}, {8, 8, 2048}};
+constexpr BinShape kBins[NBINS] = {{1, 1, 32},  {2, 1, 64},  {3, 1, 96},  {4, 1, 128},  {6, 1, 192},  {8, 1, 256},
+                                   {3, 4, 384}, {4, 4, 512}, {6, 4, 768}, {8, 4, 1024}, {6, 8, 1536}, {8, 8, 2048}};
 
 // Device-resident scalars of the sweep ([T]:315-318 plus the statistics of [T]:342-359).
 struct Scalars {
