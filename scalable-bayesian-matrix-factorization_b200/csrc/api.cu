@@ -214,6 +214,7 @@ int sbmf_cuda_destroy(sbmf_handle* h)
     for (int i = 0; i < 2; ++i)
         if (m.ev_c[i]) cudaEventDestroy(m.ev_c[i]);
     for (cudaEvent_t ev : m.ev_top) cudaEventDestroy(ev);
+    if (m.graph_exec) cudaGraphExecDestroy(m.graph_exec);
     if (m.ev_fork) cudaEventDestroy(m.ev_fork);
     if (m.ev_join) cudaEventDestroy(m.ev_join);
     if (m.s_main) cudaStreamDestroy(m.s_main);
@@ -350,11 +351,10 @@ int sbmf_cuda_init_factors(sbmf_handle* h, const float* U0, const float* V0)
     return SBMF_OK;
 }
 
-// One body of the loop [T]:335-637.
-static int one_sweep(Model& m)
+// One body of the loop [T]:335-637: enqueue only (no host synchronisation), so it can also be captured into a CUDA graph.
+static int enqueue_sweep(Model& m, bool timing)
 {
     cudaStream_t st = m.s_main;
-    const bool timing = m.timing_enabled;
     // Residual hygiene ([T]:342-359 rebuilds E from scratch every sweep).  residual_mode 0 (default): the same rebuild, but
     // fused into the user phase (its kernels already gather every factor the prediction needs), so the statistics of this
     // sweep come from the incrementally updated residual of the previous one; residual_mode 1: the stand-alone rebuild kernel
@@ -403,6 +403,82 @@ static int one_sweep(Model& m)
     launch_eval_final(m, st);
     if (timing) cudaEventRecord(m.ev_t[6], st);
     if (crc) return SBMF_ERR_NCCL;
+    return SBMF_OK;
+}
+
+struct SweepKey {   // everything host-side that shapes the launch sequence of a sweep
+    bool standalone, fused, next_standalone, e_in_csc;
+    bool operator==(const SweepKey& o) const
+    {
+        return standalone == o.standalone && fused == o.fused && next_standalone == o.next_standalone && e_in_csc == o.e_in_csc;
+    }
+};
+
+static SweepKey sweep_key(const Model& m)
+{
+    const bool due = (m.sweeps_done % m.cfg.rebuild_every) == 0;
+    const bool standalone = due && (m.sweeps_done == 0 || m.cfg.residual_mode == 1);
+    const bool next_standalone = ((m.sweeps_done + 1) % m.cfg.rebuild_every) == 0 && m.cfg.residual_mode == 1;
+    return SweepKey{standalone, due && !standalone, next_standalone, m.e_in_csc};
+}
+
+// With per-phase timing off, a steady-state sweep (~100-250 dependent launches on five streams, plus the NCCL calls) is captured
+// once into a CUDA graph and replayed: the launch sequence only depends on SweepKey, every per-sweep value (alpha, b_0, sweep
+// counter, ...) lives in device memory.  Matters where a sweep is short: small matrices, or 1/8 of a big one per GPU.
+static int graph_sweep(Model& m, bool& done)
+{
+    done = false;
+    static const bool disabled = getenv("SBMF_NO_GRAPH") != nullptr;
+    if (disabled || m.timing_enabled || m.sweeps_done < 2) return SBMF_OK;
+    const SweepKey key = sweep_key(m);
+    if (m.graph_exec && !(key == SweepKey{m.gk[0], m.gk[1], m.gk[2], m.gk[3]})) {
+        cudaGraphExecDestroy(m.graph_exec);
+        m.graph_exec = nullptr;
+    }
+    if (!m.graph_exec) {
+        if (m.graph_failed) return SBMF_OK;
+        const uint64_t l0 = m.launches;
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(m.s_main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            m.graph_failed = true;
+            return SBMF_OK;
+        }
+        const int rc = enqueue_sweep(m, false);
+        const cudaError_t ce = cudaStreamEndCapture(m.s_main, &g);
+        const bool periodic = m.e_in_csc == key.e_in_csc;
+        if (rc != SBMF_OK || ce != cudaSuccess || !g || !periodic || cudaGraphInstantiate(&m.graph_exec, g, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            m.graph_exec = nullptr;
+            m.graph_failed = true;
+            m.launches = l0;
+            m.e_in_csc = key.e_in_csc;
+            return rc != SBMF_OK ? rc : SBMF_OK;   // nothing was executed: the caller falls back to direct launches
+        }
+        cudaGraphDestroy(g);
+        m.graph_launches = m.launches - l0;
+        m.launches = l0;
+        m.gk[0] = key.standalone; m.gk[1] = key.fused; m.gk[2] = key.next_standalone; m.gk[3] = key.e_in_csc;
+    }
+    if (cudaGraphLaunch(m.graph_exec, m.s_main) != cudaSuccess) {
+        m.err = std::string("sweep: cudaGraphLaunch: ") + cudaGetErrorString(cudaGetLastError());
+        return SBMF_ERR_CUDA;
+    }
+    m.launches += m.graph_launches;
+    m.sweeps_done++;
+    done = true;
+    return SBMF_OK;
+}
+
+static int one_sweep(Model& m)
+{
+    bool done = false;
+    int grc = graph_sweep(m, done);
+    if (grc != SBMF_OK || done) return grc;
+    const bool timing = m.timing_enabled;
+    grc = enqueue_sweep(m, timing);
+    if (grc != SBMF_OK) return grc;
     m.sweeps_done++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -137,6 +137,10 @@ struct Model {
     cudaEvent_t ev_c[2] = {};          // start of the post-phase all-gathers (multi-GPU)
     std::vector<cudaEvent_t> ev_top;   // 2 per launch of the dominant kernel in one phase
     uint32_t ev_top_used = 0;
+    cudaGraphExec_t graph_exec = nullptr;   // captured steady-state sweep (api.cu: graph_sweep)
+    bool gk[4] = {};                        // its SweepKey
+    bool graph_failed = false;
+    uint64_t graph_launches = 0;
     bool timing_enabled = true;
     bool timing_detail = false;
     sbmf_timing timing{};

@@ -205,6 +205,11 @@ void close_peer_access(Model& m)
 
 void free_storage(Model& m)
 {
+    if (m.graph_exec) {   // the captured sweep points at the arrays freed below
+        cudaGraphExecDestroy(m.graph_exec);
+        m.graph_exec = nullptr;
+    }
+    m.graph_failed = false;
     if (m.world > 1 && m.comm.nccl && m.have_train) {
         // peers may still be writing into / reading from our buffers: meet them before anything is unmapped or freed
         cudaStreamSynchronize(m.s_main);
@@ -237,6 +242,10 @@ void free_storage(Model& m)
 
 void free_test(Model& m)
 {
+    if (m.graph_exec) {
+        cudaGraphExecDestroy(m.graph_exec);
+        m.graph_exec = nullptr;
+    }
     cudaFree(m.t_user); cudaFree(m.t_item); cudaFree(m.t_r); cudaFree(m.t_sum);
     m.t_user = m.t_item = nullptr; m.t_r = nullptr; m.t_sum = nullptr;
     m.have_test = false;

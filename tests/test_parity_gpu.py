@@ -384,3 +384,27 @@ def test_full_size_properties(shape):
     for k in ("U", "V", "b_i", "b_j", "E"):
         assert np.array_equal(runs[0][0][k], runs[1][0][k]), k
     assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+
+
+@pytest.mark.parametrize("case", ["ml100k", "skewed"])
+def test_graph_replay_equals_direct_launches(case, ml100k):
+    """With per-phase timing off the steady-state sweep is replayed from a CUDA graph (api.cu: graph_sweep); same bits as direct launches."""
+    import sbmf
+    d = ml100k if case == "ml100k" else skewed_case()
+    outs = []
+    for timing in (1, 0):
+        m = sbmf.SbmfModel(K=20, sample_mode=0, seed=5)
+        m.set_train(d["train_user"], d["train_item"], d["train_rating"], d["num_users"], d["num_items"])
+        m.set_test(d["test_user"], d["test_item"], d["test_rating"])
+        m.init_factors()
+        m.set_timing_enabled(timing)
+        m.sweep(3)
+        m.sweep(4)
+        m.init_factors()      # restart: the captured graph is reused
+        m.sweep(7)
+        outs.append((m.get_state(), m.rmse_history(0, 7)[0].copy(), m.timing()["kernel_launches"]))
+        m.close()
+    for k in ("U", "V", "b_i", "b_j", "E"):
+        assert np.array_equal(outs[0][0][k], outs[1][0][k]), k
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2]          # the launch count is kept honest under replay
