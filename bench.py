@@ -363,7 +363,7 @@ def main():
         breakdown = {"set_train_s": round(te1 - te0, 4), "set_test_init_s": round(te2 - te1, 4), "sweeps_s": round(te3 - te2, 4),
                      "get_pred_s": round(te4 - te3, 4)}
         h2d = 12.0 * (n_train + n_test)
-        d2h = 16.0 * a.steps + 8.0 * n_test
+        d2h = 16.0 * a.steps + 4.0 * n_test
         e2e = {"value": fu_per_sweep * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
                "seconds_total": e2e_s, "sweeps": a.steps, "final_rmse": last[0], "breakdown_rank0": breakdown,
                "what": "set_train(H2D COO + device CSR/CSC build) + set_test + init_factors + steps x (sweep + eval D2H) + get_pred D2H, wall clock"}

@@ -632,7 +632,6 @@ int sbmf_cuda_get_pred(sbmf_handle* h, float* pred)
         return SBMF_ERR_STATE;
     }
     API_CK(cudaSetDevice(m.device));
-    std::vector<double> tmp(m.Nt ? m.Nt : 1);
     if (m.world > 1) {   // every rank accumulated its own slice of the test set
         std::vector<size_t> off(m.world), cnt(m.world);
         for (int q = 0; q < m.world; ++q) {
@@ -641,10 +640,13 @@ int sbmf_cuda_get_pred(sbmf_handle* h, float* pred)
         }
         if (comm_allgatherv_f64(m.comm, m.t_sum, off.data(), cnt.data(), m.s_main, m.err) != 0) return SBMF_ERR_NCCL;
     }
-    API_CK(cudaMemcpyAsync(tmp.data(), m.t_sum, m.Nt * 8, cudaMemcpyDeviceToHost, m.s_main));
-    API_CK(cudaStreamSynchronize(m.s_main));
     const double denom = (double)(m.sweeps_done - m.cfg.burn_in);
-    for (uint64_t t = 0; t < m.Nt; ++t) pred[t] = (float)(tmp[t] / denom);
+    float* d_out = nullptr;
+    API_CK(cudaMallocAsync((void**)&d_out, (m.Nt ? m.Nt : 1) * 4, m.s_main));
+    launch_pred_mean(m, d_out, denom, m.s_main);
+    API_CK(cudaMemcpyAsync(pred, d_out, m.Nt * 4, cudaMemcpyDeviceToHost, m.s_main));
+    API_CK(cudaFreeAsync(d_out, m.s_main));
+    API_CK(cudaStreamSynchronize(m.s_main));
     return SBMF_OK;
 }
 

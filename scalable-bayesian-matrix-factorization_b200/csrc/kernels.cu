@@ -1223,6 +1223,18 @@ void launch_eval(Model& m, cudaStream_t st)
     m.launches++;
 }
 
+__global__ void __launch_bounds__(256)
+pred_mean_kernel(const double* __restrict__ tsum, float* __restrict__ out, uint64_t n, double denom)
+{
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (uint64_t)gridDim.x * 256) out[t] = (float)(tsum[t] / denom);
+}
+
+void launch_pred_mean(Model& m, float* d_out, double denom, cudaStream_t st)
+{
+    pred_mean_kernel<<<grid_for(m.Nt, 256, m.sm_count * 8), 256, 0, st>>>(m.t_sum, d_out, m.Nt, denom);
+    m.launches++;
+}
+
 void launch_eval_final(Model& m, cudaStream_t st)
 {
     eval_final_kernel<<<1, 32, 0, st>>>(m.sc, m.red2, m.Nt, m.rmse_hist, m.hist_cap);

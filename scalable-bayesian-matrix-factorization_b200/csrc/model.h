@@ -175,7 +175,8 @@ int launch_barrier(Model& m, cudaStream_t st);                    // cross-GPU b
 int launch_reduce_pair(Model& m, cudaStream_t st);                // red_part -> red2 (+ all-reduce over ranks)
 int launch_allgather_side(Model& m, Side& s, cudaStream_t st);    // replicate the rows each rank just updated (factors + bias)
 void launch_eval(Model& m, cudaStream_t st);             // [T]:610-636: prediction + partial squared errors of this rank's slice
-void launch_eval_final(Model& m, cudaStream_t st);       // RMSE from the reduced sums, history, sweep counter
+void launch_eval_final(Model& m, cudaStream_t st);
+void launch_pred_mean(Model& m, float* d_out, double denom, cudaStream_t st);   // posterior-mean prediction = running sum / collected sweeps       // RMSE from the reduced sums, history, sweep counter
 
 }  // namespace sbmf
 
