@@ -15,7 +15,9 @@
 //       -out F               posterior-mean clamped test predictions, one per line (libfm.cpp:629-634, DVector::save)
 //       -rlog F              tab-separated per-sweep log (src/util/rlog.h)
 //       -seed n              Philox key (libFM parses -seed and ignores it, libfm.cpp:124; [T] never seeds)
-//       -method mcmc|sbmf    accepted for libFM command lines; -task r; -verbosity n; -help
+//       -method sbmf|mcmc    sbmf (default): [T]'s stdout.  mcmc: libFM's MCMC front-end outputs instead (fm_learn_mcmc_simultaneous.h:
+//                            57-62, 143-147, 244-245): "#Iter=%3d\tTrain=..\tTest=.." per sweep and the file test_rmse_<k0><k1><K>_mcmc
+//                            in the CWD with one running-mean test RMSE per line; -task r; -verbosity n; -help
 //     extensions: -do_sampling 0 (conditional-mean updates; libFM's do_sample=false), -stdev_mode ref|sqrt,
 //       -burn_in n, -rebuild_every n, -device n, -item_offset n|auto (libFM text/binary: item feature id - offset = item id),
 //       -dump_triples F (write the parsed train triples), -dry_run 1 (parse, print the header lines, stop before touching a GPU)
@@ -325,7 +327,14 @@ int main(int argc, char** argv)
         if (cmd.has(p_rlog) && !cmd.get(p_rlog, "").empty()) {
             rlog.open(cmd.get(p_rlog, "").c_str());
             if (!rlog.is_open()) throw "unable to open " + cmd.get(p_rlog, "");
-            rlog << "rmse\trmse_sweep\talpha\tb_0\ttime_learn\n";
+            // libFM's field names where the quantity exists here (fm_learn_mcmc_simultaneous.h:231-251), then this sampler's own
+            rlog << "rmse\trmse_mcmc_this\trmse_mcmc_all\ttime_learn\talpha\tb_0\n";
+        }
+        const bool libfm_out = (method != "sbmf");
+        std::ofstream file_rmse;
+        if (libfm_out) {
+            file_rmse.open(("test_rmse_11" + std::to_string(K) + "_mcmc").c_str());   // k0 = k1 = 1
+            if (!file_rmse.is_open()) throw std::string("unable to open test_rmse_*_mcmc in the current directory");
         }
         const int verbosity = (int)cmd.geti(p_verb, 0);
         for (uint32_t iter = 0; iter < T; ++iter) {
@@ -334,14 +343,22 @@ int main(int argc, char** argv)
             ck(sbmf_cuda_sweep(h, 1), h, "sweep");
             ck(sbmf_cuda_eval(h, &rmse, &rmse_sweep), h, "eval");
             const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            std::cout << "rmse is " << rmse << std::endl;                                   // [T]:635
-            if (rlog.is_open() || verbosity > 0) {
+            if (!libfm_out) std::cout << "rmse is " << rmse << std::endl;                  // [T]:635
+            if (libfm_out || rlog.is_open() || verbosity > 0) {
                 sbmf_state st;
                 memset(&st, 0, sizeof(st));
                 ck(sbmf_cuda_get_state(h, &st), h, "get_state");
-                if (rlog.is_open()) rlog << rmse << "\t" << rmse_sweep << "\t" << st.alpha << "\t" << st.b_0 << "\t" << dt << "\n" << std::flush;
-                if (verbosity > 0)
-                    std::cout << "#Iter=" << iter << "\tTest=" << rmse_sweep << "\talpha=" << st.alpha << "\tb_0=" << st.b_0 << "\ttime=" << dt << std::endl;
+                if (libfm_out) {
+                    // Train = RMSE of the training residual this sweep started from (sum e^2 of [T]:358)
+                    const double rmse_train = tr.user.empty() ? 0.0 : sqrt(st.sum_e2 / (double)tr.user.size());
+                    char buf[16];
+                    snprintf(buf, sizeof(buf), "%3u", iter);
+                    std::cout << "#Iter=" << buf << "\tTrain=" << rmse_train << "\tTest=" << rmse << std::endl;
+                    file_rmse << rmse << "\n" << std::flush;
+                }
+                if (rlog.is_open())
+                    rlog << rmse << "\t" << rmse_sweep << "\t" << rmse << "\t" << dt << "\t" << st.alpha << "\t" << st.b_0 << "\n" << std::flush;
+                if (verbosity > 0) std::cout << "alpha=" << st.alpha << "\tb_0=" << st.b_0 << "\ttime=" << dt << std::endl;
             }
         }
         if (cmd.has(p_out)) {

@@ -73,7 +73,7 @@ def test_cli_matches_binding(cli, tmp_path, ml100k, fmt):
         write_libfm(tr, d["train_user"], d["train_item"], d["train_rating"], d["num_users"])
         write_libfm(te, d["test_user"], d["test_item"], d["test_rating"], d["num_users"])
     out, rlog = str(tmp_path / "pred"), str(tmp_path / "rlog")
-    r = run(cli, "-task", "r", "-train", tr, "-test", te, "-dim", "1,1,20", "-iter", "6", "-seed", "42", "-out", out, "-rlog", rlog, "-method", "mcmc")
+    r = run(cli, "-task", "r", "-train", tr, "-test", te, "-dim", "1,1,20", "-iter", "6", "-seed", "42", "-out", out, "-rlog", rlog)
     assert r.returncode == 0, r.stderr
     lines = r.stdout.splitlines()
     assert lines[:3] == ["number rows =90570", "number of user =943", "number of items =1682"]
@@ -89,7 +89,14 @@ def test_cli_matches_binding(cli, tmp_path, ml100k, fmt):
     assert pred.shape == (9430,) and np.max(np.abs(pred - m.get_pred())) < 1e-5
     assert pred.min() >= 0.5 and pred.max() <= 5.0
     log = open(rlog).read().splitlines()
-    assert log[0].split("\t") == ["rmse", "rmse_sweep", "alpha", "b_0", "time_learn"] and len(log) == 7
+    assert log[0].split("\t") == ["rmse", "rmse_mcmc_this", "rmse_mcmc_all", "time_learn", "alpha", "b_0"] and len(log) == 7
+    # -method mcmc: libFM's front-end outputs (fm_learn_mcmc_simultaneous.h:57-62, 244-245) instead of [T]'s "rmse is" lines
+    r2 = run(cli, "-task", "r", "-train", tr, "-test", te, "-dim", "1,1,20", "-iter", "6", "-seed", "42", "-method", "mcmc", cwd=str(tmp_path))
+    assert r2.returncode == 0, r2.stderr
+    it = [ln for ln in r2.stdout.splitlines() if ln.startswith("#Iter=")]
+    assert len(it) == 6 and it[0].startswith("#Iter=  0\tTrain=") and [ln.split("Test=")[1] for ln in it] == want
+    assert "rmse is" not in r2.stdout
+    assert open(tmp_path / "test_rmse_1120_mcmc").read().split() == want
     m.close()
 
 
