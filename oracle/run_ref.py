@@ -17,8 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 
 
-def ref_binary(K=20, T=100, shim=False):
-    name = "gibbs_ref" + ("_shim" if shim else "")
+def ref_binary(K=20, T=100, shim=False, variant="T"):
+    name = ("gibbs_ref" if variant == "T" else "gibbs_refS") + ("_shim" if shim else "")
     if not (K == 20 and T == 100):
         name += f"_D{K}_T{T}"
     path = os.path.join(REF_DIR, name)
@@ -32,6 +32,11 @@ def run_ref(binary, train, test, threads=1, env_extra=None, timeout=None):
         os.makedirs(os.path.join(tmp, "a", "b"))
         os.symlink(os.path.abspath(train), os.path.join(tmp, "data", "ra.train_sbpmf"))
         os.symlink(os.path.abspath(test), os.path.join(tmp, "data", "ra.test_sbpmf"))
+        # [S] = src/libfm/gibbs_sbpmf2.cpp opens ../../data/m100k/train (passes 1-2), .../train_sbpmf (pass 3) and .../test ([S]:33-192)
+        os.makedirs(os.path.join(tmp, "data", "m100k"))
+        for name in ("train", "train_sbpmf"):
+            os.symlink(os.path.abspath(train), os.path.join(tmp, "data", "m100k", name))
+        os.symlink(os.path.abspath(test), os.path.join(tmp, "data", "m100k", "test"))
         env = dict(os.environ)
         env["OMP_NUM_THREADS"] = str(threads)
         if env_extra:

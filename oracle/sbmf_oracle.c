@@ -41,6 +41,10 @@ struct sbmf_oracle {
     double mu_0, mu_1, mu_2, mu_4, mu_5;
     double sigma_0, sigma_1, sigma_2, sigma_4, sigma_5;
     double clamp_lo, clamp_hi;
+    /* variant 0 = [T] (top-level gibbs_sbpmf2.cpp); 1 = [S] (src/libfm/gibbs_sbpmf2.cpp as committed: no biases, no global
+       mean, Normal-Gamma factor hyper-prior, including the slip at [S]:412); 2 = [S] with that slip corrected */
+    int variant;
+    double ng_a_0, ng_b_0, nu_0, ng_mu_0, ng_alpha_0, ng_beta_0;   /* [S]:260-269 */
 };
 
 #include "rand_samplers.h"
@@ -207,6 +211,8 @@ sbmf_oracle* sbmf_oracle_create(uint64_t n, const uint32_t* user, const uint32_t
     h->sigma_0 = h->sigma_1 = h->sigma_2 = h->sigma_4 = h->sigma_5 = 1.0;
     h->mu_b_0 = 0.0; h->sigma_b_0 = 0.0; h->b_0 = 0.0; h->alpha = 0.0;
     h->clamp_lo = 0.5; h->clamp_hi = 5.0;                                    /* [T]:627-628 */
+    h->variant = 0;
+    h->ng_a_0 = 1; h->ng_b_0 = 1; h->nu_0 = 1; h->ng_mu_0 = 0.0; h->ng_alpha_0 = 1; h->ng_beta_0 = 1;   /* [S]:260-269 */
     return h;
 }
 
@@ -223,6 +229,7 @@ void sbmf_oracle_destroy(sbmf_oracle* h)
 }
 
 void sbmf_oracle_srand(unsigned seed) { srand(seed); }
+void sbmf_oracle_set_variant(sbmf_oracle* h, int variant) { h->variant = variant; }
 
 int sbmf_oracle_set_log(sbmf_oracle* h, const char* path)
 {
@@ -235,7 +242,8 @@ int sbmf_oracle_set_log(sbmf_oracle* h, const char* path)
 static void log_init(sbmf_oracle* h)
 {
     if (h->log) {
-        double rec[3] = {0.0, 0.0, 1.0};   /* ran_gaussian(0.0,1.0) of [T]:242, 248 */
+        /* [T]:242, 248 call ran_gaussian(0.0,1.0) and scale by 0.1; [S]:240, 248 call ran_gaussian(0.0,0.1) */
+        double rec[3] = {0.0, 0.0, h->variant != 0 ? 0.1 : 1.0};
         fwrite(rec, sizeof(double), 3, h->log);
     }
 }
@@ -446,8 +454,131 @@ static void one_sweep(sbmf_oracle* h, double* rmse_out, double* rmse_sweep_out)
     h->iter++;
 }
 
+/* ------------------------------------------------------------------ one sweep of [S] = src/libfm/gibbs_sbpmf2.cpp:308-563
+ * (the active code only: everything about b_0 / b_i / b_j sits inside comments there) */
+static void one_sweep_S(sbmf_oracle* h, double* rmse_out, double* rmse_sweep_out)
+{
+    const uint32_t I = h->I, J = h->J, D = h->K;
+    const uint64_t N = h->N;
+    double* U = h->U; double* V = h->V; double* E = h->E;
+    const double num_rows = (double)N;
+
+    /* [S]:317-334 */
+    double E_sum = 0.0, E_sq = 0.0;
+    for (uint64_t n = 0; n < N; ++n) {
+        uint32_t user = h->tu[n], item = h->ti[n];
+        double temp = 0.0;
+        for (uint32_t k = 0; k < D; ++k) temp += U[(size_t)user * D + k] * V[(size_t)k * J + item];
+        E[n] = h->target[n] - (0.0 + 0.0 + 0.0 + temp);
+        E_sum += E[n];
+        E_sq += (E[n] * E[n]);
+    }
+    /* tau, [S]:339-342 */
+    h->alpha = draw_gamma(h, SBMF_SITE_ALPHA, 0, h->ng_a_0 + 0.5 * num_rows, h->ng_b_0 + 0.5 * E_sq);
+
+    /* Normal-Gamma factor hypers, [S]:375-414 */
+    for (uint32_t k = 0; k < D; ++k) {
+        double temp = 0.0, temp2 = 0.0;
+        for (uint32_t i = 0; i < I; ++i) {
+            double u = U[(size_t)i * D + k];
+            temp += (u - h->mu_u[k]) * (u - h->mu_u[k]);
+            temp2 += u;
+        }
+        double a = h->ng_alpha_0 + 0.5 * (double)(I + 1);
+        double b = h->ng_beta_0 + h->nu_0 * (h->mu_u[k] - h->ng_mu_0) * (h->mu_u[k] - h->ng_mu_0) + (0.5) * temp;
+        h->sigma_u[k] = draw_gamma(h, SBMF_SITE_SIGMA_U, k, a, b);
+        double sigma_u_k_star = (double)1.0 / (h->nu_0 * h->sigma_u[k] + h->sigma_u[k] * (double)I);
+        double mu_u_k_star = sigma_u_k_star * (h->nu_0 * h->ng_mu_0 * h->sigma_u[k] + h->sigma_u[k] * temp2);
+        h->mu_u[k] = draw_gauss(h, SBMF_SITE_MU_U, k, 0, mu_u_k_star, post_stdev(h, sigma_u_k_star));
+
+        temp = 0.0; temp2 = 0.0;
+        for (uint32_t j = 0; j < J; ++j) {
+            double v = V[(size_t)k * J + j];
+            temp += (v - h->mu_v[k]) * (v - h->mu_v[k]);
+            temp2 += v;
+        }
+        a = h->ng_alpha_0 + 0.5 * (double)(J + 1);
+        b = h->ng_beta_0 + h->nu_0 * (h->mu_v[k] - h->ng_mu_0) * (h->mu_v[k] - h->ng_mu_0) + (0.5) * temp;
+        h->sigma_v[k] = draw_gamma(h, SBMF_SITE_SIGMA_V, k, a, b);
+        double sigma_v_k_star = (double)1.0 / (h->nu_0 * h->sigma_v[k] + h->sigma_v[k] * (double)J);
+        /* [S]:412 multiplies by sigma_u_k_star (a copy-paste slip); variant 2 uses sigma_v_k_star */
+        double lead = (h->variant == 1) ? sigma_u_k_star : sigma_v_k_star;
+        double mu_v_k_star = lead * (h->nu_0 * h->ng_mu_0 * h->sigma_v[k] + h->sigma_v[k] * temp2);
+        h->mu_v[k] = draw_gauss(h, SBMF_SITE_MU_V, k, 0, mu_v_k_star, post_stdev(h, sigma_v_k_star));
+    }
+
+    /* users, [S]:452-489 (bias step commented out there) */
+    for (uint32_t i = 0; i < I; ++i) {
+        const int64_t beg = h->rptr[i];
+        const uint32_t c = (uint32_t)(h->rptr[i + 1] - beg);
+        const uint64_t* id = h->r_id + beg;
+        const uint32_t* val = h->r_val + beg;
+        for (uint32_t k = 0; k < D; ++k) {
+            const double* Vk = V + (size_t)k * J;
+            double* u = &U[(size_t)i * D + k];
+            double temp = 0.0, temp2 = 0.0;
+            for (uint32_t p = 0; p < c; ++p) {
+                temp += (Vk[val[p]] * Vk[val[p]]);
+                temp2 += (Vk[val[p]] * (E[id[p]] + Vk[val[p]] * (*u)));
+            }
+            double s = (double)1.0 / (h->sigma_u[k] + (h->alpha * temp));
+            double m = s * (h->alpha * temp2 + h->sigma_u[k] * h->mu_u[k]);
+            double old = *u;
+            *u = draw_gauss(h, SBMF_SITE_U, i, k, m, post_stdev(h, s));
+            for (uint32_t p = 0; p < c; ++p) E[id[p]] += Vk[val[p]] * (old - *u);
+        }
+    }
+    /* items, [S]:494-534 */
+    for (uint32_t j = 0; j < J; ++j) {
+        const int64_t beg = h->cptr[j];
+        const uint32_t c = (uint32_t)(h->cptr[j + 1] - beg);
+        const uint64_t* id = h->c_id + beg;
+        const uint32_t* val = h->c_val + beg;
+        for (uint32_t k = 0; k < D; ++k) {
+            double* v = &V[(size_t)k * J + j];
+            double temp = 0.0, temp2 = 0.0;
+            for (uint32_t p = 0; p < c; ++p) {
+                double u = U[(size_t)val[p] * D + k];
+                temp += (u * u);
+                temp2 += (u * (E[id[p]] + (*v) * u));
+            }
+            double s = (double)1.0 / (h->sigma_v[k] + (h->alpha * temp));
+            double m = s * (h->alpha * temp2 + h->sigma_v[k] * h->mu_v[k]);
+            double old = *v;
+            *v = draw_gauss(h, SBMF_SITE_V, j, k, m, post_stdev(h, s));
+            for (uint32_t p = 0; p < c; ++p) E[id[p]] += U[(size_t)val[p] * D + k] * (old - *v);
+        }
+    }
+    /* test RMSE, [S]:538-562 */
+    {
+        double diff_sqr_sum = 0.0, diff_sweep = 0.0;
+        for (uint64_t t = 0; t < h->Nt; ++t) {
+            uint32_t user = h->su[t], item = h->si[t];
+            double temp = 0.0;
+            for (uint32_t k = 0; k < D; ++k) temp += U[(size_t)user * D + k] * V[(size_t)k * J + item];
+            temp = temp < h->clamp_hi ? temp : h->clamp_hi;
+            temp = temp > h->clamp_lo ? temp : h->clamp_lo;
+            h->sum[t] += temp;
+            double d = h->ttarget[t] - ((double)h->sum[t] / (h->iter + 1));
+            diff_sqr_sum += d * d;
+            diff_sweep += (h->ttarget[t] - temp) * (h->ttarget[t] - temp);
+        }
+        double rmse = sqrt(diff_sqr_sum / (double)h->Nt);
+        h->last_rmse_sweep = sqrt(diff_sweep / (double)h->Nt);
+        if (rmse_out) *rmse_out = rmse;
+        if (rmse_sweep_out) *rmse_sweep_out = h->last_rmse_sweep;
+    }
+    h->iter++;
+    (void)E_sum;
+}
+
 void sbmf_oracle_sweep(sbmf_oracle* h, uint32_t n, double* rmse_out, double* rmse_sweep_out)
 {
+    if (h->variant != 0) {
+        for (uint32_t s = 0; s < n; ++s) one_sweep_S(h, rmse_out ? rmse_out + s : NULL, rmse_sweep_out ? rmse_sweep_out + s : NULL);
+        if (h->log) fflush(h->log);
+        return;
+    }
     for (uint32_t s = 0; s < n; ++s) one_sweep(h, rmse_out ? rmse_out + s : NULL, rmse_sweep_out ? rmse_sweep_out + s : NULL);
     if (h->log) fflush(h->log);
 }

@@ -54,6 +54,11 @@ sbmf_oracle* sbmf_oracle_create(uint64_t n, const uint32_t* user, const uint32_t
                                 int noise_mode, int stdev_mode, uint64_t seed);
 void sbmf_oracle_destroy(sbmf_oracle*);
 
+/* 0 (default) = the top-level gibbs_sbpmf2.cpp ([T]); 1 = src/libfm/gibbs_sbpmf2.cpp ([S]) as committed: no biases / global
+   mean, Normal-Gamma factor hyper-prior, tau ~ G(a0 + N/2, b0 + sum e^2 / 2), including the slip at [S]:412; 2 = [S] with the
+   slip corrected.  Call before init_factors. */
+void sbmf_oracle_set_variant(sbmf_oracle*, int variant);
+
 /* glibc srand(); the reference never calls it (seed 1). */
 void sbmf_oracle_srand(unsigned seed);
 

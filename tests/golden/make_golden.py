@@ -55,16 +55,18 @@ def log_summary(path):
             "sample": [[float(x).hex() for x in a[i]] for i in idx]}
 
 
-def shim_case(name, train, test, live_init, K=20, T=10):
+def shim_case(name, train, test, live_init, K=20, T=10, variant="T"):
+    """variant "T" = top-level gibbs_sbpmf2.cpp, "S" = src/libfm/gibbs_sbpmf2.cpp (Normal-Gamma hyper-prior, no biases)"""
     for mode in ("live", "zero"):
         log = f"/tmp/sbmf_golden_{name}_{mode}.log"
         env = {"SBMF_SHIM_LOG": log}
         if mode == "zero":
             env.update({"SBMF_SHIM_MODE": "zero", "SBMF_SHIM_LIVE_INIT": str(live_init)})
-        r = run_ref(ref_binary(K, T, shim=True), train, test, threads=1, env_extra=env)
+        r = run_ref(ref_binary(K, T, shim=True, variant=variant), train, test, threads=1, env_extra=env)
         out = {"case": name, "K": K, "T": T, "mode": mode, "num_rows": r["num_rows"], "num_users": r["num_users"],
                "num_items": r["num_items"], "rmse": r["rmse_text"], "log": log_summary(log)}
-        with open(os.path.join(HERE, f"ref_{name}_K{K}_T{T}_{mode}.json"), "w") as f:
+        tag = "ref" if variant == "T" else "refS"
+        with open(os.path.join(HERE, f"{tag}_{name}_K{K}_T{T}_{mode}.json"), "w") as f:
             json.dump(out, f, indent=1)
         os.remove(log)
         print(name, mode, r["rmse_text"][:3], "...")
@@ -80,6 +82,12 @@ def main():
     write_tiny()
     shim_case("tiny_unsorted", os.path.join(HERE, "tiny_unsorted.train"), os.path.join(HERE, "tiny_unsorted.test"),
               50 * 20 + 20 * 40)
+    # [S]: the sibling program src/libfm/gibbs_sbpmf2.cpp (unmodified; its input names are staged by run_ref)
+    r = run_ref(ref_binary(20, 100, variant="S"), os.path.join(ML, "train_sbpmf"), os.path.join(ML, "test_sbpmf"), threads=1)
+    with open(os.path.join(HERE, "refS_ml100k_K20_T100_rmse.txt"), "w") as f:
+        f.write("# unmodified reference src/libfm/gibbs_sbpmf2.cpp, data/m100k, D=20, 100 sweeps, OMP_NUM_THREADS=1, glibc rand seed 1\n")
+        f.write("\n".join(r["rmse_text"]) + "\n")
+    shim_case("ml100k", os.path.join(ML, "train_sbpmf"), os.path.join(ML, "test_sbpmf"), 943 * 20 + 20 * 1682, variant="S")
 
 
 if __name__ == "__main__":

@@ -31,6 +31,7 @@ def lib():
                                          C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint64]
         L.sbmf_oracle_destroy.argtypes = [C.c_void_p]
         L.sbmf_oracle_srand.argtypes = [C.c_uint]
+        L.sbmf_oracle_set_variant.argtypes = [C.c_void_p, C.c_int]
         L.sbmf_oracle_init_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.sbmf_oracle_sweep.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.sbmf_oracle_set_log.argtypes = [C.c_void_p, C.c_char_p]
@@ -54,7 +55,9 @@ def _p(a):
 
 
 class Oracle:
-    def __init__(self, tu, ti, tr, su, si, sr, num_users, num_items, K, noise=NOISE_RAND, stdev_mode=STDEV_REF, seed=1):
+    def __init__(self, tu, ti, tr, su, si, sr, num_users, num_items, K, noise=NOISE_RAND, stdev_mode=STDEV_REF, seed=1, variant=0):
+        """variant 0 = top-level gibbs_sbpmf2.cpp ([T]); 1 = src/libfm/gibbs_sbpmf2.cpp ([S], Normal-Gamma hypers, no biases) as
+        committed; 2 = [S] with its line-412 slip corrected"""
         self.L = lib()
         self.tu, self.ti = np.ascontiguousarray(tu, np.uint32), np.ascontiguousarray(ti, np.uint32)
         self.tr = np.ascontiguousarray(tr, np.float64)
@@ -63,6 +66,8 @@ class Oracle:
         self.I, self.J, self.K, self.N, self.Nt = num_users, num_items, K, self.tu.size, self.su.size
         self.h = self.L.sbmf_oracle_create(self.N, _p(self.tu), _p(self.ti), _p(self.tr), self.Nt, _p(self.su), _p(self.si), _p(self.sr),
                                            num_users, num_items, K, noise, stdev_mode, seed)
+        if variant:
+            self.L.sbmf_oracle_set_variant(self.h, variant)
 
     def close(self):
         if self.h:
