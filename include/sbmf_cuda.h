@@ -48,7 +48,13 @@ typedef enum sbmf_sample_mode {
 } sbmf_sample_mode;
 
 typedef enum sbmf_hyper_mode {
-    SBMF_HYPER_REF_T = 0                /* hyper-parameter updates exactly as [T]:366-511 */
+    SBMF_HYPER_REF_T = 0,               /* hyper-parameter updates exactly as [T]:366-511 */
+    /* the sibling program src/libfm/gibbs_sbpmf2.cpp ("[S]", the paper's Algorithm 1 hyper step): Normal-Gamma prior on the
+       per-dimension (mu, sigma) ([S]:375-414), tau ~ Gamma(a0 + N/2, b0 + sum e^2 / 2) ([S]:339-342), and -- as in [S], where
+       that code is commented out -- NO biases and NO global mean (they stay 0).  NG_S reproduces [S] including the slip at
+       [S]:412 (the mean of mu_v is scaled by the USER posterior variance); NG uses the item one. */
+    SBMF_HYPER_NG_S = 1,
+    SBMF_HYPER_NG = 2
 } sbmf_hyper_mode;
 
 /* Prior constants of [T]:284-313, indexed like the reference's names: alpha_0 (sigma_b_0), alpha_1
@@ -57,6 +63,8 @@ typedef enum sbmf_hyper_mode {
 typedef struct sbmf_priors {
     double alpha[6], beta[6], mu[6], sigma[6];
     double alpha_dash, beta_dash;
+    /* Normal-Gamma modes, [S]:260-269: a_0, b_0 (noise precision), alpha_0, beta_0, mu_0, nu_0 (factor hypers); all 1/1/1/1/0/1 */
+    double ng_a_0, ng_b_0, ng_alpha_0, ng_beta_0, ng_mu_0, ng_nu_0;
 } sbmf_priors;
 
 typedef struct sbmf_config {

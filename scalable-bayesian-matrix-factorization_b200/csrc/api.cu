@@ -62,6 +62,8 @@ int sbmf_cuda_config_default(sbmf_config* cfg)
     }
     cfg->priors.alpha_dash = 1.0;
     cfg->priors.beta_dash = 1.0;
+    cfg->priors.ng_a_0 = cfg->priors.ng_b_0 = cfg->priors.ng_alpha_0 = cfg->priors.ng_beta_0 = cfg->priors.ng_nu_0 = 1.0;   // [S]:260-269
+    cfg->priors.ng_mu_0 = 0.0;
     cfg->rank = 0;
     cfg->world_size = 1;
     return SBMF_OK;
@@ -82,7 +84,7 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
         g_create_err = "create: K must be in [1, SBMF_MAX_K]";
         return SBMF_ERR_INVALID;
     }
-    if (cfg->sample_mode < 0 || cfg->sample_mode > 2 || cfg->hyper_mode != SBMF_HYPER_REF_T) {
+    if (cfg->sample_mode < 0 || cfg->sample_mode > 2 || cfg->hyper_mode < 0 || cfg->hyper_mode > 2) {
         g_create_err = "create: unknown sample_mode / hyper_mode";
         return SBMF_ERR_INVALID;
     }
@@ -374,7 +376,7 @@ static int enqueue_sweep(Model& m, bool timing)
     if (timing) cudaEventRecord(m.ev_t[1], st);
     launch_global_hypers(m, st);                     // [T]:366-410
     launch_dim_hypers(m, st);                        // [T]:415-467
-    launch_bias_hypers(m, st);                       // [T]:469-511
+    if (m.cfg.hyper_mode == SBMF_HYPER_REF_T) launch_bias_hypers(m, st);   // [T]:469-511 ([S] has no biases)
     // peer-mapped replicas: the user phase writes U rows into every replica, so every rank must be done reading U first
     if (m.peer_ok) crc |= launch_barrier(m, st);
     if (timing) cudaEventRecord(m.ev_t[2], st);

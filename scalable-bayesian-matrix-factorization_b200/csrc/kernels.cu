@@ -614,7 +614,7 @@ reduce_pair_kernel(const double* __restrict__ part, uint32_t nparts, double* __r
 }
 
 __global__ void __launch_bounds__(32)
-global_hypers_kernel(Scalars* sc, const double* __restrict__ red2, uint64_t N, sbmf_priors pr, int mode, uint64_t seed)
+global_hypers_kernel(Scalars* sc, const double* __restrict__ red2, uint64_t N, sbmf_priors pr, int mode, int hyper_mode, uint64_t seed)
 {
     if (threadIdx.x != 0) return;
     const double S1 = red2[0], S2 = red2[1];
@@ -622,6 +622,13 @@ global_hypers_kernel(Scalars* sc, const double* __restrict__ red2, uint64_t N, s
     const double Nd = (double)N;
     sc->sum_e = S1;
     sc->sum_e2 = S2;
+    if (hyper_mode != SBMF_HYPER_REF_T) {   // [S]:339-342; global mean and biases do not exist in [S]
+        const double tau = draw_gamma_f64(mode, seed, SITE_ALPHA, 0, sweep, pr.ng_a_0 + 0.5 * Nd, pr.ng_b_0 + 0.5 * S2);
+        sc->alpha = tau;
+        sc->alpha_f = (float)tau;
+        sc->shift_f = 0.f;
+        return;
+    }
     const double alpha = draw_gamma_f64(mode, seed, SITE_ALPHA, 0, sweep, pr.alpha_dash + Nd, pr.beta_dash + S2);
     double b0 = sc->b_0, mu_b0 = sc->mu_b_0;
     const double sigma_b0 = draw_gamma_f64(mode, seed, SITE_SIGMA_B0, 0, sweep, pr.alpha[0] + 1.0, pr.beta[0] + 0.5 * (b0 - mu_b0) * (b0 - mu_b0));
@@ -698,7 +705,7 @@ dim_hyper_partial_kernel(const float* __restrict__ F, uint32_t n, uint32_t ns, c
 __global__ void __launch_bounds__(32)
 dim_hyper_final_kernel(const double* __restrict__ part, uint32_t chunks, uint32_t n, uint32_t K, double* sigma_k, double* mu_k, float* sigma_kf,
                        float* mu_kf, const Scalars* sc, double pa, double pb, double pmu, double psigma, int mode, uint64_t seed,
-                       uint32_t site_sigma, uint32_t site_mu)
+                       uint32_t site_sigma, uint32_t site_mu, int hyper_mode, sbmf_priors pr, double* post_var, const double* lead_var)
 {
     const uint32_t b = blockIdx.x, k = threadIdx.x;
     if (k >= 8) return;
@@ -717,6 +724,23 @@ dim_hyper_final_kernel(const double* __restrict__ part, uint32_t chunks, uint32_
     }
     const uint32_t sweep = sc->sweep;
     const double nd = (double)n;
+    if (hyper_mode != SBMF_HYPER_REF_T) {   // Normal-Gamma step of [S]:383-413
+        const double mo = mu_k[kk];
+        const double a = pr.ng_alpha_0 + 0.5 * (nd + 1.0);
+        const double b = pr.ng_beta_0 + pr.ng_nu_0 * (mo - pr.ng_mu_0) * (mo - pr.ng_mu_0) + 0.5 * SS;
+        const double sg = draw_gamma_f64(mode, seed, site_sigma, kk, sweep, a, b);
+        const double s = 1.0 / (pr.ng_nu_0 * sg + sg * nd);
+        post_var[kk] = s;
+        // [S]:412 scales the item-side mean by the USER side's posterior variance; lead_var != NULL reproduces that
+        const double lead = lead_var ? lead_var[kk] : s;
+        const double mn = lead * (pr.ng_nu_0 * pr.ng_mu_0 * sg + sg * S);
+        const double mun = draw_gauss_f64(mode, seed, site_mu, kk, 0, sweep, mn, s);
+        sigma_k[kk] = sg;
+        mu_k[kk] = mun;
+        sigma_kf[kk] = (float)sg;
+        mu_kf[kk] = (float)mun;
+        return;
+    }
     const double sig = draw_gamma_f64(mode, seed, site_sigma, kk, sweep, pa + nd, pb + 0.5 * SS);
     const double s = 1.0 / (psigma + sig * nd);
     const double m = s * (psigma * pmu + sig * S);
@@ -912,7 +936,7 @@ void launch_stats(Model& m, cudaStream_t st)
 
 void launch_global_hypers(Model& m, cudaStream_t st)
 {
-    global_hypers_kernel<<<1, 32, 0, st>>>(m.sc, m.red2, m.N, m.cfg.priors, m.cfg.sample_mode, m.cfg.seed);
+    global_hypers_kernel<<<1, 32, 0, st>>>(m.sc, m.red2, m.N, m.cfg.priors, m.cfg.sample_mode, m.cfg.hyper_mode, m.cfg.seed);
     m.launches++;
 }
 
@@ -922,7 +946,8 @@ static void dim_hypers_side(Model& m, Side& s, cudaStream_t st)
     dim_hyper_partial_kernel<<<dim3(s.hyp_chunks, m.KB), 256, 0, st>>>(s.F, s.n, s.n + 1, s.mu_k, s.hyp_part, s.hyp_chunks);
     dim_hyper_final_kernel<<<m.KB, 32, 0, st>>>(s.hyp_part, s.hyp_chunks, s.n, m.K, s.sigma_k, s.mu_k, s.sigma_kf, s.mu_kf, m.sc, p.alpha[s.prior],
                                                 p.beta[s.prior], p.mu[s.prior], p.sigma[s.prior], m.cfg.sample_mode, m.cfg.seed, s.site_sigma_k,
-                                                s.site_mu_k);
+                                                s.site_mu_k, m.cfg.hyper_mode, p, s.post_var,
+                                                (m.cfg.hyper_mode == SBMF_HYPER_NG_S && &s == &m.it) ? m.us.post_var : nullptr);
     m.launches += 2;
 }
 
@@ -994,6 +1019,7 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
 
     const int KB = (int)m.KB;
     const bool heavy = self.n_heavy > 0;
+    const bool with_bias = m.cfg.hyper_mode == SBMF_HYPER_REF_T;   // [S] (the Normal-Gamma modes) has no bias half-step
     // row classes are independent (disjoint rows, slots and factor rows): the streaming pipeline runs on its own stream and the
     // resident bins are spread over three, so the tail of one launch overlaps the head of another
     cudaStream_t sr = m.s_main, sh = m.s_aux;
@@ -1009,7 +1035,7 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     if (nb > KB) nb = KB;
     for (int b0 = 0; b0 < KB; b0 += nb) {
         const int b1 = (b0 + nb < KB) ? b0 + nb : KB;
-        const int do_bias = (b0 == 0) ? 1 : 0;
+        const int do_bias = (b0 == 0 && with_bias) ? 1 : 0;
         launch_bin<11>(m, a, self, b0, b1, do_bias, refresh, sb[0]);   // longest rows first
         launch_bin<10>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
         launch_bin<9>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
@@ -1037,9 +1063,13 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         if (refresh) heavy_accumulate_kernel<PREV, CUR, 2, 64, true><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);  \
         else heavy_accumulate_kernel<PREV, CUR, 2, 64, false><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);         \
     } while (0)
-        HEAVY_ACC(0, 1, 0, 0);
-        heavy_solve_kernel<1><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
-        HEAVY_ACC(1, 2, 0, 0);
+        if (with_bias) {
+            HEAVY_ACC(0, 1, 0, 0);
+            heavy_solve_kernel<1><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
+            HEAVY_ACC(1, 2, 0, 0);
+        } else {
+            HEAVY_ACC(0, 2, 0, 0);
+        }
         heavy_solve_kernel<2><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
         const bool detail = m.timing_detail && !apply_shift;   // item phase only
         if (detail && m.ev_top.size() < (size_t)2 * KB) {

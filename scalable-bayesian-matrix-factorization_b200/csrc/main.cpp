@@ -243,6 +243,7 @@ int main(int argc, char** argv)
         const std::string p_help = cmd.reg("help", "this screen");
         const std::string p_samp = cmd.reg("do_sampling", "0 = conditional-mean updates (no noise); default=1");
         const std::string p_sdm = cmd.reg("stdev_mode", "ref = draw with stdev 1/lambda like the reference, sqrt = sqrt(1/lambda); default=ref");
+        const std::string p_hyper = cmd.reg("hyper", "t = hyper-parameter updates of gibbs_sbpmf2.cpp (default); ng_s = Normal-Gamma, no biases, as src/libfm/gibbs_sbpmf2.cpp; ng = the same with its line-412 slip corrected");
         const std::string p_burn = cmd.reg("burn_in", "sweeps before predictions are averaged; default=0");
         const std::string p_reb = cmd.reg("rebuild_every", "rebuild the residual every n sweeps; default=1");
         const std::string p_dev = cmd.reg("device", "CUDA device ordinal; default=0");
@@ -312,6 +313,9 @@ int main(int argc, char** argv)
         cfg.init_stdev = cmd.getd(p_init, 0.1);
         cfg.burn_in = (uint32_t)cmd.geti(p_burn, 0);
         cfg.rebuild_every = (uint32_t)cmd.geti(p_reb, 1);
+        const std::string hyp = cmd.get(p_hyper, "t");
+        if (hyp != "t" && hyp != "ng_s" && hyp != "ng") throw std::string("-hyper must be t, ng_s or ng");
+        cfg.hyper_mode = hyp == "t" ? SBMF_HYPER_REF_T : (hyp == "ng_s" ? SBMF_HYPER_NG_S : SBMF_HYPER_NG);
         const std::string sdm = cmd.get(p_sdm, "ref");
         if (sdm != "ref" && sdm != "sqrt") throw std::string("-stdev_mode must be ref or sqrt");
         cfg.sample_mode = cmd.geti(p_samp, 1) == 0 ? SBMF_SAMPLE_ZERO_NOISE : (sdm == "sqrt" ? SBMF_SAMPLE_SQRT : SBMF_SAMPLE_REF_VAR_AS_STDEV);

@@ -57,6 +57,7 @@ struct Side {
     float* F = nullptr;               // [KB][n][8]  K8-blocked factors (own rows; gather target of the other side)
     float *bias = nullptr, *mu_b = nullptr, *sigma_b = nullptr;   // [n]
     double *sigma_k = nullptr, *mu_k = nullptr;                   // [KP] hyper-parameters (fp64 masters)
+    double* post_var = nullptr;                                   // [KP] posterior variance of mu_k (Normal-Gamma modes, [S]:391/411)
     float *sigma_kf = nullptr, *mu_kf = nullptr;                  // [KP] fp32 mirrors read by the row kernels
     double* hyp_part = nullptr;       // [KB][hyp_chunks][16] partial (sum, sumsq) of the per-dimension hyper step
     uint32_t hyp_chunks = 0;

@@ -97,7 +97,7 @@ static void free_side(Side& s)
 {
     cudaFree(s.ptr); cudaFree(s.idx); cudaFree(s.e); cudaFree(s.F);
     cudaFree(s.bias); cudaFree(s.mu_b); cudaFree(s.sigma_b);
-    cudaFree(s.sigma_k); cudaFree(s.mu_k); cudaFree(s.sigma_kf); cudaFree(s.mu_kf); cudaFree(s.hyp_part);
+    cudaFree(s.sigma_k); cudaFree(s.mu_k); cudaFree(s.post_var); cudaFree(s.sigma_kf); cudaFree(s.mu_kf); cudaFree(s.hyp_part);
     for (int b = 0; b < NBINS; ++b) cudaFree(s.bin_rows[b]);
     cudaFree(s.heavy_rows); cudaFree(s.heavy_slice_ptr); cudaFree(s.slices); cudaFree(s.hpart); cudaFree(s.hdelta);
     const uint32_t sf = s.site_f, sb = s.site_b, a = s.site_sigma_k, b_ = s.site_mu_k, c = s.site_sigma_b, d = s.site_mu_b;
@@ -407,7 +407,7 @@ static int alloc_side_state(Model& m, Side& s)
 {
     CK(dmalloc(&s.F, (size_t)m.KB * (s.n + 1) * 8));   // + the all-zero pad row
     CK(dmalloc(&s.bias, s.n)); CK(dmalloc(&s.mu_b, s.n)); CK(dmalloc(&s.sigma_b, s.n));
-    CK(dmalloc(&s.sigma_k, m.KP)); CK(dmalloc(&s.mu_k, m.KP)); CK(dmalloc(&s.sigma_kf, m.KP)); CK(dmalloc(&s.mu_kf, m.KP));
+    CK(dmalloc(&s.sigma_k, m.KP)); CK(dmalloc(&s.mu_k, m.KP)); CK(dmalloc(&s.post_var, m.KP)); CK(dmalloc(&s.sigma_kf, m.KP)); CK(dmalloc(&s.mu_kf, m.KP));
     s.hyp_chunks = (s.n + 16383) / 16384;
     if (s.hyp_chunks < 1) s.hyp_chunks = 1;
     CK(dmalloc(&s.hyp_part, (size_t)m.KB * s.hyp_chunks * 16));

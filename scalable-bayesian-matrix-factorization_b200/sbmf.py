@@ -14,11 +14,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsbmf_cuda.so")
 
 SAMPLE_REF, SAMPLE_SQRT, SAMPLE_ZERO = 0, 1, 2
+HYPER_REF_T, HYPER_NG_S, HYPER_NG = 0, 1, 2
 
 
 class Priors(C.Structure):
     _fields_ = [("alpha", C.c_double * 6), ("beta", C.c_double * 6), ("mu", C.c_double * 6), ("sigma", C.c_double * 6),
-                ("alpha_dash", C.c_double), ("beta_dash", C.c_double)]
+                ("alpha_dash", C.c_double), ("beta_dash", C.c_double), ("ng_a_0", C.c_double), ("ng_b_0", C.c_double),
+                ("ng_alpha_0", C.c_double), ("ng_beta_0", C.c_double), ("ng_mu_0", C.c_double), ("ng_nu_0", C.c_double)]
 
 
 class Config(C.Structure):
