@@ -264,10 +264,11 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
     hsp.push_back(0);
     // slice length: at most SLICE_LEN, but short enough that one streaming launch is >= ~8 waves of CTAs on this GPU
     // (a multi-GPU shard or a thin heavy tail would otherwise run 2-3 ragged waves per launch)
+    static const int64_t resident_max = getenv("SBMF_RESIDENT_MAX") ? atol(getenv("SBMF_RESIDENT_MAX")) : RESIDENT_MAX;   // tuning knob (<= 2048)
     uint64_t nnz_heavy_total = 0;
     for (uint32_t r = row0; r < row1; ++r) {
         const int64_t c = ptr[r + 1] - ptr[r];
-        if (c > RESIDENT_MAX) nnz_heavy_total += (uint64_t)c;
+        if (c > resident_max) nnz_heavy_total += (uint64_t)c;
     }
     int64_t slice_len = SLICE_LEN;
     {
@@ -277,7 +278,7 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
     }
     for (uint32_t r = row0; r < row1; ++r) {
         const int64_t c = ptr[r + 1] - ptr[r];
-        if (c <= RESIDENT_MAX) {
+        if (c <= resident_max) {
             int b = 0;
             while (c > kBins[b].cap) ++b;
             bins[b].push_back(r);
