@@ -97,7 +97,7 @@ typedef struct sbmf_state {
     float *mu_b_i, *sigma_b_i;   /* [num_users] */
     float *mu_b_j, *sigma_b_j;   /* [num_items] */
     double *sigma_u, *mu_u, *sigma_v, *mu_v;   /* [K] */
-    float* E;                    /* [n_train], rating order; as left by the last sweep */
+    float* E;                    /* [n_train], rating order; as left by the last sweep (multi-GPU: only this rank's shard is written) */
     double b_0, alpha, mu_b_0, sigma_b_0;      /* out */
     double sum_e, sum_e2;        /* out: the statistics of [T]:357-358 taken at the start of the last sweep */
     uint32_t sweeps_done;        /* out */
@@ -106,16 +106,17 @@ typedef struct sbmf_state {
 
 typedef struct sbmf_timing {
     /* CUDA-event milliseconds accumulated since the last sbmf_cuda_reset_timing, per phase of [T]'s sweep */
-    double ms_rebuild;           /* [T]:342-359 */
+    double ms_rebuild;           /* [T]:342-359: stand-alone rebuild, or (fused mode) residual CSC->CSR permute + sum e / sum e^2 pass */
     double ms_hypers;            /* [T]:366-511 */
-    double ms_user_phase;        /* [T]:514-558 */
+    double ms_user_phase;        /* [T]:514-558 (+ the fused residual rebuild) */
     double ms_exchange;          /* residual CSR->CSC permutation (+ multi-GPU exchange) */
     double ms_item_phase;        /* [T]:563-606 */
     double ms_eval;              /* [T]:610-636 */
     double ms_total;
     uint64_t sweeps;
     uint64_t kernel_launches;    /* kernels of this library launched by those sweeps */
-    uint64_t nnz_light_user, nnz_heavy_user, nnz_light_item, nnz_heavy_item;   /* rating split by kernel path */
+    uint64_t nnz_light_user, nnz_heavy_user, nnz_light_item, nnz_heavy_item;   /* ratings by kernel path: rows held in
+                                    registers (<= 2048 ratings) vs rows streamed in slices; of this rank's shard */
     /* the dominant kernel, timed per launch with CUDA events on its own stream (only while detail timing is on):
        the item-phase streaming block step heavy_accumulate_kernel<2,2> (kernels.cu) */
     double ms_top_kernel;        /* sum of its launch durations */

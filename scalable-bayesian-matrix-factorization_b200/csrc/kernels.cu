@@ -408,7 +408,7 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
     const uint32_t* idx = a.idx + sl.start;
     float* ep = a.e + sl.start;
     // batches of UNR ratings per thread: all index/residual loads, then all gathers, then the math, so that
-    // 2*UNR sector gathers per thread are in flight (the kernel is bound by gather latency, not by arithmetic)
+    // 2*UNR sector gathers per thread are in flight (the kernel is bound by the L2->SM gather path, not by arithmetic)
     for (uint32_t base = threadIdx.x; base < sl.len; base += THREADS * UNR) {
         uint32_t id[UNR];
         float e[UNR];

@@ -23,8 +23,7 @@ constexpr int KBLK = 8;             // latent dimensions per factor block (one 3
 constexpr int NACC = 48;            // g[8] + upper-triangular G[36] = 44 accumulators, padded to 48
 constexpr int NBINS = 12;            // resident-row bins, see kBin* below
 constexpr int RESIDENT_MAX = 2048;  // longer rows go through the streaming ("heavy") pipeline
-constexpr int SLICE_LEN = 4096;     // ratings per heavy-row slice (one CTA)
-constexpr int SLICE_THREADS = 256;
+constexpr int SLICE_LEN = 4096;     // max ratings per heavy-row slice (one 64-thread CTA); shorter when a shard is small (storage.cu)
 constexpr int MAX_PEERS = 8;         // replicas a phase kernel can write directly (one NVSwitch domain)
 
 // resident bins: a row of c ratings is handled by WARPS warps holding RPL ratings per lane in registers
@@ -69,7 +68,7 @@ struct Side {
     uint32_t* heavy_slice_ptr = nullptr;  // [n_heavy+1] slice range of each heavy row
     Slice* slices = nullptr;              // [n_slices]
     float* hpart = nullptr;               // [n_slices][NACC]
-    float* hdelta = nullptr;              // [2][n_heavy][8] pending factor deltas (double-buffered by block parity)
+    float* hdelta = nullptr;              // [n_heavy][8] pending factor deltas of the block just solved, then [n_heavy] bias deltas
     uint64_t nnz_resident = 0, nnz_heavy = 0;
     uint32_t site_f = 0, site_b = 0;      // Philox streams of the factor / bias draws
     uint32_t site_sigma_k = 0, site_mu_k = 0, site_sigma_b = 0, site_mu_b = 0;
