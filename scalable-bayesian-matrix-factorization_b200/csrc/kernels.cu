@@ -156,7 +156,7 @@ __device__ __forceinline__ SolveOut solve_lanes(const float* sm, const PhaseArgs
     for (int l = 0; l < 8; ++l) {
         const float mean = s * fmaf(alpha, B, smu);
         const float cand = uo - fmaf(sd, z, mean);
-        const float dl = __shfl_sync(0xffffffffu, cand, l);
+        const float dl = __shfl_sync(0xffffffffu, cand, l, 8);   // within the octet: octets of a warp may hold different rows
         o.d[l] = dl;
         if (kq > l) B = fmaf(dl, Grow[l], B);
     }
@@ -164,7 +164,7 @@ __device__ __forceinline__ SolveOut solve_lanes(const float* sm, const PhaseArgs
 #pragma unroll
     for (int l = 0; l < 8; ++l) mine = (kq == l) ? o.d[l] : mine;
     o.mine = mine;
-    if (lane < 8) {
+    if (lane < 8) {   // callers pass the lane index WITHIN the row's lane group
         const float un = uo - mine;
         for (int q = 0; q < a.nrep; ++q) a.Frep[q][foff + kq] = un;   // 8 lanes x 4 B = one sector per replica
     }
@@ -359,6 +359,179 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
         const int p = r * TPR + t_in_row;
+        if (p < c) {
+            a.e[beg + p] = e[r];
+            if (REFRESH) a.pacc[beg + p] = pr[r];
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Short rows: G = 8 or 16 lanes own a row (RPL ratings per lane, rows of <= G * RPL ratings), so one warp works on 32 / G rows
+// at once.  Same arithmetic as row_resident_kernel<RPL, 1>, but the fixed per-row-block costs are shared: the transposed
+// reduction needs log2(G) halving steps and serves all rows of the warp with the same instructions, every octet runs the
+// lane-parallel solve for its own row, and the noise is drawn G / 8 blocks at a time.
+template <int G>
+__device__ __forceinline__ int group_reduce_scatter48(float (&v)[NACC], int lg)   // returns the packed index of v[0]
+{
+    if (G == 16) {
+        reduce_scatter_step<8, 24>(v, lg);
+        reduce_scatter_step<4, 12>(v, lg);
+        reduce_scatter_step<2, 6>(v, lg);
+        reduce_scatter_step<1, 3>(v, lg);
+        return ((lg >> 3) & 1) * 24 + ((lg >> 2) & 1) * 12 + ((lg >> 1) & 1) * 6 + (lg & 1) * 3;
+    } else {
+        reduce_scatter_step<4, 24>(v, lg);
+        reduce_scatter_step<2, 12>(v, lg);
+        reduce_scatter_step<1, 6>(v, lg);
+        return ((lg >> 2) & 1) * 24 + ((lg >> 1) & 1) * 12 + (lg & 1) * 6;
+    }
+}
+
+template <int RPL, int G, bool REFRESH>
+__global__ void __launch_bounds__(128, (RPL >= 6 ? 512 : RPL >= 4 ? 640 : 768) / 128)
+row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows, int b_begin, int b_end, int do_bias)
+{
+    constexpr int RPW = 32 / G;          // rows per warp
+    constexpr int NV = (G == 16) ? 3 : 6;   // reduced values per lane
+    constexpr int ZB = G / 8;            // blocks covered by one noise draw
+    __shared__ __align__(16) float s_tot[4 * RPW][SOLVE_SMEM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / G, lg = lane % G, kq = lane & 7;
+    const uint32_t r_idx = (blockIdx.x * 4 + warp) * RPW + grp;
+    const bool have_row = r_idx < nrows;                 // idle groups run along (the shuffles are warp-wide) but touch nothing
+    const uint32_t row = rows[have_row ? r_idx : nrows - 1];
+    const int64_t beg = a.ptr[row];
+    const int c = have_row ? (int)(a.ptr[row + 1] - beg) : 0;
+    float* tot = s_tot[warp * RPW + grp];
+
+    const int mode = a.mode;
+    const uint32_t K = a.K;
+    const float alpha = a.sc->alpha_f;
+    const uint32_t sweep = a.sc->sweep;
+    const uint32_t ns_other = a.ns_other, ns_self = a.ns_self;
+    const uint32_t pad_row = ns_other - 1;
+    const float* __restrict__ Fother = a.Fother;
+
+    // where this lane's NV reduced sums go in shared memory (packed once: constant-memory look-ups with a lane-dependent index are slow)
+    uint64_t off_a = 0, off_b = 0;
+    {
+        const int base0 = (G == 16) ? ((lg >> 3) & 1) * 24 + ((lg >> 2) & 1) * 12 + ((lg >> 1) & 1) * 6 + (lg & 1) * 3
+                                    : ((lg >> 2) & 1) * 24 + ((lg >> 1) & 1) * 12 + (lg & 1) * 6;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            off_a |= (uint64_t)c_pk_a[base0 + i] << (8 * i);
+            off_b |= (uint64_t)c_pk_b[base0 + i] << (8 * i);
+        }
+    }
+
+    uint32_t id[RPL];
+    float e[RPL];
+    float pr[REFRESH ? RPL : 1];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int p = r * G + lg;
+        const bool valid = p < c;
+        id[r] = valid ? a.idx[beg + p] : pad_row;
+        e[r] = valid ? a.e[beg + p] : 0.f;
+        if (REFRESH) pr[r] = (valid && b_begin > 0) ? a.pacc[beg + p] : 0.f;
+    }
+    float bias_new = 0.f;
+    if (REFRESH && !do_bias) bias_new = a.bias[row];
+    f8 f[RPL];
+    {
+        const float* Fo = Fother + (size_t)b_begin * ns_other * 8;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
+    }
+
+    if (do_bias) {
+        const float shift = a.apply_shift ? a.sc->shift_f : 0.f;
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            if (id[r] != pad_row) {
+                e[r] += shift;
+                t += e[r];
+            }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        const float bo = a.bias[row], sb = a.sigma_b[row], mb = a.mu_b[row];
+        const float s = 1.0f / (sb + alpha * (float)c);
+        const float mean = s * (sb * mb + alpha * (t + (float)c * bo));
+        float z = 0.f;
+        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        const float bn = draw_f32(mode, mean, s, z);
+        const float d = bo - bn;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            if (id[r] != pad_row) e[r] += d;
+        if (lg == 0 && have_row)
+            for (int q = 0; q < a.nrep; ++q) a.brep[q][row] = bn;
+        bias_new = bn;
+    }
+
+    float zq = 0.f;
+    for (int b = b_begin; b < b_end; ++b) {
+        const size_t foff = ((size_t)b * ns_self + row) * 8;
+        const bool live = (uint32_t)(b * 8 + kq) < K;
+        const float uo = live ? a.Fself[foff + kq] : 0.f;
+        const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
+        // this row's noise, ZB blocks at a time: lane lg of the group draws dimension 8 * ZB * (b / ZB) + lg
+        if (mode != SAMPLE_ZERO && (((b % ZB) == 0) || b == b_begin))
+            zq = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)((b - b % ZB) * 8 + lg), sweep));
+        float acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) accumulate(acc, f[r], e[r]);
+        group_reduce_scatter48<G>(acc, lg);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            tot[(uint32_t)(off_a >> (8 * i)) & 0xffu] = acc[i];
+            tot[(uint32_t)(off_b >> (8 * i)) & 0xffu] = acc[i];
+        }
+        __syncwarp();
+        const float z = __shfl_sync(0xffffffffu, zq, ((b % ZB) << 3) + kq, G);
+        float uo8[8];
+        if (REFRESH) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) uo8[k] = __shfl_sync(0xffffffffu, uo, k, 8);
+        }
+        // every octet solves its group's row (for G == 16 both octets of the group compute the same values); an idle group's
+        // lanes report lane index 8 so that they never take the write branch
+        const SolveOut so = solve_lanes(tot, a, foff, uo, sig, mu, live, mode, z, alpha, have_row ? lg : 8);
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const float fd = dot8(f[r], so.d);
+            e[r] += fd;
+            if (REFRESH) {
+                float fu = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) fu = fmaf(f[r].v[k], uo8[k], fu);
+                pr[r] += fu - fd;
+            }
+        }
+        if (b + 1 < b_end) {
+            const float* Fo = Fother + (size_t)(b + 1) * ns_other * 8;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) f[r] = ld256_nc(Fo + (size_t)id[r] * 8);
+        }
+        __syncwarp();
+    }
+
+    if (REFRESH && b_end == a.KBtot) {
+        const float b0 = a.sc->b_0_f;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const int p = r * G + lg;
+            if (p < c) a.e[beg + p] = a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]);
+        }
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int p = r * G + lg;
         if (p < c) {
             a.e[beg + p] = e[r];
             if (REFRESH) a.pacc[beg + p] = pr[r];
@@ -974,10 +1147,30 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
     constexpr int RPL = kBins[BIN].rpl, WARPS = kBins[BIN].warps;
     const uint32_t n = self.bin_count[BIN];
     if (!n) return;
-    const dim3 grid(WARPS == 1 ? (n + 3) / 4 : n), block(WARPS == 1 ? 128 : WARPS * 32);
-    if (refresh) row_resident_kernel<RPL, WARPS, true><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-    else row_resident_kernel<RPL, WARPS, false><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-    m.launches++;
+    if constexpr (WARPS == 0) {   // short rows: G lanes per row (kBins[].cap = G * RPL)
+        static const bool no_group = getenv("SBMF_NO_GROUP") != nullptr;   // debugging knob: one warp per short row instead
+        if (no_group) {
+            constexpr int R1 = kBins[BIN].cap / 32;
+            const dim3 grid1((n + 3) / 4);
+            if (refresh) row_resident_kernel<R1, 1, true><<<grid1, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            else row_resident_kernel<R1, 1, false><<<grid1, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            m.launches++;
+            return;
+        }
+        constexpr int G = kBins[BIN].cap / (RPL > 0 ? RPL : 1) >= 16 ? 16 : 8;
+        const uint32_t rows_per_cta = 4 * (32 / G);
+        const dim3 grid((n + rows_per_cta - 1) / rows_per_cta);
+        if (refresh) row_group_kernel<RPL, G, true><<<grid, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else row_group_kernel<RPL, G, false><<<grid, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        m.launches++;
+        return;
+    }
+    if constexpr (WARPS > 0) {
+        const dim3 grid(WARPS == 1 ? (n + 3) / 4 : n), block(WARPS == 1 ? 128 : WARPS * 32);
+        if (refresh) row_resident_kernel<RPL, WARPS, true><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else row_resident_kernel<RPL, WARPS, false><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        m.launches++;
+    }
 }
 
 // One half-sweep: bias then all factor blocks of every row of `self` ([T]:514-558 users / 563-606 items).

@@ -28,7 +28,8 @@ constexpr int MAX_PEERS = 8;         // replicas a phase kernel can write direct
 
 // resident bins: a row of c ratings is handled by WARPS warps holding RPL ratings per lane in registers
 struct BinShape { int rpl, warps, cap; };
-constexpr BinShape kBins[NBINS] = {{1, 1, 32},  {2, 1, 64},  {3, 1, 96},  {4, 1, 128},  {6, 1, 192},  {8, 1, 256},
+// warps == 0: short rows, cap / rpl lanes (8 or 16) per row, several rows per warp (row_group_kernel)
+constexpr BinShape kBins[NBINS] = {{4, 0, 32},  {8, 0, 64},  {6, 0, 96},  {8, 0, 128},  {6, 1, 192},  {8, 1, 256},
                                    {3, 4, 384}, {4, 4, 512}, {6, 4, 768}, {8, 4, 1024}, {6, 8, 1536}, {8, 8, 2048}};
 
 // Device-resident scalars of the sweep ([T]:315-318 plus the statistics of [T]:342-359).
