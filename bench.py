@@ -42,7 +42,18 @@ WORKLOADS = {
     "ml10m_k100": (71567, 10681, 10000000, 100),
     "ml20m_k200": (138493, 26744, 20000000, 200),
     "ml1m_k50": (6040, 3706, 1000209, 50),
+    # BASELINE.json configs[4]; the 1e13-pair grid is sampled sparsely on host threads (csrc/synth_host.cpp).  Fits one B200
+    # (~70 GB at the peak of the layout build); use --steps 3 or so: a sweep takes about a second on one GPU
+    "scaled_1b_k200": (10000000, 1000000, 900000000, 200),
 }
+
+
+def generate(sbmf, workload, device):
+    I, J, NTRAIN, _ = WORKLOADS[workload]
+    n = int(round(NTRAIN / (1 - TEST_FRAC)))
+    if float(I) * float(J) > 1e11:
+        return sbmf.synth_generate_host(I, J, n, test_frac=TEST_FRAC, seed=SEED)
+    return sbmf.synth_generate(I, J, n, test_frac=TEST_FRAC, seed=SEED, device=device)
 TEST_FRAC = 0.1
 SEED = 20151001 + 3
 METRIC = "gibbs_factor_updates_per_s"
@@ -225,7 +236,7 @@ def main():
         if rank != 0:
             return
         # the sample is cut from the same generated matrix; generation needs the GPU only as a data source
-        d = sbmf.synth_generate(I, J, int(round(NTRAIN / (1 - TEST_FRAC))), test_frac=TEST_FRAC, seed=SEED, device=0)
+        d = generate(sbmf, a.workload, 0)
         sample = take_sample(d, a.cpu_sample)
         del d
         pairs = max(1, (a.steps + 1) // 2)
@@ -275,7 +286,7 @@ def main():
     cfg["parallelism"] = f"{world} GPU(s): users (CSR) and items (CSC) sharded by rating count, factors replicated" if world > 1 else "1 GPU"
     dev = local_rank
     t0 = time.perf_counter()
-    d = sbmf.synth_generate(I, J, int(round(NTRAIN / (1 - TEST_FRAC))), test_frac=TEST_FRAC, seed=SEED, device=dev)
+    d = generate(sbmf, a.workload, dev)
     gen_s = time.perf_counter() - t0
     n_train, n_test = int(d["train_user"].size), int(d["test_user"].size)
     cfg.update({"n_train": n_train, "n_test": n_test, "synth_seconds": round(gen_s, 2)})

@@ -219,6 +219,16 @@ int sbmf_cuda_synth_generate(const sbmf_synth_spec* spec, uint64_t* n_train, uin
                              uint32_t* test_user, uint32_t* test_item, float* test_rating);
 const char* sbmf_cuda_synth_last_error(void);
 
+/* The same matrix family sampled sparsely on host threads (csrc/synth_host.cpp): O(ratings) work instead of one trial per
+   (user, item) pair, for shapes like BASELINE.json's 10M x 1M / 1B ratings whose pair grid (1e13) cannot be visited.
+   spec->device is ignored; threads <= 0: all host threads.  The six output arrays are allocated by the call
+   (release each with sbmf_cuda_synth_host_free); the matrix does not depend on the number of threads. */
+int sbmf_cuda_synth_host_generate(const sbmf_synth_spec* spec, int threads, uint64_t* n_train, uint64_t* n_test,
+                             uint32_t** train_user, uint32_t** train_item, float** train_rating,
+                             uint32_t** test_user, uint32_t** test_item, float** test_rating);
+void sbmf_cuda_synth_host_free(void* ptr);
+const char* sbmf_cuda_synth_host_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

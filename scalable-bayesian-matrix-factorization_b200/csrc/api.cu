@@ -366,11 +366,25 @@ static int enqueue_sweep(Model& m, bool timing)
     const bool fused = due && !standalone;
     if (timing) cudaEventRecord(m.ev_t[0], st);
     int crc = 0;
+    // One GPU: the residual changes slot order (CSR <-> CSC) between the phases.  CSC -> CSR (before the user phase) is not
+    // a pass of its own: the first touch of e in the user phase reads it through the inverse permutation from the item side's
+    // array (PhaseArgs::e_map), where the gather hides behind the factor gathers (measured on the Netflix-shaped matrix:
+    // -0.9 ms for the pass, +0.4 ms in the phase).  The other direction stays a stand-alone pass by default: the item phase is
+    // dominated by the streaming pipeline, whose first pass is pure streaming and turns HBM-sector-bound with the gather
+    // (-0.5 ms, +0.7 ms).  SBMF_NO_FOLD=1 / SBMF_FOLD_ITEM=1 switch either (A/B measurements).
+    static const bool no_fold = getenv("SBMF_NO_FOLD") != nullptr;
+    static const bool fold_item_env = getenv("SBMF_FOLD_ITEM") != nullptr;
+    const bool fold_user = m.world == 1 && !no_fold;
+    const bool fold = m.world == 1 && fold_item_env;
+    bool user_mapped = false;
     if (standalone) {
         launch_rebuild(m, st);                       // [T]:342-359
     } else {
-        if (m.e_in_csc) crc |= launch_permute(m, false, nullptr, st);   // (single GPU, or first use; multi-GPU sweeps do it at their end)
-        launch_stats(m, st);
+        if (m.e_in_csc) {
+            if (fold_user && ensure_perm_inverse(m, st)) user_mapped = true;
+            else crc |= launch_permute(m, false, nullptr, st);   // (single GPU, or first use; multi-GPU sweeps do it at their end)
+        }
+        launch_stats(m, st, user_mapped);
     }
     crc |= launch_reduce_pair(m, st);                // sum e, sum e^2 (all ranks)
     if (timing) cudaEventRecord(m.ev_t[1], st);
@@ -380,12 +394,12 @@ static int enqueue_sweep(Model& m, bool timing)
     // peer-mapped replicas: the user phase writes U rows into every replica, so every rank must be done reading U first
     if (m.peer_ok) crc |= launch_barrier(m, st);
     if (timing) cudaEventRecord(m.ev_t[2], st);
-    launch_phase(m, m.us, m.it, true, fused);        // [T]:514-558 (+ the fused residual refresh)
+    launch_phase(m, m.us, m.it, true, fused, user_mapped ? m.it.e : nullptr, user_mapped ? m.perm_inv : nullptr);   // [T]:514-558 (+ the fused residual refresh)
     if (timing) cudaEventRecord(m.ev_t[3], st);
     // residual CSR order -> CSC order; multi-GPU: all-to-all grouped with the all-gather of the updated U rows and user biases
-    crc |= launch_permute(m, true, &m.us, st);
+    if (!fold) crc |= launch_permute(m, true, &m.us, st);
     if (timing) cudaEventRecord(m.ev_t[4], st);
-    launch_phase(m, m.it, m.us, false, false);       // [T]:563-606
+    launch_phase(m, m.it, m.us, false, false, fold ? m.us.e : nullptr, fold ? m.perm : nullptr);       // [T]:563-606
     m.e_in_csc = true;
     if (timing) cudaEventRecord(m.ev_t[5], st);
     if (m.world > 1) {

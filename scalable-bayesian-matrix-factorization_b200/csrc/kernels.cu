@@ -55,7 +55,17 @@ struct PhaseArgs {
     const float* bias_other;  // [n_other + 1] opposite-side biases (pad row -> 0 is never read)
     float* pacc;              // [slots] partial predictions carried between launches / streaming passes
     int KBtot;                // total number of blocks (to know the last one)
+    // Residual hand-over between the phases, folded into the first touch: when e_map is set, the current residual of slot s
+    // is e_src[e_map[s]] (it lives in the OTHER side's slot order; e_map = perm or its inverse) and e[] is write-only until
+    // this phase has stored it.  Replaces the stand-alone permutation pass between the phases on one GPU.
+    const float* e_src;
+    const uint32_t* e_map;
 };
+
+__device__ __forceinline__ float load_e_first(const PhaseArgs& a, int64_t slot)
+{
+    return a.e_map ? __ldg(a.e_src + a.e_map[slot]) : a.e[slot];
+}
 
 __host__ __device__ constexpr int gi(int k, int l) { return 8 + k * 8 - (k * (k - 1)) / 2 + (l - k); }   // k <= l
 
@@ -221,7 +231,7 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         const int p = r * TPR + t_in_row;
         const bool valid = p < c;
         id[r] = valid ? a.idx[beg + p] : pad_row;
-        e[r] = valid ? a.e[beg + p] : 0.f;
+        e[r] = valid ? load_e_first(a, beg + p) : 0.f;
         if (REFRESH) pr[r] = (valid && b_begin > 0) ? a.pacc[beg + p] : 0.f;
     }
     float bias_new = 0.f;
@@ -433,7 +443,7 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
         const int p = r * G + lg;
         const bool valid = p < c;
         id[r] = valid ? a.idx[beg + p] : pad_row;
-        e[r] = valid ? a.e[beg + p] : 0.f;
+        e[r] = valid ? load_e_first(a, beg + p) : 0.f;
         if (REFRESH) pr[r] = (valid && b_begin > 0) ? a.pacc[beg + p] : 0.f;
     }
     float bias_new = 0.f;
@@ -591,7 +601,7 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
             const uint32_t i = base + u * THREADS;
             const bool ok = i < sl.len;
             id[u] = ok ? idx[i] : pad_row;
-            e[u] = ok ? ep[i] : 0.f;
+            e[u] = ok ? ((PREV == 0) ? load_e_first(a, (int64_t)sl.start + i) : ep[i]) : 0.f;
             if (REFRESH && PREV == 2) pr[u] = (ok && pb > 0) ? pp[i] : 0.f;
         }
         f8 fp[PREV == 2 ? UNR : 1], fc[CUR == 2 ? UNR : 1];
@@ -1101,9 +1111,9 @@ void launch_rebuild(Model& m, cudaStream_t st)
     m.launches++;
 }
 
-void launch_stats(Model& m, cudaStream_t st)
+void launch_stats(Model& m, cudaStream_t st, bool from_csc)
 {
-    stats_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.us.e, m.n_csr, m.red_part);
+    stats_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(from_csc ? m.it.e : m.us.e, from_csc ? m.n_csc : m.n_csr, m.red_part);
     m.launches++;
 }
 
@@ -1174,9 +1184,11 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
 }
 
 // One half-sweep: bias then all factor blocks of every row of `self` ([T]:514-558 users / 563-606 items).
-void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh)
+void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh, const float* e_src, const uint32_t* e_map)
 {
     PhaseArgs a;
+    a.e_src = e_src;   // first touch of e (block 0 launches, first streaming pass) reads through the map, see PhaseArgs
+    a.e_map = e_map;
     a.r = m.csr_r;              // only the user phase refreshes (refresh == false on the item side)
     a.bias_other = other.bias;
     a.pacc = m.pacc;
@@ -1229,6 +1241,7 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     for (int b0 = 0; b0 < KB; b0 += nb) {
         const int b1 = (b0 + nb < KB) ? b0 + nb : KB;
         const int do_bias = (b0 == 0 && with_bias) ? 1 : 0;
+        if (b0 > 0) a.e_map = nullptr;   // later launches continue from e[] as stored by the first
         launch_bin<11>(m, a, self, b0, b1, do_bias, refresh, sb[0]);   // longest rows first
         launch_bin<10>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
         launch_bin<9>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
@@ -1242,6 +1255,7 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         launch_bin<1>(m, a, self, b0, b1, do_bias, refresh, sb[1]);
         launch_bin<0>(m, a, self, b0, b1, do_bias, refresh, sb[2]);
     }
+    a.e_map = e_map;   // (only the PREV == 0 streaming pass looks at it)
     cudaEventRecord(m.ev_join_res[0], sb[1]);
     cudaEventRecord(m.ev_join_res[1], sb[2]);
     cudaStreamWaitEvent(sr, m.ev_join_res[0], 0);
@@ -1312,6 +1326,8 @@ static bool ensure_inverse(Model& m, const uint32_t* perm, uint32_t** inv, uint6
     invert_perm_kernel<<<grid_for(n, 256, m.sm_count * 16), 256, 0, st>>>(perm, *inv, n);
     return true;
 }
+
+bool ensure_perm_inverse(Model& m, cudaStream_t st) { return ensure_inverse(m, m.perm, &m.perm_inv, m.N, st); }
 
 int launch_permute(Model& m, bool csr_to_csc, Side* gather_side, cudaStream_t st)
 {

@@ -163,11 +163,14 @@ void launch_init_factors(Model& m, Side& s, uint32_t site, cudaStream_t st);
 void launch_load_factors(Model& m, Side& s, const float* d_src, bool dim_major, cudaStream_t st);
 void launch_export_factors(Model& m, const Side& s, float* d_out, bool dim_major, cudaStream_t st);
 void launch_rebuild(Model& m, cudaStream_t st);          // [T]:342-359 into the CSR-order residual + partial stats
-void launch_stats(Model& m, cudaStream_t st);            // partial stats of the existing CSR-order residual
+void launch_stats(Model& m, cudaStream_t st, bool from_csc = false);   // partial stats of the existing residual (either slot order: same multiset)
 void launch_global_hypers(Model& m, cudaStream_t st);    // [T]:366-410 (final reduce of the stats + 4 scalar draws)
 void launch_dim_hypers(Model& m, cudaStream_t st);       // [T]:415-467
 void launch_bias_hypers(Model& m, cudaStream_t st);      // [T]:469-511
-void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh);   // [T]:514-558 / 563-606
+// [T]:514-558 / 563-606; e_map != nullptr: the residual is taken over from e_src[e_map[slot]] (the other side's slot order)
+void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh, const float* e_src = nullptr,
+                  const uint32_t* e_map = nullptr);
+bool ensure_perm_inverse(Model& m, cudaStream_t st);    // perm_inv (CSR slot -> CSC slot), built on first use; false: no memory
 // one GPU: gather through perm.  G GPUs: all-to-all over NVLink, grouped with the all-gather of gather_side's updated rows (may be null)
 int launch_permute(Model& m, bool csr_to_csc, Side* gather_side, cudaStream_t st);
 int setup_peer_access(Model& m);                                  // storage.cu: exchange IPC handles, map the peers' buffers

@@ -96,6 +96,10 @@ def load_library(path=None):
     lib.sbmf_cuda_plan_exchange.argtypes = [C.c_uint64, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
     lib.sbmf_cuda_synth_generate.argtypes = [P(SynthSpec), P(C.c_uint64), P(C.c_uint64)] + [C.c_void_p] * 6
     lib.sbmf_cuda_synth_last_error.restype = C.c_char_p
+    lib.sbmf_cuda_synth_host_generate.argtypes = [P(SynthSpec), C.c_int, P(C.c_uint64), P(C.c_uint64)] + [P(C.c_void_p)] * 6
+    lib.sbmf_cuda_synth_host_free.argtypes = [C.c_void_p]
+    lib.sbmf_cuda_synth_host_free.restype = None
+    lib.sbmf_cuda_synth_host_last_error.restype = C.c_char_p
     if path is None:
         _lib = lib
     return lib
@@ -292,6 +296,28 @@ def synth_generate(num_users, num_items, n_ratings, s_user=0.8, s_item=1.0, test
                                       ("train_user", "train_item", "train_rating", "test_user", "test_item", "test_rating")])
     if rc != 0:
         raise SbmfError(rc, lib.sbmf_cuda_synth_last_error().decode())
+    out["num_users"], out["num_items"] = num_users, num_items
+    return out
+
+
+def synth_generate_host(num_users, num_items, n_ratings, s_user=0.8, s_item=1.0, test_frac=0.1, seed=20151001, threads=0):
+    """Sparse host-side sampler of the same matrix family (csrc/synth_host.cpp), for shapes whose pair grid is too large
+    for synth_generate (10M x 1M).  Returns dict of numpy arrays over the library's buffers (freed with the arrays)."""
+    import weakref
+    lib = load_library()
+    spec = SynthSpec(num_users, num_items, n_ratings, s_user, s_item, test_frac, seed, 0, 0)
+    ntr, nte = C.c_uint64(), C.c_uint64()
+    ptrs = [C.c_void_p() for _ in range(6)]
+    rc = lib.sbmf_cuda_synth_host_generate(C.byref(spec), int(threads), C.byref(ntr), C.byref(nte), *[C.byref(p) for p in ptrs])
+    if rc != 0:
+        raise SbmfError(rc, lib.sbmf_cuda_synth_host_last_error().decode())
+    out = {}
+    names = ("train_user", "train_item", "train_rating", "test_user", "test_item", "test_rating")
+    for k, p in zip(names, ptrs):
+        n = ntr.value if k.startswith("train") else nte.value
+        buf = (C.c_char * (n * 4)).from_address(p.value)
+        out[k] = np.frombuffer(buf, dtype=np.float32 if k.endswith("rating") else np.uint32, count=n)
+        weakref.finalize(buf, lib.sbmf_cuda_synth_host_free, p)
     out["num_users"], out["num_items"] = num_users, num_items
     return out
 

@@ -122,3 +122,37 @@ def test_two_process_gloo_exchange(tmp_path, sbmf_mod):
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
     rcs = [p.wait(timeout=240) for p in procs]
     assert rcs == [0, 0], rcs
+
+
+# ------------------------------------------------------------------------------------------ sparse host workload generator
+def test_synth_host_generator_properties(sbmf_mod):
+    """csrc/synth_host.cpp (bench input for the 10M x 1M / 1B configuration): distinct pairs sorted by (user, item), the requested
+    number of ratings in expectation, Zipf-shaped marginals, test split ~ test_frac, half-star ratings in [0.5, 5], and the same
+    matrix whatever the number of host threads."""
+    sbmf = sbmf_mod
+    I, J, N = 20000, 3000, 600000
+    a = sbmf.synth_generate_host(I, J, N, seed=7, threads=1)
+    b = sbmf.synth_generate_host(I, J, N, seed=7, threads=4)
+    for k in ("train_user", "train_item", "train_rating", "test_user", "test_item", "test_rating"):
+        assert np.array_equal(a[k], b[k]), k
+    ntr, nte = a["train_user"].size, a["test_user"].size
+    assert abs(ntr + nte - N) < 5 * np.sqrt(N)
+    assert abs(nte / (ntr + nte) - 0.1) < 0.005
+    for p in ("train", "test"):
+        key = a[p + "_user"].astype(np.int64) * J + a[p + "_item"]
+        assert np.all(key[1:] > key[:-1])                      # sorted by (user, item), no duplicate pair
+        assert a[p + "_user"].max() < I and a[p + "_item"].max() < J
+        r = a[p + "_rating"]
+        assert r.min() >= 0.5 and r.max() <= 5.0 and np.all(r * 2 == np.round(r * 2))
+    assert np.intersect1d(a["train_user"].astype(np.int64) * J + a["train_item"], a["test_user"].astype(np.int64) * J + a["test_item"]).size == 0
+    # marginals: degree of the rank-r item ~ r^-1, of the rank-r user ~ r^-0.8 (both flattened at the top by p = min(1, .) and by
+    # sorting noisy degrees, hence the one-sided tolerances)
+    dj = np.sort(np.bincount(np.concatenate([a["train_item"], a["test_item"]]), minlength=J))[::-1].astype(np.float64)
+    du = np.sort(np.bincount(np.concatenate([a["train_user"], a["test_user"]]), minlength=I))[::-1].astype(np.float64)
+    sj = np.polyfit(np.log(np.arange(30, 1000) + 1.0), np.log(dj[30:1000]), 1)[0]
+    su = np.polyfit(np.log(np.arange(30, 5000) + 1.0), np.log(du[30:5000]), 1)[0]
+    assert -1.05 < sj < -0.85 and -0.85 < su < -0.6, (sj, su)
+    c = sbmf.synth_generate_host(I, J, N, seed=8, threads=4)
+    assert not np.array_equal(a["train_item"][:1000], c["train_item"][:1000])
+    with pytest.raises(sbmf.SbmfError):
+        sbmf.synth_generate_host(10, 10, 90)                    # denser than half of the pair grid

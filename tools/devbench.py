@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "scalable-bayesian-matrix-factorization_b2
 import sbmf  # noqa: E402
 
 SHAPES = {"ml1m": (6040, 3706, 1000209), "ml10m": (71567, 10681, 10000000), "ml20m": (138493, 26744, 20000000),
-          "netflix": (480189, 17770, 100480507)}
+          "netflix": (480189, 17770, 100480507), "1b": (10000000, 1000000, 1000000000)}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--shape", default="ml10m")
@@ -25,7 +25,10 @@ ap.add_argument("--s_item", type=float, default=1.0)
 a = ap.parse_args()
 I, J, N = SHAPES[a.shape]
 t0 = time.time()
-s = sbmf.synth_generate(I, J, N, s_user=a.s_user, s_item=a.s_item)
+if a.shape == "1b":   # 1e13 pairs: sparse host sampler (csrc/synth_host.cpp); N counts train + test here
+    s = sbmf.synth_generate_host(I, J, N, s_user=a.s_user, s_item=a.s_item)
+else:
+    s = sbmf.synth_generate(I, J, N, s_user=a.s_user, s_item=a.s_item)
 t1 = time.time()
 du = np.bincount(s["train_user"], minlength=I); di = np.bincount(s["train_item"], minlength=J)
 print(f"synth {a.shape}: train {s['train_user'].size} test {s['test_user'].size} in {t1 - t0:.1f}s; user deg max {du.max()} med {int(np.median(du))}"
