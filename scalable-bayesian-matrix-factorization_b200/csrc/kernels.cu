@@ -1233,9 +1233,13 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     if (heavy) cudaStreamWaitEvent(sh, m.ev_fork, 0);
     cudaStreamWaitEvent(sb[1], m.ev_fork, 0);
     cudaStreamWaitEvent(sb[2], m.ev_fork, 0);
-    // resident rows: as many blocks per launch as keep the gathered factor blocks L2-resident
+    // resident rows: several blocks per launch (e, idx and the row set-up are then touched once per launch, not once per
+    // block), bounded by the bytes of gathered factor blocks one launch has in flight.  Measured: a 48 MB bound (blocks
+    // strictly L2-resident) loses to 100-200 MB on both the Netflix-shaped matrix (item phase 10.94 -> 10.90 ms) and the
+    // 10M x 1M one (user phase 378 -> 271 ms); beyond ~200 MB it is flat.
     const size_t block_bytes = (size_t)other.n * 32;
-    int nb = (int)((size_t)(48u << 20) / (block_bytes ? block_bytes : 1));
+    static const size_t l2_budget = (size_t)(getenv("SBMF_L2_BUDGET_MB") ? atol(getenv("SBMF_L2_BUDGET_MB")) : 192) << 20;   // tuning knob
+    int nb = (int)(l2_budget / (block_bytes ? block_bytes : 1));
     if (nb < 1) nb = 1;
     if (nb > KB) nb = KB;
     for (int b0 = 0; b0 < KB; b0 += nb) {
