@@ -657,23 +657,33 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
     }
 }
 
+// One CTA of 8 warps per heavy row.  A row has up to several hundred slices (more on a multi-GPU shard, where slices are
+// shorter): warp w sums the partials of slices s0 + w, s0 + w + 8, ... (independent coalesced 192-byte reads), the eight
+// sums are combined in warp order -- a fixed tree, so results are reproducible -- and warp 0 performs the update(s).
+constexpr int HS_WARPS = 8;
 template <int CUR>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(HS_WARPS * 32)
 heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const uint32_t* __restrict__ slice_ptr, uint32_t n_heavy,
                    const float* __restrict__ hpart, float* __restrict__ hdelta, float* __restrict__ hbias_delta, int b)
 {
-    __shared__ __align__(16) float s_tot[4][NACC];
+    __shared__ __align__(16) float s_part[HS_WARPS][NACC];
+    __shared__ __align__(16) float s_tot[NACC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t hrow = blockIdx.x * 4 + warp;
-    if (hrow >= n_heavy) return;
+    const uint32_t hrow = blockIdx.x;
     const uint32_t row = heavy_rows[hrow];
     const uint32_t s0 = slice_ptr[hrow], s1 = slice_ptr[hrow + 1];
-    const float alpha = a.sc->alpha_f;
-    const uint32_t sweep = a.sc->sweep;
     if (CUR == 1) {
         float t = 0.f;
-        for (uint32_t s = s0 + lane; s < s1; s += 32) t += hpart[(size_t)s * NACC];
+        for (uint32_t s = s0 + threadIdx.x; s < s1; s += HS_WARPS * 32) t += hpart[(size_t)s * NACC];
         t = warp_sum(t);
+        if (lane == 0) s_part[warp][0] = t;
+        __syncthreads();
+        if (warp != 0) return;
+        t = 0.f;
+#pragma unroll
+        for (int w = 0; w < HS_WARPS; ++w) t += s_part[w][0];
+        const float alpha = a.sc->alpha_f;
+        const uint32_t sweep = a.sc->sweep;
         const float c = (float)(a.ptr[row + 1] - a.ptr[row]);
         const float bo = a.bias[row], sb = a.sigma_b[row], mb = a.mu_b[row];
         const float s = 1.0f / (sb + alpha * c);
@@ -686,15 +696,29 @@ heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const u
             hbias_delta[hrow] = bo - bn;
         }
     } else {
-        float zl = 0.f;
-        if (a.mode != SAMPLE_ZERO && lane < 8) zl = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)(b * 8 + lane), sweep));
         float a0 = 0.f, a1 = 0.f;
-        for (uint32_t s = s0; s < s1; ++s) {
+#pragma unroll 4
+        for (uint32_t s = s0 + warp; s < s1; s += HS_WARPS) {
             a0 += hpart[(size_t)s * NACC + lane];
             if (lane < NACC - 32) a1 += hpart[(size_t)s * NACC + 32 + lane];
         }
-        s_tot[warp][lane] = a0;
-        if (lane < NACC - 32) s_tot[warp][32 + lane] = a1;
+        s_part[warp][lane] = a0;
+        if (lane < NACC - 32) s_part[warp][32 + lane] = a1;
+        __syncthreads();
+        if (warp != 0) return;
+        const float alpha = a.sc->alpha_f;
+        const uint32_t sweep = a.sc->sweep;
+        float zl = 0.f;
+        if (a.mode != SAMPLE_ZERO && lane < 8) zl = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)(b * 8 + lane), sweep));
+        a0 = 0.f;
+        a1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < HS_WARPS; ++w) {
+            a0 += s_part[w][lane];
+            if (lane < NACC - 32) a1 += s_part[w][32 + lane];
+        }
+        s_tot[lane] = a0;
+        if (lane < NACC - 32) s_tot[32 + lane] = a1;
         __syncwarp();
         float z[8];
 #pragma unroll
@@ -703,7 +727,7 @@ heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const u
         const f8 uo = ld256(a.Fself + foff);
         f8 un;
         float d[8];
-        solve_block(s_tot[warp], uo, z, a.sigma_kf + b * 8, a.mu_kf + b * 8, alpha, a.mode, (int)a.K - b * 8, un, d);
+        solve_block(s_tot, uo, z, a.sigma_kf + b * 8, a.mu_kf + b * 8, alpha, a.mode, (int)a.K - b * 8, un, d);
         if (lane == 0) {
             for (int q = 0; q < a.nrep; ++q) st256(a.Frep[q] + foff, un);
 #pragma unroll
@@ -1266,7 +1290,7 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     cudaStreamWaitEvent(sr, m.ev_join_res[1], 0);
     if (heavy) {
         const uint32_t ns = self.n_slices, nh = self.n_heavy;
-        const uint32_t gs = (nh + 3) / 4;
+        const uint32_t gs = nh;   // one CTA per heavy row
         float* hbias = self.hdelta + (size_t)nh * 8;
     // 2 ratings per thread x 64 threads per slice CTA measured best on B200 (profiles/): small CTAs, ~20 warps per SM
 #define HEAVY_ACC(PREV, CUR, PB, B)                                                                                                              \
@@ -1276,12 +1300,12 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     } while (0)
         if (with_bias) {
             HEAVY_ACC(0, 1, 0, 0);
-            heavy_solve_kernel<1><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
+            heavy_solve_kernel<1><<<gs, HS_WARPS * 32, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
             HEAVY_ACC(1, 2, 0, 0);
         } else {
             HEAVY_ACC(0, 2, 0, 0);
         }
-        heavy_solve_kernel<2><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
+        heavy_solve_kernel<2><<<gs, HS_WARPS * 32, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
         const bool detail = m.timing_detail && !apply_shift;   // item phase only
         if (detail && m.ev_top.size() < (size_t)2 * KB) {
             while (m.ev_top.size() < (size_t)2 * KB) {
@@ -1295,7 +1319,7 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
             HEAVY_ACC(2, 2, b - 1, b);
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
-            heavy_solve_kernel<2><<<gs, 128, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, b);
+            heavy_solve_kernel<2><<<gs, HS_WARPS * 32, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, b);
         }
         HEAVY_ACC(2, 0, KB - 1, 0);
 #undef HEAVY_ACC
