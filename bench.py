@@ -338,6 +338,17 @@ def main():
         prof = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if os.path.exists(prof):
             roof["traffic"] = json.load(open(prof)).get("heavy_accumulate_kernel<2,2>", {}).get("dram_bytes_per_launch")
+        # the bound this kernel actually runs against: random 32-byte sector gathers from an L2-resident table, one LDG.E.256 per
+        # lane.  tools/gather_probe.cu measures that access form alone on B200: 0.88-0.90 sectors per clock per SM (8.2-8.3 TB/s).
+        try:
+            props_sms, sm_mhz = 148, 1965.0
+            sectors = 2.0 * t["top_kernel_ratings"]             # previous block (delta apply) + current block (accumulate) per rating
+            spc = sectors / (us * 1e-6) / (props_sms * sm_mhz * 1e6)
+            roof["gather_path"] = {"sectors_per_launch": sectors, "achieved_sectors_per_clk_per_sm": spc, "probe_peak_sectors_per_clk_per_sm": 0.90,
+                                   "frac": spc / 0.90, "assumes": f"{props_sms} SMs at {sm_mhz:.0f} MHz (see clocks)",
+                                   "source": "tools/gather_probe.cu (profiles/gather_probe_r1.txt)"}
+        except Exception:   # noqa: BLE001 - informational only
+            pass
     phases = {k: round(t[k] / max(t["sweeps"], 1), 3) for k in ("ms_rebuild", "ms_hypers", "ms_user_phase", "ms_exchange", "ms_item_phase", "ms_eval", "ms_allgather", "ms_total")}
     sweep_roof = {"algorithmic_bytes_per_sweep": ALG_BYTES_PER_FU * fu_per_sweep, "achieved_gbs_per_gpu": ALG_BYTES_PER_FU * value / 1e9 / world,
                   "frac_of_peak": ALG_BYTES_PER_FU * value / 1e9 / peak / world}

@@ -1346,7 +1346,8 @@ invert_perm_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ inv
 static bool ensure_inverse(Model& m, const uint32_t* perm, uint32_t** inv, uint64_t n, cudaStream_t st)
 {
     if (*inv) return true;
-    if (cudaMalloc((void**)inv, (n ? n : 1) * 4) != cudaSuccess) {
+    // one GPU: from the stream-ordered pool like the rest of the layout (storage.cu: palloc)
+    if ((m.world == 1 ? cudaMallocAsync((void**)inv, (n ? n : 1) * 4, st) : cudaMalloc((void**)inv, (n ? n : 1) * 4)) != cudaSuccess) {
         *inv = nullptr;
         cudaGetLastError();
         return false;   // fall back to the scatter form

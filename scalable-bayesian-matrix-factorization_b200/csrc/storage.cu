@@ -34,7 +34,29 @@ namespace sbmf {
 template <typename T>
 static cudaError_t dmalloc(T** p, size_t n)
 {
-    return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+    cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+    if (e == cudaErrorMemoryAllocation) {   // memory parked in the stream-ordered pool (see palloc) is given back before giving up
+        cudaGetLastError();
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+            e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+        }
+    }
+    return e;
+}
+
+// The rating-sized arrays of a single-GPU model come from the device's stream-ordered pool (release threshold raised in
+// sbmf_cuda_create): a second set_train in the same process then reuses the memory of the first instead of paying
+// cudaMalloc / cudaFree of several GB again (measured 25-110 ms and varying for the layout alone).  Multi-GPU models keep
+// cudaMalloc throughout: their buffers are exported through CUDA IPC, which pool memory does not support.
+template <class T>
+static cudaError_t palloc(const Model& m, T** p, size_t n, cudaStream_t st)
+{
+    if (m.world > 1) return dmalloc(p, n);
+    return cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), st);
 }
 
 __global__ void iota_kernel(uint32_t* v, uint64_t n)
@@ -210,6 +232,7 @@ void free_storage(Model& m)
         m.graph_exec = nullptr;
     }
     m.graph_failed = false;
+    cudaDeviceSynchronize();   // pool allocations are released with cudaFree below, which does not wait for work that still uses them
     if (m.world > 1 && m.comm.nccl && m.have_train) {
         // peers may still be writing into / reading from our buffers: meet them before anything is unmapped or freed
         cudaStreamSynchronize(m.s_main);
@@ -246,6 +269,7 @@ void free_test(Model& m)
         cudaGraphExecDestroy(m.graph_exec);
         m.graph_exec = nullptr;
     }
+    cudaDeviceSynchronize();   // see free_storage
     cudaFree(m.t_user); cudaFree(m.t_item); cudaFree(m.t_r); cudaFree(m.t_sum);
     m.t_user = m.t_item = nullptr; m.t_r = nullptr; m.t_sum = nullptr;
     m.have_test = false;
@@ -415,13 +439,14 @@ static int alloc_side_state(Model& m, Side& s)
     return SBMF_OK;
 }
 
-struct Trace {   // SBMF_TRACE=1: wall-clock of the set_train stages on stderr
+struct Trace {   // SBMF_TRACE=1: wall-clock of the set_train stages on stderr (=2: host time only, no device synchronisation)
     bool on = getenv("SBMF_TRACE") != nullptr;
+    bool sync = !(getenv("SBMF_TRACE") && getenv("SBMF_TRACE")[0] == '2');
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     void lap(const char* what)
     {
         if (!on) return;
-        cudaDeviceSynchronize();
+        if (sync) cudaDeviceSynchronize();
         const auto t1 = std::chrono::steady_clock::now();
         fprintf(stderr, "[sbmf trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
@@ -481,9 +506,10 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
         return SBMF_ERR_INVALID;
     }
 
-    CKC(dmalloc(&m.us.ptr, (size_t)num_users + 1)); CKC(dmalloc(&m.it.ptr, (size_t)num_items + 1));
-    CKC(dmalloc(&m.us.idx, n)); CKC(dmalloc(&m.it.idx, n)); CKC(dmalloc(&m.us.e, n)); CKC(dmalloc(&m.it.e, n));
-    CKC(dmalloc(&m.csr_urow, n)); CKC(dmalloc(&m.csr_r, n)); CKC(dmalloc(&m.csr_id, n)); CKC(dmalloc(&m.csc_id, n)); CKC(dmalloc(&m.perm, n));
+    CKC(palloc(m, &m.us.ptr, (size_t)num_users + 1, st)); CKC(palloc(m, &m.it.ptr, (size_t)num_items + 1, st));
+    CKC(palloc(m, &m.us.idx, n, st)); CKC(palloc(m, &m.it.idx, n, st)); CKC(palloc(m, &m.us.e, n, st)); CKC(palloc(m, &m.it.e, n, st));
+    CKC(palloc(m, &m.csr_urow, n, st)); CKC(palloc(m, &m.csr_r, n, st)); CKC(palloc(m, &m.csr_id, n, st)); CKC(palloc(m, &m.csc_id, n, st));
+    CKC(palloc(m, &m.perm, n, st));
 
     tr.lap("id check + alloc layout");
     size_t tmp_bytes = 0;
@@ -523,7 +549,7 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     m.red_blocks = (uint32_t)m.sm_count * 8;
     CK(dmalloc(&m.red_part, (size_t)m.red_blocks * 2));
     CK(dmalloc(&m.red2, 2));
-    CK(dmalloc(&m.pacc, m.n_csr));
+    CK(palloc(m, &m.pacc, m.n_csr, m.s_main));
     CK(dmalloc(&m.bar, 1));
     CK(cudaMemset(m.bar, 0, 8));
     if (m.world > 1 && (rc = setup_peer_access(m)) != SBMF_OK) return rc;
@@ -537,7 +563,8 @@ int build_test(Model& m, uint64_t nt, const uint32_t* user, const uint32_t* item
 {
     free_test(m);
     m.Nt = nt;
-    CK(dmalloc(&m.t_user, nt)); CK(dmalloc(&m.t_item, nt)); CK(dmalloc(&m.t_r, nt)); CK(dmalloc(&m.t_sum, nt));
+    CK(palloc(m, &m.t_user, nt, m.s_main)); CK(palloc(m, &m.t_item, nt, m.s_main)); CK(palloc(m, &m.t_r, nt, m.s_main));
+    CK(palloc(m, &m.t_sum, nt, m.s_main));
     if (nt) {
         CK(cudaMemcpyAsync(m.t_user, user, nt * 4, cudaMemcpyHostToDevice, m.s_main));
         CK(cudaMemcpyAsync(m.t_item, item, nt * 4, cudaMemcpyHostToDevice, m.s_main));

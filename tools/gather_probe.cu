@@ -138,6 +138,7 @@ int main(int argc, char** argv)
             run<1, 2>("1 sector/rating  unroll 2", table, idx, n_sectors, out, sms, ghz);
             run<1, 4>("1 sector/rating  unroll 4", table, idx, n_sectors, out, sms, ghz);
             run<1, 8>("1 sector/rating  unroll 8", table, idx, n_sectors, out, sms, ghz);
+            run<1, 4, 2>("1 sect, LDG.128x2, unr 4", table, idx, n_sectors, out, sms, ghz);
         } else if (span == 2) {
             run<2, 2, 2>("2 sect, LDG.128x2, unr 2", table, idx, n_sectors, out, sms, ghz);
             run<2, 4, 2>("2 sect, LDG.128x2, unr 4", table, idx, n_sectors, out, sms, ghz);
