@@ -657,11 +657,12 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
     }
 }
 
-// One CTA of 8 warps per heavy row.  A row has up to several hundred slices (more on a multi-GPU shard, where slices are
-// shorter): warp w sums the partials of slices s0 + w, s0 + w + 8, ... (independent coalesced 192-byte reads), the eight
+// One CTA of HS_WARPS warps per heavy row.  A row has up to several hundred slices (more on a multi-GPU shard, where slices
+// are shorter): warp w sums the partials of slices s0 + w, s0 + w + HS_WARPS, ... (independent coalesced 192-byte reads), the
 // sums are combined in warp order -- a fixed tree, so results are reproducible -- and warp 0 performs the update(s).
-constexpr int HS_WARPS = 8;
-template <int CUR>
+// HS_WARPS = 8 where rows average many slices, 2 otherwise (thousands of rows with a handful of slices: fewer idle warps);
+// the choice (launch_phase) depends only on the work lists, so it is the same every sweep.
+template <int CUR, int HS_WARPS>
 __global__ void __launch_bounds__(HS_WARPS * 32)
 heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const uint32_t* __restrict__ slice_ptr, uint32_t n_heavy,
                    const float* __restrict__ hpart, float* __restrict__ hdelta, float* __restrict__ hbias_delta, int b)
@@ -1298,14 +1299,20 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         if (refresh) heavy_accumulate_kernel<PREV, CUR, 2, 64, true><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);  \
         else heavy_accumulate_kernel<PREV, CUR, 2, 64, false><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);         \
     } while (0)
+        const bool wide_solve = ns >= 8u * nh;   // >= 8 slices per heavy row on average
+#define HEAVY_SOLVE(CUR, B)                                                                                                                       \
+    do {                                                                                                                                         \
+        if (wide_solve) heavy_solve_kernel<CUR, 8><<<gs, 256, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, B); \
+        else heavy_solve_kernel<CUR, 2><<<gs, 64, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, B);   \
+    } while (0)
         if (with_bias) {
             HEAVY_ACC(0, 1, 0, 0);
-            heavy_solve_kernel<1><<<gs, HS_WARPS * 32, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
+            HEAVY_SOLVE(1, 0);
             HEAVY_ACC(1, 2, 0, 0);
         } else {
             HEAVY_ACC(0, 2, 0, 0);
         }
-        heavy_solve_kernel<2><<<gs, HS_WARPS * 32, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, 0);
+        HEAVY_SOLVE(2, 0);
         const bool detail = m.timing_detail && !apply_shift;   // item phase only
         if (detail && m.ev_top.size() < (size_t)2 * KB) {
             while (m.ev_top.size() < (size_t)2 * KB) {
@@ -1319,10 +1326,11 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
             HEAVY_ACC(2, 2, b - 1, b);
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
-            heavy_solve_kernel<2><<<gs, HS_WARPS * 32, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, b);
+            HEAVY_SOLVE(2, b);
         }
         HEAVY_ACC(2, 0, KB - 1, 0);
 #undef HEAVY_ACC
+#undef HEAVY_SOLVE
         m.launches += 2 * KB + 3;
         cudaEventRecord(m.ev_join, sh);
         cudaStreamWaitEvent(sr, m.ev_join, 0);
