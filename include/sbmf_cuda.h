@@ -185,6 +185,39 @@ int sbmf_cuda_get_rmse_history(sbmf_handle* h, uint32_t first, uint32_t count, d
 /* Posterior-mean (clamped) prediction per test pair = sum/(sweeps - burn_in), libFM's -out content. */
 int sbmf_cuda_get_pred(sbmf_handle* h, float* pred);
 
+/* ---- checkpoint / resume ---------------------------------------------------------------------------
+   [T] has none (DVector/DMatrix::save/load exist in matrix.h:130-207, 268-328 but [T] never calls them).
+   The complete sampler state at a sweep boundary is what sbmf_cuda_get_state returns plus the running prediction sums
+   of [T]:145, 629; every draw is a pure function of (seed, site, row, k, sweep), so a chain restored with set_state +
+   set_pred_sum continues exactly as the uninterrupted one would have. */
+/* After set_train (+ set_test): replaces init_factors.  in->U and in->V are required; NULL bias / hyper arrays mean zeros
+   (the state [T]:268-281 starts from).  in->sweeps_done becomes the sweep counter (and the Philox counter).  in->E
+   (rating order, as written by get_state) restores the residual; NULL => the next sweep rebuilds it stand-alone like
+   sweep 0 ([T]:342-359).  Multi-GPU: every rank passes the same factors / biases / hypers and its own E.  The RMSE
+   history of the sweeps before the restore point reads 0.  Also zeroes the prediction sums: call set_pred_sum AFTER it. */
+int sbmf_cuda_set_state(sbmf_handle* h, const sbmf_state* in);
+/* running sums of the clamped test predictions over the collected sweeps, [n_test] doubles ([T]:629).  Multi-GPU: get
+   is collective (every rank holds the sums of its slice of the test set), set takes the full array on every rank. */
+int sbmf_cuda_get_pred_sum(sbmf_handle* h, double* sum);
+int sbmf_cuda_set_pred_sum(sbmf_handle* h, const double* sum);
+
+/* Checkpoint files (pure host code, csrc/checkpoint.cpp): a 96-byte little-endian header (magic "SBMFCKP1", the
+   dimensions below) followed by the arrays of sbmf_state in declaration order, then pred_sum; absent arrays have their
+   bit in `present` cleared.  write: NULL members of st / NULL pred_sum are recorded as absent.  read_dims: header only.
+   read: st's non-NULL members must be caller-allocated for the dimensions of the file; members absent from the file
+   are reported by clearing the pointer in st (and *pred_sum_present = 0). */
+typedef struct sbmf_checkpoint_dims {
+    uint32_t num_users, num_items, K;
+    int32_t hyper_mode;
+    uint64_t n_train, n_test;
+    uint32_t sweeps_done;
+    uint32_t present;            /* bit i = i-th pointer member of sbmf_state (U = bit 0 ... E = bit 12), bit 13 = pred_sum */
+} sbmf_checkpoint_dims;
+int sbmf_cuda_checkpoint_write(const char* path, const sbmf_checkpoint_dims* dims, const sbmf_state* st, const double* pred_sum);
+int sbmf_cuda_checkpoint_read_dims(const char* path, sbmf_checkpoint_dims* dims);
+int sbmf_cuda_checkpoint_read(const char* path, sbmf_state* st, double* pred_sum, int* pred_sum_present);
+const char* sbmf_cuda_checkpoint_last_error(void);
+
 /* ---- instrumentation -------------------------------------------------------------------------------- */
 int sbmf_cuda_get_timing(sbmf_handle* h, sbmf_timing* out);
 int sbmf_cuda_reset_timing(sbmf_handle* h);

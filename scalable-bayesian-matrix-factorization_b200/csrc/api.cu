@@ -349,6 +349,7 @@ int sbmf_cuda_init_factors(sbmf_handle* h, const float* U0, const float* V0)
     API_CK(cudaStreamSynchronize(st));
     m.sweeps_done = 0;
     m.e_in_csc = false;
+    m.need_rebuild = false;
     m.have_factors = true;
     return SBMF_OK;
 }
@@ -362,7 +363,8 @@ static int enqueue_sweep(Model& m, bool timing)
     // sweep come from the incrementally updated residual of the previous one; residual_mode 1: the stand-alone rebuild kernel
     // at the start of the sweep, literally as in [T].  Sweep 0 always rebuilds stand-alone (nothing to update yet).
     const bool due = (m.sweeps_done % m.cfg.rebuild_every) == 0;
-    const bool standalone = due && (m.sweeps_done == 0 || m.cfg.residual_mode == 1);
+    // need_rebuild: state restored without a residual (sbmf_cuda_set_state with E == NULL) -- there is nothing to update yet
+    const bool standalone = m.need_rebuild || (due && (m.sweeps_done == 0 || m.cfg.residual_mode == 1));
     const bool fused = due && !standalone;
     if (timing) cudaEventRecord(m.ev_t[0], st);
     int crc = 0;
@@ -433,7 +435,7 @@ struct SweepKey {   // everything host-side that shapes the launch sequence of a
 static SweepKey sweep_key(const Model& m)
 {
     const bool due = (m.sweeps_done % m.cfg.rebuild_every) == 0;
-    const bool standalone = due && (m.sweeps_done == 0 || m.cfg.residual_mode == 1);
+    const bool standalone = m.need_rebuild || (due && (m.sweeps_done == 0 || m.cfg.residual_mode == 1));
     const bool next_standalone = ((m.sweeps_done + 1) % m.cfg.rebuild_every) == 0 && m.cfg.residual_mode == 1;
     return SweepKey{standalone, due && !standalone, next_standalone, m.e_in_csc};
 }
@@ -445,7 +447,7 @@ static int graph_sweep(Model& m, bool& done)
 {
     done = false;
     static const bool disabled = getenv("SBMF_NO_GRAPH") != nullptr;
-    if (disabled || m.timing_enabled || m.sweeps_done < 2) return SBMF_OK;
+    if (disabled || m.timing_enabled || m.sweeps_done < 2 || m.need_rebuild) return SBMF_OK;
     const SweepKey key = sweep_key(m);
     if (m.graph_exec && !(key == SweepKey{m.gk[0], m.gk[1], m.gk[2], m.gk[3]})) {
         cudaGraphExecDestroy(m.graph_exec);
@@ -495,6 +497,7 @@ static int one_sweep(Model& m)
     const bool timing = m.timing_enabled;
     grc = enqueue_sweep(m, timing);
     if (grc != SBMF_OK) return grc;
+    m.need_rebuild = false;
     m.sweeps_done++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -722,6 +725,123 @@ int sbmf_cuda_get_state(sbmf_handle* h, sbmf_state* out)
     out->sum_e = sc.sum_e;
     out->sum_e2 = sc.sum_e2;
     out->sweeps_done = m.sweeps_done;
+    return SBMF_OK;
+}
+
+// Restore of the complete sampler state at a sweep boundary (checkpoint / resume; the reference has none).
+// Built on init_factors (factor upload + the zero state of [T]:268-281, 315-318), then every array the caller provides
+// overwrites its zero.  Per-sweep scratch (shift_f, pacc, heavy-row partials, post_var) is recomputed by the next sweep.
+int sbmf_cuda_set_state(sbmf_handle* h, const sbmf_state* in)
+{
+    if (!h || !in) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (!m.have_train) {
+        m.err = "set_state: call set_train first";
+        return SBMF_ERR_STATE;
+    }
+    if (!in->U || !in->V) {
+        m.err = "set_state: U and V are required";
+        return SBMF_ERR_INVALID;
+    }
+    const int rc = sbmf_cuda_init_factors(h, in->U, in->V);
+    if (rc != SBMF_OK) return rc;
+    cudaStream_t st = m.s_main;
+    struct Up {
+        void* dst;
+        const void* src;
+        size_t bytes;
+    };
+    const Up ups[] = {{m.us.bias, in->b_i, (size_t)m.I * 4},    {m.it.bias, in->b_j, (size_t)m.J * 4},
+                      {m.us.mu_b, in->mu_b_i, (size_t)m.I * 4}, {m.us.sigma_b, in->sigma_b_i, (size_t)m.I * 4},
+                      {m.it.mu_b, in->mu_b_j, (size_t)m.J * 4}, {m.it.sigma_b, in->sigma_b_j, (size_t)m.J * 4}};
+    for (const Up& u : ups)
+        if (u.src) API_CK(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, st));
+    // per-dimension hyper-parameters: fp64 masters (the next sweep's Gamma step needs the OLD means, [T]:424, 450) and the fp32
+    // mirrors the row kernels read; padding dimensions K..KP-1 get the values dim_hyper_final_kernel gives them (1, 0)
+    std::vector<double> hd[4];
+    std::vector<float> hf[4];
+    {
+        const double* src[4] = {in->sigma_u, in->mu_u, in->sigma_v, in->mu_v};
+        double* dstd[4] = {m.us.sigma_k, m.us.mu_k, m.it.sigma_k, m.it.mu_k};
+        float* dstf[4] = {m.us.sigma_kf, m.us.mu_kf, m.it.sigma_kf, m.it.mu_kf};
+        for (int a = 0; a < 4; ++a) {
+            if (!src[a]) continue;
+            const double padv = (a % 2 == 0) ? 1.0 : 0.0;
+            hd[a].assign(m.KP, padv);
+            hf[a].assign(m.KP, (float)padv);
+            for (uint32_t k = 0; k < m.K; ++k) {
+                hd[a][k] = src[a][k];
+                hf[a][k] = (float)src[a][k];
+            }
+            API_CK(cudaMemcpyAsync(dstd[a], hd[a].data(), (size_t)m.KP * 8, cudaMemcpyHostToDevice, st));
+            API_CK(cudaMemcpyAsync(dstf[a], hf[a].data(), (size_t)m.KP * 4, cudaMemcpyHostToDevice, st));
+        }
+    }
+    Scalars sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.b_0 = in->b_0;
+    sc.alpha = in->alpha;
+    sc.mu_b_0 = in->mu_b_0;
+    sc.sigma_b_0 = in->sigma_b_0;
+    sc.sum_e = in->sum_e;
+    sc.sum_e2 = in->sum_e2;
+    sc.alpha_f = (float)in->alpha;
+    sc.b_0_f = (float)in->b_0;
+    sc.sweep = in->sweeps_done;
+    API_CK(cudaMemcpyAsync(m.sc, &sc, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    std::vector<float> e;
+    if (in->E) {
+        // the residual goes back where the uninterrupted chain keeps it at a sweep boundary: the item side's (CSC) order on one
+        // GPU, the user side's (CSR) order on several (enqueue_sweep), so the next sweep's statistics sum it in the same order
+        const bool to_csc = (m.world == 1);
+        const uint64_t nl = to_csc ? m.n_csc : m.n_csr;
+        std::vector<uint32_t> id(nl ? nl : 1);
+        e.resize(nl ? nl : 1);
+        API_CK(cudaMemcpyAsync(id.data(), to_csc ? m.csc_id : m.csr_id, nl * 4, cudaMemcpyDeviceToHost, st));
+        API_CK(cudaStreamSynchronize(st));
+        for (uint64_t s = 0; s < nl; ++s) e[s] = in->E[id[s]];
+        API_CK(cudaMemcpyAsync(to_csc ? m.it.e : m.us.e, e.data(), nl * 4, cudaMemcpyHostToDevice, st));
+        m.e_in_csc = to_csc;
+    }
+    API_CK(cudaStreamSynchronize(st));
+    m.need_rebuild = !in->E && in->sweeps_done > 0;
+    m.sweeps_done = in->sweeps_done;
+    return SBMF_OK;
+}
+
+int sbmf_cuda_get_pred_sum(sbmf_handle* h, double* sum)
+{
+    if (!h || !sum) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (!m.have_test) {
+        m.err = "get_pred_sum: no test set";
+        return SBMF_ERR_STATE;
+    }
+    API_CK(cudaSetDevice(m.device));
+    if (m.world > 1) {   // every rank accumulated its own slice of the test set
+        std::vector<size_t> off(m.world), cnt(m.world);
+        for (int q = 0; q < m.world; ++q) {
+            off[q] = m.Nt * (uint64_t)q / (uint64_t)m.world;
+            cnt[q] = m.Nt * (uint64_t)(q + 1) / (uint64_t)m.world - off[q];
+        }
+        if (comm_allgatherv_f64(m.comm, m.t_sum, off.data(), cnt.data(), m.s_main, m.err) != 0) return SBMF_ERR_NCCL;
+    }
+    API_CK(cudaMemcpyAsync(sum, m.t_sum, m.Nt * 8, cudaMemcpyDeviceToHost, m.s_main));
+    API_CK(cudaStreamSynchronize(m.s_main));
+    return SBMF_OK;
+}
+
+int sbmf_cuda_set_pred_sum(sbmf_handle* h, const double* sum)
+{
+    if (!h || !sum) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    if (!m.have_test) {
+        m.err = "set_pred_sum: no test set";
+        return SBMF_ERR_STATE;
+    }
+    API_CK(cudaSetDevice(m.device));
+    API_CK(cudaMemcpyAsync(m.t_sum, sum, m.Nt * 8, cudaMemcpyHostToDevice, m.s_main));
+    API_CK(cudaStreamSynchronize(m.s_main));
     return SBMF_OK;
 }
 

@@ -249,6 +249,8 @@ int main(int argc, char** argv)
         const std::string p_dev = cmd.reg("device", "CUDA device ordinal; default=0");
         const std::string p_off = cmd.reg("item_offset", "libFM text/binary input: item id = item feature id - offset; default=auto");
         const std::string p_dump = cmd.reg("dump_triples", "write the parsed training triples (user item rating) to this file");
+        const std::string p_save = cmd.reg("save_state", "write a checkpoint (factors, biases, hyper-parameters, residual, prediction sums) to this file after the last sweep");
+        const std::string p_load = cmd.reg("load_state", "continue the chain from this checkpoint instead of initialising; -iter = number of further sweeps");
         const std::string p_dry = cmd.reg("dry_run", "1 = parse the inputs, print the header lines and stop (no GPU needed)");
         if (cmd.has(p_help)) {
             cmd.print_help();
@@ -324,7 +326,37 @@ int main(int argc, char** argv)
         if (sbmf_cuda_create(&cfg, &h) != SBMF_OK) throw std::string("sbmf_cuda_create: ") + sbmf_cuda_last_error(NULL);
         ck(sbmf_cuda_set_train(h, tr.user.size(), tr.user.data(), tr.item.data(), tr.rating.data(), num_users, num_items), h, "set_train");
         ck(sbmf_cuda_set_test(h, te.user.size(), te.user.data(), te.item.data(), te.rating.data()), h, "set_test");
-        ck(sbmf_cuda_init_factors(h, NULL, NULL), h, "init_factors");
+        // state arrays of a checkpoint (sbmf_state members point into these)
+        const size_t nI = num_users, nJ = num_items, nN = tr.user.size(), nT = te.user.size();
+        std::vector<float> cU, cV, cbi, cbj, cmbi, csbi, cmbj, csbj, cE;
+        std::vector<double> csu, cmu, csv, cmv, cps;
+        auto bind_state = [&](sbmf_state& st) {
+            cU.resize(nI * K); cV.resize((size_t)K * nJ); cbi.resize(nI); cbj.resize(nJ); cmbi.resize(nI); csbi.resize(nI);
+            cmbj.resize(nJ); csbj.resize(nJ); cE.resize(nN ? nN : 1); csu.resize(K); cmu.resize(K); csv.resize(K); cmv.resize(K);
+            cps.resize(nT ? nT : 1);
+            memset(&st, 0, sizeof(st));
+            st.U = cU.data(); st.V = cV.data(); st.b_i = cbi.data(); st.b_j = cbj.data(); st.mu_b_i = cmbi.data();
+            st.sigma_b_i = csbi.data(); st.mu_b_j = cmbj.data(); st.sigma_b_j = csbj.data(); st.sigma_u = csu.data();
+            st.mu_u = cmu.data(); st.sigma_v = csv.data(); st.mu_v = cmv.data(); st.E = cE.data();
+        };
+        uint32_t first_iter = 0;
+        if (cmd.has(p_load)) {
+            const std::string path = cmd.get(p_load, "");
+            sbmf_checkpoint_dims cd;
+            if (sbmf_cuda_checkpoint_read_dims(path.c_str(), &cd) != SBMF_OK) throw std::string(sbmf_cuda_checkpoint_last_error());
+            if (cd.num_users != num_users || cd.num_items != num_items || cd.K != K || cd.n_train != nN || cd.n_test != nT ||
+                cd.hyper_mode != cfg.hyper_mode)
+                throw path + ": checkpoint was written for another problem (users/items/K/ratings/-hyper differ)";
+            sbmf_state st;
+            bind_state(st);
+            int have_ps = 0;
+            if (sbmf_cuda_checkpoint_read(path.c_str(), &st, cps.data(), &have_ps) != SBMF_OK) throw std::string(sbmf_cuda_checkpoint_last_error());
+            ck(sbmf_cuda_set_state(h, &st), h, "set_state");
+            if (have_ps) ck(sbmf_cuda_set_pred_sum(h, cps.data()), h, "set_pred_sum");
+            first_iter = st.sweeps_done;
+        } else {
+            ck(sbmf_cuda_init_factors(h, NULL, NULL), h, "init_factors");
+        }
         ck(sbmf_cuda_set_timing_enabled(h, 0), h, "set_timing_enabled");
 
         std::ofstream rlog;
@@ -341,7 +373,7 @@ int main(int argc, char** argv)
             if (!file_rmse.is_open()) throw std::string("unable to open test_rmse_*_mcmc in the current directory");
         }
         const int verbosity = (int)cmd.geti(p_verb, 0);
-        for (uint32_t iter = 0; iter < T; ++iter) {
+        for (uint32_t iter = first_iter; iter < first_iter + T; ++iter) {
             const auto t0 = std::chrono::steady_clock::now();
             double rmse = 0.0, rmse_sweep = 0.0;
             ck(sbmf_cuda_sweep(h, 1), h, "sweep");
@@ -367,10 +399,22 @@ int main(int argc, char** argv)
         }
         if (cmd.has(p_out)) {
             std::vector<float> pred(te.user.size());
-            if (T > cfg.burn_in) ck(sbmf_cuda_get_pred(h, pred.data()), h, "get_pred");
+            if (first_iter + T > cfg.burn_in) ck(sbmf_cuda_get_pred(h, pred.data()), h, "get_pred");
             std::ofstream o(cmd.get(p_out, "").c_str());
             if (!o.is_open()) throw "unable to open " + cmd.get(p_out, "");
             for (float v : pred) o << (double)v << std::endl;                               // DVector::save, matrix.h:268-277
+        }
+        if (cmd.has(p_save)) {
+            sbmf_state st;
+            bind_state(st);
+            ck(sbmf_cuda_get_state(h, &st), h, "get_state");
+            ck(sbmf_cuda_get_pred_sum(h, cps.data()), h, "get_pred_sum");
+            sbmf_checkpoint_dims cd;
+            memset(&cd, 0, sizeof(cd));
+            cd.num_users = num_users; cd.num_items = num_items; cd.K = K; cd.hyper_mode = cfg.hyper_mode;
+            cd.n_train = nN; cd.n_test = nT;
+            if (sbmf_cuda_checkpoint_write(cmd.get(p_save, "").c_str(), &cd, &st, cps.data()) != SBMF_OK)
+                throw std::string(sbmf_cuda_checkpoint_last_error());
         }
         sbmf_cuda_destroy(h);
     } catch (std::string& e) {

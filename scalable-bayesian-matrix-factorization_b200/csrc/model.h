@@ -96,6 +96,7 @@ struct Model {
     uint32_t* perm = nullptr;         // [N] CSR slot of each CSC slot
     uint32_t *perm_inv = nullptr, *recv_pos_inv = nullptr, *send_idx_inv = nullptr;   // inverse maps for the reverse direction, built on first use
     bool e_in_csc = false;            // where the freshest residual lives
+    bool need_rebuild = false;        // set_state without a residual: the next sweep rebuilds it stand-alone, like sweep 0
     // multi-GPU: rank r owns users [ub[r], ub[r+1]) with their CSR slots and items [ib[r], ib[r+1]) with their
     // CSC slots; every slot array above is then the LOCAL shard, ptr[] is rebased to local slots, factors/biases are replicas
     Comm comm;

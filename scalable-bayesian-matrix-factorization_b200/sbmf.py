@@ -39,6 +39,15 @@ class State(C.Structure):
                 ("sum_e", C.c_double), ("sum_e2", C.c_double), ("sweeps_done", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
+class CheckpointDims(C.Structure):
+    _fields_ = [("num_users", C.c_uint32), ("num_items", C.c_uint32), ("K", C.c_uint32), ("hyper_mode", C.c_int32),
+                ("n_train", C.c_uint64), ("n_test", C.c_uint64), ("sweeps_done", C.c_uint32), ("present", C.c_uint32)]
+
+
+STATE_ARRAYS = ("U", "V", "b_i", "b_j", "mu_b_i", "sigma_b_i", "mu_b_j", "sigma_b_j", "sigma_u", "mu_u", "sigma_v", "mu_v", "E")
+STATE_SCALARS = ("b_0", "alpha", "mu_b_0", "sigma_b_0", "sum_e", "sum_e2", "sweeps_done")
+
+
 class Timing(C.Structure):
     _fields_ = [("ms_rebuild", C.c_double), ("ms_hypers", C.c_double), ("ms_user_phase", C.c_double), ("ms_exchange", C.c_double),
                 ("ms_item_phase", C.c_double), ("ms_eval", C.c_double), ("ms_total", C.c_double), ("sweeps", C.c_uint64),
@@ -81,6 +90,13 @@ def load_library(path=None):
     lib.sbmf_cuda_get_layout.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     lib.sbmf_cuda_init_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sbmf_cuda_get_state.argtypes = [C.c_void_p, P(State)]
+    lib.sbmf_cuda_set_state.argtypes = [C.c_void_p, P(State)]
+    lib.sbmf_cuda_get_pred_sum.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sbmf_cuda_set_pred_sum.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sbmf_cuda_checkpoint_write.argtypes = [C.c_char_p, P(CheckpointDims), P(State), C.c_void_p]
+    lib.sbmf_cuda_checkpoint_read_dims.argtypes = [C.c_char_p, P(CheckpointDims)]
+    lib.sbmf_cuda_checkpoint_read.argtypes = [C.c_char_p, P(State), C.c_void_p, P(C.c_int)]
+    lib.sbmf_cuda_checkpoint_last_error.restype = C.c_char_p
     lib.sbmf_cuda_sweep.argtypes = [C.c_void_p, C.c_uint32]
     lib.sbmf_cuda_eval.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double)]
     lib.sbmf_cuda_get_rmse_history.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -218,6 +234,21 @@ class SbmfModel:
             arr[k] = getattr(st, k)
         return arr
 
+    def set_state(self, arr):
+        """sbmf_cuda_set_state from a dict shaped like get_state()'s (missing / None arrays are passed as NULL)"""
+        st, keep = _state_struct(arr, self.I, self.J, self.K, self.N)
+        self._ck(self.lib.sbmf_cuda_set_state(self.h, C.byref(st)))
+
+    def get_pred_sum(self):
+        s = np.empty(self.Nt, np.float64)
+        self._ck(self.lib.sbmf_cuda_get_pred_sum(self.h, _ptr(s)))
+        return s
+
+    def set_pred_sum(self, s):
+        s = np.ascontiguousarray(s, np.float64)
+        assert s.shape == (self.Nt,)
+        self._ck(self.lib.sbmf_cuda_set_pred_sum(self.h, _ptr(s)))
+
     def timing(self):
         t = Timing()
         self._ck(self.lib.sbmf_cuda_get_timing(self.h, C.byref(t)))
@@ -237,6 +268,65 @@ class SbmfModel:
 
     def synchronize(self):
         self._ck(self.lib.sbmf_cuda_synchronize(self.h))
+
+
+def _state_shapes(I, J, K, N):
+    return {"U": ((I, K), np.float32), "V": ((K, J), np.float32), "b_i": ((I,), np.float32), "b_j": ((J,), np.float32),
+            "mu_b_i": ((I,), np.float32), "sigma_b_i": ((I,), np.float32), "mu_b_j": ((J,), np.float32),
+            "sigma_b_j": ((J,), np.float32), "sigma_u": ((K,), np.float64), "mu_u": ((K,), np.float64),
+            "sigma_v": ((K,), np.float64), "mu_v": ((K,), np.float64), "E": ((N,), np.float32)}
+
+
+def _state_struct(arr, I, J, K, N):
+    """sbmf_state over the arrays of a get_state()-shaped dict; returns (struct, list keeping the buffers alive)"""
+    st, keep = State(), []
+    for k, (shape, dt) in _state_shapes(I, J, K, N).items():
+        v = arr.get(k)
+        if v is None:
+            continue
+        v = np.ascontiguousarray(v, dt)
+        assert v.shape == shape, (k, v.shape, shape)
+        keep.append(v)
+        setattr(st, k, v.ctypes.data)
+    for k in STATE_SCALARS:
+        if k in arr:
+            setattr(st, k, arr[k])
+    return st, keep
+
+
+def checkpoint_write(path, arr, num_users, num_items, K, n_train, n_test, hyper_mode=0, pred_sum=None):
+    """sbmf_cuda_checkpoint_write: a get_state()-shaped dict (+ the running prediction sums) to a file; host only"""
+    lib = load_library()
+    st, keep = _state_struct(arr, num_users, num_items, K, n_train)
+    ps = None if pred_sum is None else np.ascontiguousarray(pred_sum, np.float64)
+    assert ps is None or ps.shape == (n_test,)
+    dims = CheckpointDims(num_users, num_items, K, hyper_mode, n_train, n_test, 0, 0)
+    rc = lib.sbmf_cuda_checkpoint_write(os.fsencode(path), C.byref(dims), C.byref(st), _ptr(ps))
+    if rc != 0:
+        raise SbmfError(rc, lib.sbmf_cuda_checkpoint_last_error().decode())
+
+
+def checkpoint_read(path):
+    """sbmf_cuda_checkpoint_read_dims + _read: returns (dims dict, get_state()-shaped dict, pred_sum or None); host only"""
+    lib = load_library()
+    dims = CheckpointDims()
+    rc = lib.sbmf_cuda_checkpoint_read_dims(os.fsencode(path), C.byref(dims))
+    if rc != 0:
+        raise SbmfError(rc, lib.sbmf_cuda_checkpoint_last_error().decode())
+    I, J, K, N, Nt = dims.num_users, dims.num_items, dims.K, dims.n_train, dims.n_test
+    arr = {k: np.empty(shape, dt) for k, (shape, dt) in _state_shapes(I, J, K, N).items() if (dims.present >> STATE_ARRAYS.index(k)) & 1}
+    st = State()
+    for k, v in arr.items():
+        setattr(st, k, v.ctypes.data)
+    ps = np.empty(Nt, np.float64) if (dims.present >> 13) & 1 else None
+    have = C.c_int(0)
+    rc = lib.sbmf_cuda_checkpoint_read(os.fsencode(path), C.byref(st), _ptr(ps), C.byref(have))
+    if rc != 0:
+        raise SbmfError(rc, lib.sbmf_cuda_checkpoint_last_error().decode())
+    for k in STATE_SCALARS:
+        arr[k] = getattr(st, k)
+    d = {k: getattr(dims, k) for k, _ in CheckpointDims._fields_}
+    return d, arr, (ps if have.value else None)
 
 
 def nccl_unique_id():

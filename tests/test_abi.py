@@ -50,13 +50,14 @@ def test_ctypes_struct_layout_matches_header(built, tmp_path):
     sys.path.insert(0, PKG)
     import sbmf
     c = tmp_path / "sz.c"
-    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sbmf_cuda.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(sbmf_config),'
-                 ' sizeof(sbmf_priors), sizeof(sbmf_state), sizeof(sbmf_timing), sizeof(sbmf_synth_spec), offsetof(sbmf_config, priors), offsetof(sbmf_config, nccl_id));return 0;}\n')
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sbmf_cuda.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(sbmf_config),'
+                 ' sizeof(sbmf_priors), sizeof(sbmf_state), sizeof(sbmf_timing), sizeof(sbmf_synth_spec), offsetof(sbmf_config, priors), offsetof(sbmf_config, nccl_id),'
+                 ' sizeof(sbmf_checkpoint_dims));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(sbmf.Config), ctypes.sizeof(sbmf.Priors), ctypes.sizeof(sbmf.State), ctypes.sizeof(sbmf.Timing),
-            ctypes.sizeof(sbmf.SynthSpec), sbmf.Config.priors.offset, sbmf.Config.nccl_id.offset]
+            ctypes.sizeof(sbmf.SynthSpec), sbmf.Config.priors.offset, sbmf.Config.nccl_id.offset, ctypes.sizeof(sbmf.CheckpointDims)]
     assert got == want
 
 
