@@ -348,6 +348,7 @@ int sbmf_cuda_init_factors(sbmf_handle* h, const float* U0, const float* V0)
     API_CK(cudaGetLastError());
     API_CK(cudaStreamSynchronize(st));
     m.sweeps_done = 0;
+    m.sweeps_since_init = 0;
     m.e_in_csc = false;
     m.need_rebuild = false;
     m.have_factors = true;
@@ -447,7 +448,9 @@ static int graph_sweep(Model& m, bool& done)
 {
     done = false;
     static const bool disabled = getenv("SBMF_NO_GRAPH") != nullptr;
-    if (disabled || m.timing_enabled || m.sweeps_done < 2 || m.need_rebuild) return SBMF_OK;
+    // the first two sweeps after init_factors / set_state run as direct launches: they build the lazily allocated inverse
+    // maps (ensure_inverse), which must not happen inside a capture
+    if (disabled || m.timing_enabled || m.sweeps_done < 2 || m.sweeps_since_init < 2 || m.need_rebuild) return SBMF_OK;
     const SweepKey key = sweep_key(m);
     if (m.graph_exec && !(key == SweepKey{m.gk[0], m.gk[1], m.gk[2], m.gk[3]})) {
         cudaGraphExecDestroy(m.graph_exec);
@@ -485,6 +488,7 @@ static int graph_sweep(Model& m, bool& done)
     }
     m.launches += m.graph_launches;
     m.sweeps_done++;
+    m.sweeps_since_init++;
     done = true;
     return SBMF_OK;
 }
@@ -499,6 +503,7 @@ static int one_sweep(Model& m)
     if (grc != SBMF_OK) return grc;
     m.need_rebuild = false;
     m.sweeps_done++;
+    m.sweeps_since_init++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         m.err = std::string("sweep: kernel launch failed: ") + cudaGetErrorString(e);

@@ -86,6 +86,7 @@ struct Model {
     uint32_t I = 0, J = 0;
     bool have_train = false, have_test = false, have_factors = false;
     uint32_t sweeps_done = 0;
+    uint32_t sweeps_since_init = 0;   // sweeps this handle has launched since init_factors / set_state (lazily built maps exist after 2)
 
     Side us, it;                      // user side (CSR), item side (CSC)
     uint32_t* csr_urow = nullptr;     // [N] user of each CSR slot (COO row index for the flat rebuild)
