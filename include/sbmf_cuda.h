@@ -149,6 +149,13 @@ int sbmf_cuda_plan_shards(const int64_t* ptr, uint32_t n_rows, int world, uint32
 int sbmf_cuda_plan_exchange(uint64_t n, const uint32_t* perm, int world, int rank, const int64_t* csr_bounds,
                             const int64_t* csc_bounds, uint32_t* send_idx, int64_t* send_counts, uint32_t* recv_pos,
                             int64_t* recv_counts);
+/* The same plan computed on the device (csrc/storage.cu: pair-count histogram, stable compaction, stable sort by source
+   rank): what set_train uses with SBMF_DEVICE_PLAN=1 instead of downloading perm.  This entry takes HOST arrays and runs on
+   one GPU, so a single-GPU box can check it against sbmf_cuda_plan_exchange.  pair_counts[src * world + dst] = residuals
+   whose user lives on rank src and whose item lives on rank dst (send_counts of rank r = row r, recv_counts = column r). */
+int sbmf_cuda_plan_exchange_device(uint64_t n, const uint32_t* perm, int world, int rank, const int64_t* csr_bounds,
+                                   const int64_t* csc_bounds, uint32_t* send_idx, uint32_t* recv_pos, int64_t* pair_counts,
+                                   int device);
 
 /* ---- rating storage: replaces the jagged R / R_t build of [T]:32-221 --------------------------------- */
 /* COO in FILE ORDER (rating index n = position), 0-based ids, num_users = 1 + max user id over train U test

@@ -52,10 +52,18 @@ static cudaError_t dmalloc(T** p, size_t n)
 // sbmf_cuda_create): a second set_train in the same process then reuses the memory of the first instead of paying
 // cudaMalloc / cudaFree of several GB again (measured 25-110 ms and varying for the layout alone).  Multi-GPU models keep
 // cudaMalloc throughout: their buffers are exported through CUDA IPC, which pool memory does not support.
+// SBMF_MGPU_POOL=1 (opt-in until measured on a multi-GPU box): the pool also serves the multi-GPU layout -- only the six
+// buffers setup_peer_access exports (factors, biases, exchange buffers; plain dmalloc below) have to be cudaMalloc memory.
+static bool mgpu_pool()
+{
+    static const bool on = getenv("SBMF_MGPU_POOL") != nullptr;
+    return on;
+}
+
 template <class T>
 static cudaError_t palloc(const Model& m, T** p, size_t n, cudaStream_t st)
 {
-    if (m.world > 1) return dmalloc(p, n);
+    if (m.world > 1 && !mgpu_pool()) return dmalloc(p, n);
     return cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), st);
 }
 
@@ -345,15 +353,186 @@ __global__ void rebase_kernel(int64_t* ptr, uint32_t n, int64_t base)
 }
 
 template <typename T>
-static cudaError_t slice_inplace(T*& arr, uint64_t off, uint64_t cnt)
+static cudaError_t slice_inplace(T*& arr, uint64_t off, uint64_t cnt, cudaStream_t st)
 {
     T* loc = nullptr;
+    if (mgpu_pool()) {   // everything stream-ordered: no cudaMalloc / cudaFree of rating-sized arrays
+        cudaError_t e = cudaMallocAsync((void**)&loc, (cnt ? cnt : 1) * sizeof(T), st);
+        if (e != cudaSuccess) return e;
+        if (cnt) e = cudaMemcpyAsync(loc, arr + off, cnt * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        cudaFreeAsync(arr, st);
+        arr = loc;
+        return e;
+    }
     cudaError_t e = dmalloc(&loc, cnt);
     if (e != cudaSuccess) return e;
     if (cnt) e = cudaMemcpy(loc, arr + off, cnt * sizeof(T), cudaMemcpyDeviceToDevice);
     cudaFree(arr);
     arr = loc;
     return e;
+}
+
+// ---- exchange planning on the device: the same plan as plan.cpp (sbmf_cuda_plan_exchange + sbmf_cuda_plan_pair_counts)
+// without moving the 4-byte-per-rating permutation to the host and walking it there three times.
+//   pair counts : histogram of (owner of perm[t], owner of t) over all CSC slots t
+//   send_idx    : stream compaction (stable, ascending t) of the perm values that fall into this rank's CSR shard -- ascending
+//                 t is "grouped by destination rank, in the destination's CSC order", exactly plan.cpp's order
+//   recv_pos    : stable sort of this rank's CSC slots by source rank gives the receive order (position -> slot); its inverse
+//                 is recv_pos
+constexpr int MAX_WORLD = 64;
+struct ShardBounds {
+    int64_t csr[MAX_WORLD + 1], csc[MAX_WORLD + 1];
+    int world;
+};
+
+// last q with b[q] <= slot (plan.cpp: owner); empty shards are never chosen
+__device__ __forceinline__ int owner_of(const int64_t* b, int world, int64_t slot)
+{
+    int lo = 0, hi = world - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (b[mid] <= slot) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+pair_count_kernel(const uint32_t* __restrict__ perm, uint64_t n, ShardBounds b, unsigned long long* __restrict__ counts)
+{
+    extern __shared__ uint32_t s_hist[];   // [world * world]
+    const int W = b.world;
+    for (int i = threadIdx.x; i < W * W; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        const int src = owner_of(b.csr, W, (int64_t)perm[t]);
+        const int dst = owner_of(b.csc, W, (int64_t)t);
+        atomicAdd(&s_hist[src * W + dst], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < W * W; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&counts[i], (unsigned long long)s_hist[i]);
+}
+
+__global__ void source_rank_kernel(const uint32_t* __restrict__ perm_local, uint64_t n, ShardBounds b, uint32_t* __restrict__ key)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        key[i] = (uint32_t)owner_of(b.csr, b.world, (int64_t)perm_local[i]);
+}
+
+__global__ void subtract_kernel(uint32_t* v, uint64_t n, uint32_t base)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] -= base;
+}
+
+struct InCsrShard {
+    uint32_t lo, hi;
+    __host__ __device__ bool operator()(const uint32_t& s) const { return s >= lo && s < hi; }
+};
+
+// d_perm: [N] on the device.  d_send_idx [n_csr of rank], d_recv_pos [n_csc of rank]: device outputs.  h_pc: [G * G] host output,
+// h_pc[src * G + dst].  Synchronises the stream.
+static int plan_exchange_device(Model& m, cudaStream_t st, uint64_t N, const uint32_t* d_perm, int G, int r, const int64_t* cb,
+                                const int64_t* tb, uint32_t* d_send_idx, uint32_t* d_recv_pos, int64_t* h_pc)
+{
+    if (G < 1 || G > MAX_WORLD || r < 0 || r >= G || (uint64_t)cb[G] != N || (uint64_t)tb[G] != N || N >= (1ull << 31)) {
+        m.err = "exchange planning: bad bounds";
+        return SBMF_ERR_INVALID;
+    }
+    ShardBounds b;
+    memset(&b, 0, sizeof(b));
+    b.world = G;
+    for (int q = 0; q <= G; ++q) {
+        b.csr[q] = cb[q];
+        b.csc[q] = tb[q];
+    }
+    const uint64_t c0 = (uint64_t)cb[r], c1 = (uint64_t)cb[r + 1], t0 = (uint64_t)tb[r], t1 = (uint64_t)tb[r + 1];
+    const uint64_t n_csr = c1 - c0, n_csc = t1 - t0;
+    const int T = 256;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((N + T - 1) / T + 1, (uint64_t)m.sm_count * 16);
+    const uint32_t grid_l = (uint32_t)std::min<uint64_t>((n_csc + T - 1) / T + 1, (uint64_t)m.sm_count * 16);
+    unsigned long long* d_pc = nullptr;
+    int* d_nsel = nullptr;
+    uint32_t *d_key = nullptr, *d_key_out = nullptr, *d_iota = nullptr, *d_order = nullptr;
+    void* d_tmp = nullptr;
+    auto cleanup = [&]() {
+        for (void* p : {(void*)d_pc, (void*)d_nsel, (void*)d_key, (void*)d_key_out, (void*)d_iota, (void*)d_order, d_tmp})
+            if (p) cudaFreeAsync(p, st);
+    };
+#define CKP(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            m.err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            cleanup();                                                                             \
+            return (e_ == cudaErrorMemoryAllocation) ? SBMF_ERR_NOMEM : SBMF_ERR_CUDA;             \
+        }                                                                                          \
+    } while (0)
+    auto talloc = [&](void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, st); };
+    CKP(talloc((void**)&d_pc, (size_t)G * G * 8));
+    CKP(talloc((void**)&d_nsel, 4));
+    CKP(talloc((void**)&d_key, n_csc * 4)); CKP(talloc((void**)&d_key_out, n_csc * 4));
+    CKP(talloc((void**)&d_iota, n_csc * 4)); CKP(talloc((void**)&d_order, n_csc * 4));
+    size_t sel_bytes = 0, sort_bytes = 0;
+    const InCsrShard in_shard{(uint32_t)c0, (uint32_t)c1};
+    CKP(cub::DeviceSelect::If(nullptr, sel_bytes, d_perm, d_send_idx, d_nsel, (int)N, in_shard, st));
+    CKP(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_key, d_key_out, d_iota, d_order, (int)n_csc, 0, bits_for((uint32_t)G), st));
+    CKP(talloc(&d_tmp, std::max(sel_bytes, sort_bytes)));
+    // traffic matrix
+    CKP(cudaMemsetAsync(d_pc, 0, (size_t)G * G * 8, st));
+    if (N) pair_count_kernel<<<grid, T, (size_t)G * G * 4, st>>>(d_perm, N, b, d_pc);
+    // send order
+    CKP(cub::DeviceSelect::If(d_tmp, sel_bytes, d_perm, d_send_idx, d_nsel, (int)N, in_shard, st));
+    if (n_csr) subtract_kernel<<<grid, T, 0, st>>>(d_send_idx, n_csr, (uint32_t)c0);
+    // receive order
+    if (n_csc) {
+        source_rank_kernel<<<grid_l, T, 0, st>>>(d_perm + t0, n_csc, b, d_key);
+        iota_kernel<<<grid_l, T, 0, st>>>(d_iota, n_csc);
+        CKP(cub::DeviceRadixSort::SortPairs(d_tmp, sort_bytes, d_key, d_key_out, d_iota, d_order, (int)n_csc, 0, bits_for((uint32_t)G), st));
+        invert_kernel<<<grid_l, T, 0, st>>>(d_order, d_recv_pos, n_csc);
+    }
+    CKP(cudaGetLastError());
+    std::vector<unsigned long long> pc((size_t)G * G);
+    int nsel = 0;
+    CKP(cudaMemcpyAsync(pc.data(), d_pc, (size_t)G * G * 8, cudaMemcpyDeviceToHost, st));
+    CKP(cudaMemcpyAsync(&nsel, d_nsel, 4, cudaMemcpyDeviceToHost, st));
+    CKP(cudaStreamSynchronize(st));
+    cleanup();
+#undef CKP
+    if ((uint64_t)nsel != n_csr) {
+        m.err = "exchange planning: perm is not a permutation";
+        return SBMF_ERR_INVALID;
+    }
+    for (size_t i = 0; i < pc.size(); ++i) h_pc[i] = (int64_t)pc[i];
+    return SBMF_OK;
+}
+
+// Test hook (single GPU is enough): the device planner on host arrays, for comparison with sbmf_cuda_plan_exchange.
+extern "C" int sbmf_cuda_plan_exchange_device(uint64_t n, const uint32_t* perm, int world, int rank, const int64_t* csr_bounds,
+                                              const int64_t* csc_bounds, uint32_t* send_idx, uint32_t* recv_pos, int64_t* pair_counts, int device)
+{
+    if (!perm || !csr_bounds || !csc_bounds || !send_idx || !recv_pos || !pair_counts || world < 1 || world > MAX_WORLD || rank < 0 || rank >= world)
+        return SBMF_ERR_INVALID;
+    Model m;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SBMF_ERR_CUDA;
+    m.sm_count = prop.multiProcessorCount;
+    const uint64_t n_csr = (uint64_t)(csr_bounds[rank + 1] - csr_bounds[rank]), n_csc = (uint64_t)(csc_bounds[rank + 1] - csc_bounds[rank]);
+    uint32_t *d_perm = nullptr, *d_s = nullptr, *d_r = nullptr;
+    cudaStream_t st = nullptr;
+    int rc = SBMF_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess && dmalloc(&d_perm, n) == cudaSuccess &&
+        dmalloc(&d_s, n_csr) == cudaSuccess && dmalloc(&d_r, n_csc) == cudaSuccess &&
+        cudaMemcpyAsync(d_perm, perm, n * 4, cudaMemcpyHostToDevice, st) == cudaSuccess) {
+        rc = plan_exchange_device(m, st, n, d_perm, world, rank, csr_bounds, csc_bounds, d_s, d_r, pair_counts);
+        if (rc == SBMF_OK && (cudaMemcpy(send_idx, d_s, n_csr * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                              cudaMemcpy(recv_pos, d_r, n_csc * 4, cudaMemcpyDeviceToHost) != cudaSuccess))
+            rc = SBMF_ERR_CUDA;
+    }
+    cudaGetLastError();
+    cudaFree(d_perm); cudaFree(d_s); cudaFree(d_r);
+    if (st) cudaStreamDestroy(st);
+    return rc;
 }
 
 // multi-GPU: cut the global layout into this rank's CSR shard (its users) and CSC shard (its items) and plan the residual
@@ -383,16 +562,31 @@ static int shard_storage(Model& m)
     m.n_csr = c1 - c0;
     m.n_csc = t1 - t0;
     {
-        std::vector<uint32_t> perm(m.N ? m.N : 1), sidx(m.n_csr ? m.n_csr : 1), rpos(m.n_csc ? m.n_csc : 1);
-        std::vector<int64_t> sc(G), rc(G);
-        CK(cudaMemcpy(perm.data(), m.perm, m.N * 4, cudaMemcpyDeviceToHost));
-        if (sbmf_cuda_plan_exchange(m.N, perm.data(), G, r, cb.data(), tb.data(), sidx.data(), sc.data(), rpos.data(), rc.data()) != SBMF_OK) {
-            m.err = "set_train: exchange planning failed (internal)";
-            return SBMF_ERR_INVALID;
+        // SBMF_DEVICE_PLAN=1: plan on the device (plan_exchange_device above) instead of downloading perm and walking it on the
+        // host.  Opt-in until it has run on a multi-GPU box; the host path is the one the CPU tests cover.
+        static const bool device_plan = getenv("SBMF_DEVICE_PLAN") != nullptr;
+        std::vector<int64_t> sc(G), rc(G), pc((size_t)G * G);
+        CK(dmalloc(&m.send_idx, m.n_csr)); CK(dmalloc(&m.recv_pos, m.n_csc));
+        CK(dmalloc(&m.sendbuf, m.n_csr)); CK(dmalloc(&m.recvbuf, m.n_csc));
+        if (device_plan) {
+            const int prc = plan_exchange_device(m, m.s_main, m.N, m.perm, G, r, cb.data(), tb.data(), m.send_idx, m.recv_pos, pc.data());
+            if (prc != SBMF_OK) return prc;
+            for (int q = 0; q < G; ++q) {
+                sc[q] = pc[(size_t)r * G + q];   // what I send to q: my users' ratings of q's items
+                rc[q] = pc[(size_t)q * G + r];   // what q sends to me
+            }
+        } else {
+            std::vector<uint32_t> perm(m.N ? m.N : 1), sidx(m.n_csr ? m.n_csr : 1), rpos(m.n_csc ? m.n_csc : 1);
+            CK(cudaMemcpy(perm.data(), m.perm, m.N * 4, cudaMemcpyDeviceToHost));
+            if (sbmf_cuda_plan_exchange(m.N, perm.data(), G, r, cb.data(), tb.data(), sidx.data(), sc.data(), rpos.data(), rc.data()) != SBMF_OK) {
+                m.err = "set_train: exchange planning failed (internal)";
+                return SBMF_ERR_INVALID;
+            }
+            sbmf_cuda_plan_pair_counts(m.N, perm.data(), G, cb.data(), tb.data(), pc.data());
+            CK(cudaMemcpy(m.send_idx, sidx.data(), m.n_csr * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(m.recv_pos, rpos.data(), m.n_csc * 4, cudaMemcpyHostToDevice));
         }
         {   // where my segments start in every peer's buffers (for the direct-push exchange)
-            std::vector<int64_t> pc((size_t)G * G);
-            sbmf_cuda_plan_pair_counts(m.N, perm.data(), G, cb.data(), tb.data(), pc.data());
             m.fwd_dst_off.assign(G, 0);
             m.rev_dst_off.assign(G, 0);
             for (int q = 0; q < G; ++q) {
@@ -411,16 +605,14 @@ static int shard_storage(Model& m)
             m.send_off[q] = so; m.send_cnt[q] = (size_t)sc[q]; so += (size_t)sc[q];
             m.recv_off[q] = ro; m.recv_cnt[q] = (size_t)rc[q]; ro += (size_t)rc[q];
         }
-        CK(dmalloc(&m.send_idx, m.n_csr)); CK(dmalloc(&m.recv_pos, m.n_csc));
-        CK(dmalloc(&m.sendbuf, m.n_csr)); CK(dmalloc(&m.recvbuf, m.n_csc));
-        CK(cudaMemcpy(m.send_idx, sidx.data(), m.n_csr * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(m.recv_pos, rpos.data(), m.n_csc * 4, cudaMemcpyHostToDevice));
     }
-    cudaFree(m.perm);
+    if (mgpu_pool()) cudaFreeAsync(m.perm, m.s_main);
+    else cudaFree(m.perm);
     m.perm = nullptr;
-    CK(slice_inplace(m.us.idx, c0, m.n_csr)); CK(slice_inplace(m.us.e, c0, m.n_csr)); CK(slice_inplace(m.csr_urow, c0, m.n_csr));
-    CK(slice_inplace(m.csr_r, c0, m.n_csr)); CK(slice_inplace(m.csr_id, c0, m.n_csr));
-    CK(slice_inplace(m.it.idx, t0, m.n_csc)); CK(slice_inplace(m.it.e, t0, m.n_csc)); CK(slice_inplace(m.csc_id, t0, m.n_csc));
+    cudaStream_t st = m.s_main;
+    CK(slice_inplace(m.us.idx, c0, m.n_csr, st)); CK(slice_inplace(m.us.e, c0, m.n_csr, st)); CK(slice_inplace(m.csr_urow, c0, m.n_csr, st));
+    CK(slice_inplace(m.csr_r, c0, m.n_csr, st)); CK(slice_inplace(m.csr_id, c0, m.n_csr, st));
+    CK(slice_inplace(m.it.idx, t0, m.n_csc, st)); CK(slice_inplace(m.it.e, t0, m.n_csc, st)); CK(slice_inplace(m.csc_id, t0, m.n_csc, st));
     rebase_kernel<<<(m.I + 256) / 256, 256, 0, m.s_main>>>(m.us.ptr, m.I, (int64_t)c0);
     rebase_kernel<<<(m.J + 256) / 256, 256, 0, m.s_main>>>(m.it.ptr, m.J, (int64_t)t0);
     CK(cudaGetLastError());

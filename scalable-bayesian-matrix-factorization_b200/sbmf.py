@@ -110,6 +110,7 @@ def load_library(path=None):
     lib.sbmf_cuda_host_free.argtypes = [C.c_void_p]
     lib.sbmf_cuda_plan_shards.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
     lib.sbmf_cuda_plan_exchange.argtypes = [C.c_uint64, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+    lib.sbmf_cuda_plan_exchange_device.argtypes = [C.c_uint64, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
     lib.sbmf_cuda_synth_generate.argtypes = [P(SynthSpec), P(C.c_uint64), P(C.c_uint64)] + [C.c_void_p] * 6
     lib.sbmf_cuda_synth_last_error.restype = C.c_char_p
     lib.sbmf_cuda_synth_host_generate.argtypes = [P(SynthSpec), C.c_int, P(C.c_uint64), P(C.c_uint64)] + [P(C.c_void_p)] * 6
@@ -355,6 +356,19 @@ def plan_exchange(perm, world, rank, csr_bounds, csc_bounds):
     rc = load_library().sbmf_cuda_plan_exchange(perm.size, _ptr(perm), world, rank, _ptr(cb), _ptr(tb), _ptr(send_idx), _ptr(sc), _ptr(recv_pos), _ptr(rc_))
     assert rc == 0, rc
     return send_idx, sc, recv_pos, rc_
+
+
+def plan_exchange_device(perm, world, rank, csr_bounds, csc_bounds, device=0):
+    """the device-side planner on host arrays (needs a GPU): returns (send_idx, recv_pos, pair_counts[world, world])"""
+    perm = np.ascontiguousarray(perm, np.uint32)
+    cb, tb = np.ascontiguousarray(csr_bounds, np.int64), np.ascontiguousarray(csc_bounds, np.int64)
+    send_idx = np.empty(int(cb[rank + 1] - cb[rank]), np.uint32)
+    recv_pos = np.empty(int(tb[rank + 1] - tb[rank]), np.uint32)
+    pc = np.empty((world, world), np.int64)
+    rc = load_library().sbmf_cuda_plan_exchange_device(perm.size, _ptr(perm), world, rank, _ptr(cb), _ptr(tb), _ptr(send_idx), _ptr(recv_pos), _ptr(pc), device)
+    if rc != 0:
+        raise SbmfError(rc, "sbmf_cuda_plan_exchange_device failed")
+    return send_idx, recv_pos, pc
 
 
 def pinned_empty(n, dtype):

@@ -74,6 +74,26 @@ def test_plan_exchange_reproduces_permute(case, world, ml100k, tiny, sbmf_mod):
         assert np.array_equal(e_csc_local, e_csr[perm][tb[r]:tb[r + 1]])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["ml100k", "tiny"])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_device_planner_equals_host_planner(case, world, ml100k, tiny, sbmf_mod):
+    """The exchange plan computed on the device (SBMF_DEVICE_PLAN=1 path of set_train) is bit-identical to plan.cpp's, for every
+    rank: send order, receive positions and the traffic matrix.  Runs on ONE GPU (the planner takes the bounds as arguments)."""
+    d = ml100k if case == "ml100k" else tiny
+    L = layout_of(d)
+    perm = L["perm"].astype(np.uint32)
+    ub, ib = sbmf_mod.plan_shards(L["row_ptr"], world), sbmf_mod.plan_shards(L["col_ptr"], world)
+    cb, tb = L["row_ptr"][ub.astype(np.int64)], L["col_ptr"][ib.astype(np.int64)]
+    for r in range(world):
+        send_idx, sc, recv_pos, rc = sbmf_mod.plan_exchange(perm, world, r, cb, tb)
+        d_send, d_recv, pc = sbmf_mod.plan_exchange_device(perm, world, r, cb, tb)
+        assert np.array_equal(d_send, send_idx), (world, r)
+        assert np.array_equal(d_recv, recv_pos), (world, r)
+        assert np.array_equal(pc[r, :], sc) and np.array_equal(pc[:, r], rc), (world, r)
+        assert pc.sum() == perm.size
+
+
 WORKER = r'''
 import os, sys
 import numpy as np
