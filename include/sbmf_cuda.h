@@ -172,6 +172,15 @@ int sbmf_cuda_set_test(sbmf_handle* h, uint64_t nt, const uint32_t* user, const 
 int sbmf_cuda_get_layout(sbmf_handle* h, int64_t* row_ptr, uint32_t* col, uint64_t* csr_id,
                          int64_t* col_ptr, uint32_t* row, uint64_t* csc_id, uint64_t* perm);
 
+/* libFM's transposed binary design matrix (".xt", fmatrix.h:34-52) of the training data from the layout get_layout returns:
+   feature f < num_users is the user's CSR row, feature item_offset + j the item's CSC row, entries {rating index, 1.0f} in
+   rating order -- byte-identical to what the reference's src/libfm/tools/transpose.cpp (83-166) writes for the same .x
+   (num_features = that file's num_cols = 1 + the largest feature id in it).  Pure host code (csrc/xt_writer.cpp). */
+int sbmf_cuda_write_libfm_xt(const char* path, uint32_t num_features, uint32_t num_users, uint32_t num_items,
+                             uint32_t item_offset, uint64_t n, const int64_t* row_ptr, const uint64_t* csr_id,
+                             const int64_t* col_ptr, const uint64_t* csc_id);
+const char* sbmf_cuda_write_libfm_xt_last_error(void);
+
 /* ---- model state ----------------------------------------------------------------------------------- */
 /* U0 [num_users][K] row-major, V0 [K][num_items]; NULL => 0.1*N(0,1) from the Philox INIT streams
    ([T]:239-250).  Zeroes biases/hypers ([T]:268-281, 315-318), the sweep counter and the prediction sums. */

@@ -251,6 +251,7 @@ int main(int argc, char** argv)
         const std::string p_dump = cmd.reg("dump_triples", "write the parsed training triples (user item rating) to this file");
         const std::string p_save = cmd.reg("save_state", "write a checkpoint (factors, biases, hyper-parameters, residual, prediction sums) to this file after the last sweep");
         const std::string p_load = cmd.reg("load_state", "continue the chain from this checkpoint instead of initialising; -iter = number of further sweeps");
+        const std::string p_xt = cmd.reg("dump_xt", "write the transposed design matrix of the training data (libFM binary .xt, as tools/transpose writes it) from the device-built layout");
         const std::string p_dry = cmd.reg("dry_run", "1 = parse the inputs, print the header lines and stop (no GPU needed)");
         if (cmd.has(p_help)) {
             cmd.print_help();
@@ -326,6 +327,20 @@ int main(int argc, char** argv)
         if (sbmf_cuda_create(&cfg, &h) != SBMF_OK) throw std::string("sbmf_cuda_create: ") + sbmf_cuda_last_error(NULL);
         ck(sbmf_cuda_set_train(h, tr.user.size(), tr.user.data(), tr.item.data(), tr.rating.data(), num_users, num_items), h, "set_train");
         ck(sbmf_cuda_set_test(h, te.user.size(), te.user.data(), te.item.data(), te.rating.data()), h, "set_test");
+        if (cmd.has(p_xt)) {
+            // the device storage build IS the transpose: CSR rows = user features, CSC rows = item features (csrc/xt_writer.cpp).
+            // Item features are numbered after the users: at the offset of the libFM input, else at num_users like
+            // scripts/triple_format_to_libfm.pl; the feature count is that of the training file alone, like tools/convert.
+            const uint32_t xoff = (libfm_tr && off > 0) ? (uint32_t)off : num_users;
+            const uint32_t nfeat = tr.item.empty() ? num_users : xoff + tr.item_max + 1;
+            const size_t n = tr.user.size();
+            std::vector<int64_t> rp((size_t)num_users + 1), cp((size_t)num_items + 1);
+            std::vector<uint64_t> rid(n ? n : 1), cid(n ? n : 1);
+            ck(sbmf_cuda_get_layout(h, rp.data(), NULL, rid.data(), cp.data(), NULL, cid.data(), NULL), h, "get_layout");
+            if (sbmf_cuda_write_libfm_xt(cmd.get(p_xt, "").c_str(), nfeat, num_users, num_items, xoff, n, rp.data(), rid.data(), cp.data(),
+                                         cid.data()) != SBMF_OK)
+                throw std::string(sbmf_cuda_write_libfm_xt_last_error());
+        }
         // state arrays of a checkpoint (sbmf_state members point into these)
         const size_t nI = num_users, nJ = num_items, nN = tr.user.size(), nT = te.user.size();
         std::vector<float> cU, cV, cbi, cbj, cmbi, csbi, cmbj, csbj, cE;

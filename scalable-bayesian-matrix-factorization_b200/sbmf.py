@@ -111,6 +111,8 @@ def load_library(path=None):
     lib.sbmf_cuda_plan_shards.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
     lib.sbmf_cuda_plan_exchange.argtypes = [C.c_uint64, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
     lib.sbmf_cuda_plan_exchange_device.argtypes = [C.c_uint64, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+    lib.sbmf_cuda_write_libfm_xt.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64] + [C.c_void_p] * 4
+    lib.sbmf_cuda_write_libfm_xt_last_error.restype = C.c_char_p
     lib.sbmf_cuda_synth_generate.argtypes = [P(SynthSpec), P(C.c_uint64), P(C.c_uint64)] + [C.c_void_p] * 6
     lib.sbmf_cuda_synth_last_error.restype = C.c_char_p
     lib.sbmf_cuda_synth_host_generate.argtypes = [P(SynthSpec), C.c_int, P(C.c_uint64), P(C.c_uint64)] + [P(C.c_void_p)] * 6
@@ -369,6 +371,16 @@ def plan_exchange_device(perm, world, rank, csr_bounds, csc_bounds, device=0):
     if rc != 0:
         raise SbmfError(rc, "sbmf_cuda_plan_exchange_device failed")
     return send_idx, recv_pos, pc
+
+
+def write_libfm_xt(path, layout, num_features, num_users, num_items, item_offset):
+    """sbmf_cuda_write_libfm_xt from a get_layout()-shaped dict (row_ptr, csr_id, col_ptr, csc_id); host only"""
+    lib = load_library()
+    rp, cp = np.ascontiguousarray(layout["row_ptr"], np.int64), np.ascontiguousarray(layout["col_ptr"], np.int64)
+    rid, cid = np.ascontiguousarray(layout["csr_id"], np.uint64), np.ascontiguousarray(layout["csc_id"], np.uint64)
+    rc = lib.sbmf_cuda_write_libfm_xt(os.fsencode(path), num_features, num_users, num_items, item_offset, rid.size, _ptr(rp), _ptr(rid), _ptr(cp), _ptr(cid))
+    if rc != 0:
+        raise SbmfError(rc, lib.sbmf_cuda_write_libfm_xt_last_error().decode())
 
 
 def pinned_empty(n, dtype):

@@ -10,6 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CONVERT = os.path.join(ROOT, "oracle", "_ref", "convert")
+TRANSPOSE = os.path.join(ROOT, "oracle", "_ref", "transpose")   # src/libfm/tools/transpose.cpp, unmodified
 NUM_USERS = 50
 
 for split in ("train", "test"):
@@ -21,3 +22,7 @@ for split in ("train", "test"):
             o.write(f"{r} {u}:1 {int(i) + NUM_USERS}:1\n")
     subprocess.run([CONVERT, "-ifile", txt, "-ofilex", txt + "_bin.x", "-ofiley", txt + "_bin.y"], check=True, capture_output=True)
     print(split, os.path.getsize(txt + "_bin.x"), os.path.getsize(txt + "_bin.y"))
+# the transposed design matrix of the training data, written by the reference's own transpose tool
+xt = os.path.join(HERE, "tiny_libfm.train_bin.xt")
+subprocess.run([TRANSPOSE, "-ifile", os.path.join(HERE, "tiny_libfm.train_bin.x"), "-ofile", xt], check=True, capture_output=True)
+print("xt", os.path.getsize(xt))
