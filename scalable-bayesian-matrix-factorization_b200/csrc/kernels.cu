@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "gram.cuh"
 #include "model.h"
 
 namespace sbmf {
@@ -67,17 +68,7 @@ __device__ __forceinline__ float load_e_first(const PhaseArgs& a, int64_t slot)
     return a.e_map ? __ldg(a.e_src + a.e_map[slot]) : a.e[slot];
 }
 
-__host__ __device__ constexpr int gi(int k, int l) { return 8 + k * 8 - (k * (k - 1)) / 2 + (l - k); }   // k <= l
-
-__device__ __forceinline__ void accumulate(float (&acc)[NACC], const f8& f, float e)
-{
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = fmaf(f.v[k], e, acc[k]);
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int l = k; l < 8; ++l) acc[gi(k, l)] = fmaf(f.v[k], f.v[l], acc[gi(k, l)]);
-}
+// gi(k, l), the per-rating accumulation (GramAcc: 44 FFMA, or 24 FFMA2 with -DSBMF_FFMA2=1) and its layouts: gram.cuh
 
 __device__ __forceinline__ float dot8(const f8& a, const float (&d)[8])
 {
@@ -288,10 +279,13 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         if (mode != SAMPLE_ZERO && (((b & 3) == 0) || b == b_begin))
             zq = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)((b & ~3) * 8 + lane), sweep));
         float acc[NACC];
+        {
+            GramAcc ga;
+            ga.clear();
 #pragma unroll
-        for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) accumulate(acc, f[r], e[r]);
+            for (int r = 0; r < RPL; ++r) ga.add(f[r], e[r]);
+            ga.finish(acc);
+        }
         warp_reduce_scatter48(acc, lane);
         if (WARPS == 1) {
             if ((lane & 1) == 0) {
@@ -491,10 +485,13 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
         if (mode != SAMPLE_ZERO && (((b % ZB) == 0) || b == b_begin))
             zq = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)((b - b % ZB) * 8 + lg), sweep));
         float acc[NACC];
+        {
+            GramAcc ga;
+            ga.clear();
 #pragma unroll
-        for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) accumulate(acc, f[r], e[r]);
+            for (int r = 0; r < RPL; ++r) ga.add(f[r], e[r]);
+            ga.finish(acc);
+        }
         group_reduce_scatter48<G>(acc, lg);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -587,7 +584,9 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
     const uint32_t pad_row = a.ns_other - 1;
     float acc[NACC];
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;   // (CUR == 1 sums into acc[0]; CUR == 2 fills it from ga after the loop)
+    GramAcc ga;
+    ga.clear();
     const uint32_t* idx = a.idx + sl.start;
     float* ep = a.e + sl.start;
     // batches of UNR ratings per thread: all index/residual loads, then all gathers, then the math, so that
@@ -625,7 +624,7 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
             }
             if (i < sl.len) ep[i] = e[u];
             if (CUR == 1 && i < sl.len) acc[0] += e[u];
-            if (CUR == 2) accumulate(acc, fc[u], e[u]);
+            if (CUR == 2) ga.add(fc[u], e[u]);
         }
     }
     if (CUR == 1) {
@@ -640,6 +639,7 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
         }
     }
     if (CUR == 2) {
+        ga.finish(acc);
         warp_reduce_scatter48(acc, lane);
         const int base = reduce_scatter_base(lane);
         if ((lane & 1) == 0) {

@@ -86,3 +86,17 @@ def test_product_does_not_reference_the_oracle():
                     if re.search(r"liboracle|sbmf_oracle|oracle_py|oracle/", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_packed_gram_accumulation_equals_scalar(tmp_path):
+    """csrc/gram.cuh: the FFMA2 (fma.rn.f32x2) form of the per-rating Gram accumulation visits every sum with the same fused
+    multiply-adds in the same order as the scalar form -- checked bit for bit on the CPU (host emulation = two fmaf)."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "ffma2_check"
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(PKG, "csrc"), "-o", str(exe),
+                    os.path.join(ROOT, "tools", "ffma2_check.cu")], check=True, capture_output=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "agree bit for bit" in r.stdout, r.stdout + r.stderr
