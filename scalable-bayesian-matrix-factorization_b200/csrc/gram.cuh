@@ -87,6 +87,17 @@ __host__ __device__ __forceinline__ void unpack_pairs(const float2 (&a2)[NPAIR],
     for (int i = 44; i < NACC; ++i) acc[i] = 0.f;
 }
 
+// Residual update + prediction refresh of one rating: fd = <f, d>, fu = <f, u> (two 8-term chains, each summed in the order
+// k = 0..7 like dot8 in kernels.cu).  Packed form: the pair (fd, fu) advances with ONE FFMA2 per k -- f[k] broadcast, the pair
+// (d[k], u[k]) prepared once per row and block -- instead of two FFMA; same operations per chain, same results.
+__host__ __device__ __forceinline__ float2 dot8_pair(const f8& f, const float2 (&du)[8])
+{
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = fma2_bcast(f.v[k], du[k], s);
+    return s;
+}
+
 // The accumulator of one (row | slice, block) step in whichever form the build selects.
 struct GramAcc {
 #if SBMF_FFMA2

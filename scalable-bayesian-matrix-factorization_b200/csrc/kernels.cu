@@ -69,6 +69,7 @@ __device__ __forceinline__ float load_e_first(const PhaseArgs& a, int64_t slot)
 }
 
 // gi(k, l), the per-rating accumulation (GramAcc: 44 FFMA, or 24 FFMA2 with -DSBMF_FFMA2=1) and its layouts: gram.cuh
+constexpr bool kPairedDots = SBMF_FFMA2 != 0;   // REFRESH kernels: (<f, d>, <f, u>) as one FFMA2 chain (dot8_pair)
 
 __device__ __forceinline__ float dot8(const f8& a, const float (&d)[8])
 {
@@ -331,15 +332,27 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 #pragma unroll
             for (int l = 0; l < 8; ++l) so.d[l] = s_d[l];
         }
+        if (kPairedDots && REFRESH) {   // (<f, d>, <f, u_old>) as one pair per rating: 8 FFMA2 instead of 16 FFMA (gram.cuh)
+            float2 du[8];
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            const float fd = dot8(f[r], so.d);
-            e[r] += fd;
-            if (REFRESH) {   // <f, u_new> = <f, u_old> - <f, d>; u_old broadcast from the 8 lanes that hold it
-                float fu = 0.f;
+            for (int k = 0; k < 8; ++k) du[k] = make_float2(so.d[k], uo8[k]);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) fu = fmaf(f[r].v[k], uo8[k], fu);
-                pr[r] += fu - fd;
+            for (int r = 0; r < RPL; ++r) {
+                const float2 s2 = dot8_pair(f[r], du);
+                e[r] += s2.x;
+                pr[r] += s2.y - s2.x;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const float fd = dot8(f[r], so.d);
+                e[r] += fd;
+                if (REFRESH) {   // <f, u_new> = <f, u_old> - <f, d>; u_old broadcast from the 8 lanes that hold it
+                    float fu = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) fu = fmaf(f[r].v[k], uo8[k], fu);
+                    pr[r] += fu - fd;
+                }
             }
         }
         if (b + 1 < b_end) {   // next block's gathers (a register double buffer for them costs more occupancy than it hides latency)
@@ -508,15 +521,27 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
         // every octet solves its group's row (for G == 16 both octets of the group compute the same values); an idle group's
         // lanes report lane index 8 so that they never take the write branch
         const SolveOut so = solve_lanes(tot, a, foff, uo, sig, mu, live, mode, z, alpha, have_row ? lg : 8);
+        if (kPairedDots && REFRESH) {
+            float2 du[8];
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            const float fd = dot8(f[r], so.d);
-            e[r] += fd;
-            if (REFRESH) {
-                float fu = 0.f;
+            for (int k = 0; k < 8; ++k) du[k] = make_float2(so.d[k], uo8[k]);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) fu = fmaf(f[r].v[k], uo8[k], fu);
-                pr[r] += fu - fd;
+            for (int r = 0; r < RPL; ++r) {
+                const float2 s2 = dot8_pair(f[r], du);
+                e[r] += s2.x;
+                pr[r] += s2.y - s2.x;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const float fd = dot8(f[r], so.d);
+                e[r] += fd;
+                if (REFRESH) {
+                    float fu = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) fu = fmaf(f[r].v[k], uo8[k], fu);
+                    pr[r] += fu - fd;
+                }
             }
         }
         if (b + 1 < b_end) {
@@ -577,6 +602,9 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
         for (int k = 0; k < 8; ++k) unprev[k] = Fsp[k];
         if (CUR == 0) row_const = a.sc->b_0_f + a.bias[row];
     }
+    float2 dun[8];   // (d_prev[k], u_new_prev[k]) pairs of the packed form
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dun[k] = make_float2((PREV == 2) ? dprev[k] : 0.f, unprev[k]);
     float* pp = a.pacc + sl.start;
     const float* rp = a.r + sl.start;
     const float* Fp = a.Fother + (size_t)pb * a.ns_other * 8;
@@ -615,10 +643,16 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const uint32_t i = base + u * THREADS;
-            if (PREV == 2) e[u] += dot8(fp[u], dprev);
-            else e[u] += dscalar;
+            if (kPairedDots && REFRESH && PREV == 2) {   // (<f_prev, d_prev>, <f_prev, u_new_prev>) as one FFMA2 chain
+                const float2 s2 = dot8_pair(fp[u], dun);
+                e[u] += s2.x;
+                pr[u] += s2.y;
+            } else {
+                if (PREV == 2) e[u] += dot8(fp[u], dprev);
+                else e[u] += dscalar;
+                if (REFRESH && PREV == 2) pr[u] += dot8(fp[u], unprev);
+            }
             if (REFRESH && PREV == 2) {
-                pr[u] += dot8(fp[u], unprev);
                 if (CUR == 0) e[u] = (i < sl.len) ? rp[i] - (row_const + a.bias_other[id[u]] + pr[u]) : 0.f;   // phase done: fresh residual
                 else if (i < sl.len) pp[i] = pr[u];
             }

@@ -50,6 +50,23 @@ int main()
                 ++bad;
             }
     }
+    // the paired dot products of the REFRESH kernels: (<f, d>, <f, u>) as one chain of pairs == two scalar chains (dot8 of kernels.cu)
+    for (int trial = 0; trial < 200; ++trial) {
+        f8 f;
+        float d[8], u[8];
+        float2 du[8];
+        for (int k = 0; k < 8; ++k) {
+            f.v[k] = rnd();
+            d[k] = rnd() * 1e-2f;
+            u[k] = rnd();
+            du[k] = make_float2(d[k], u[k]);
+        }
+        float fd = 0.f, fu = 0.f;
+        for (int k = 0; k < 8; ++k) fd = fmaf(f.v[k], d[k], fd);
+        for (int k = 0; k < 8; ++k) fu = fmaf(f.v[k], u[k], fu);
+        const float2 s2 = dot8_pair(f, du);
+        if (memcmp(&s2.x, &fd, 4) != 0 || memcmp(&s2.y, &fu, 4) != 0) ++bad;
+    }
     if (bad) return printf("FAILED: %d mismatching sums\n", bad), 1;
     printf("ffma2_check ok: packed and scalar Gram accumulation agree bit for bit (200 trials, 44 sums each)\n");
     return 0;
