@@ -34,6 +34,7 @@
 #include <string>
 #include <vector>
 
+#include "rating_reader.h"
 #include "sbmf_cuda.h"
 
 namespace {
@@ -170,42 +171,19 @@ void read_ratings(const std::string& path, Ratings& out, long item_offset, bool&
         }
         return;
     }
-    std::ifstream f(path.c_str());
-    if (!f.is_open()) throw "unable to open " + path;
-    std::string line;
-    bool detected = false, libfm = false;
-    std::vector<uint32_t> raw_item;
-    uint64_t lineno = 0;
-    while (std::getline(f, line)) {
-        ++lineno;
-        if (!detected) {
-            if (line.find_first_not_of(" \t\r\n") == std::string::npos) continue;
-            libfm = line.find(':') != std::string::npos;
-            detected = true;
-        }
-        unsigned u, m;
-        double r;
-        if (!libfm) {
-            char w1, w2;
-            if (sscanf(line.c_str(), "%u%c%u%c%lf", &u, &w1, &m, &w2, &r) >= 5) {
-                out.user.push_back(u);
-                out.item.push_back(m);
-                out.rating.push_back((float)r);
-            } else if (line.find_first_not_of(" \t\r\n") != std::string::npos) {
-                // [T] would skip the line but still advance its rating index and write out of bounds later
-                throw "malformed rating line " + std::to_string(lineno) + " in " + path;
-            }
-        } else {
-            double v1, v2;
-            if (sscanf(line.c_str(), "%lf %u:%lf %u:%lf", &r, &u, &v1, &m, &v2) == 5) {
-                out.user.push_back(u);
-                out.item.push_back(m);
-                out.rating.push_back((float)r);
-            } else if (line.find_first_not_of(" \t\r\n") != std::string::npos) {
-                throw "libFM text line " + std::to_string(lineno) + " in " + path + " is not `y user:1 item:1`";
-            }
-        }
+    // text: one read, one chunk per host thread, sscanf semantics (rating_reader.h)
+    rating_reader::Parsed parsed;
+    bool libfm = false;
+    uint64_t bad_line = 0;
+    if (!rating_reader::read_text(path, parsed, libfm, bad_line)) throw "unable to open " + path;
+    if (bad_line) {
+        // [T] would skip the line but still advance its rating index and write out of bounds later
+        if (!libfm) throw "malformed rating line " + std::to_string(bad_line) + " in " + path;
+        throw "libFM text line " + std::to_string(bad_line) + " in " + path + " is not `y user:1 item:1`";
     }
+    out.user.swap(parsed.user);
+    out.item.swap(parsed.item);
+    out.rating.swap(parsed.rating);
     was_libfm = libfm;
     if (libfm && item_offset > 0)
         for (auto& m : out.item) {

@@ -139,3 +139,53 @@ def test_binary_header_checks(cli, tmp_path):
     open(p + ".y", "wb").write(struct.pack("<III", 1, 4, 1))
     r = run(cli, "-train", p, "-test", p, "-dry_run", "1")
     assert r.returncode == 1 and "file id != 2" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------ text reader: sscanf semantics, fast path
+ODD_TRIPLES = [
+    "0\t0\t3.5", "1 2 4", "  2   3    5  ", "3,4,1.5 trailing words", "4;5;2e0", "5\t6\t+3.0", "6 7 0x1p1", "7 8 .5", "9 10 4.\r",
+    "", "   \t ", "10 11 1e-1", "0000012 13 3.25", "+13 14 2", "14 +15 2.5", "15 16 -1.5", "16 17 3.5abc", "17 18 1e5f",
+    "4000000000 19 1", "20 4000000001 2", "123456789 21 3", "22:23:4", "23 24 inf",
+]
+
+
+def test_text_reader_fast_path_equals_sscanf(cli, tmp_path):
+    """The hand-written line parser (csrc/rating_reader.h) must accept exactly what sscanf("%u%c%u%c%lf") / ("%lf %u:%lf %u:%lf")
+    accepts and produce the same values: the same files through SBMF_SLOW_PARSER=1 (every line through sscanf) give the same dump,
+    on odd spellings and on a multi-chunk file (> 1 MB, parsed by several threads)."""
+    rs = np.random.RandomState(1)
+
+    def both(train_lines, name):
+        tr = tmp_path / f"{name}.train"
+        tr.write_text("\n".join(train_lines) + "\n")
+        te = tmp_path / f"{name}.test"
+        te.write_text(train_lines[0] + "\n")
+        outs = []
+        for slow in (False, True):
+            dump = str(tmp_path / f"{name}.{int(slow)}.dump")
+            env = dict(os.environ, **({"SBMF_SLOW_PARSER": "1"} if slow else {}))
+            env.pop("SBMF_SLOW_PARSER", None) if not slow else None
+            r = subprocess.run([cli, "-train", str(tr), "-test", str(te), "-dry_run", "1", "-dump_triples", dump], capture_output=True, text=True, env=env)
+            outs.append((r.returncode, r.stdout, r.stderr, open(dump).read() if os.path.exists(dump) else None))
+        assert outs[0] == outs[1], name
+        return outs[0]
+
+    rc, out, err, dump = both(ODD_TRIPLES, "odd")
+    assert rc == 0, err
+    rows = [ln.split("\t") for ln in dump.splitlines()]
+    assert len(rows) == len([ln for ln in ODD_TRIPLES if ln.strip()])        # every non-blank line is a rating for sscanf
+    assert rows[0] == ["0", "0", "3.5"] and rows[3] == ["3", "4", "1.5"] and rows[6] == ["6", "7", "2"] and rows[19][:2] == ["22", "23"]
+    libfm = ["3.5 0:1 60:1", " 4  1:1   61:1  ", "1e0 2:1 62:1 tail", "+2 3:1.0 63:1", "0x1p1 4:1 64:1", "2.5\t5:1\t65:1\r", "", "3 6:1 66:+1"]
+    rc, out, err, dump = both(libfm, "libfm")
+    assert rc == 0, err
+    assert len(dump.splitlines()) == 7
+    big = [f"{u}\t{i}\t{r}" for u, i, r in zip(np.sort(rs.randint(0, 5000, 150000)), rs.randint(0, 3000, 150000), rs.randint(1, 11, 150000) / 2.0)]
+    big[70000] = "  " + big[70000].replace("\t", "  ") + " \r"
+    rc, out, err, dump = both(big, "big")
+    assert rc == 0 and out.splitlines()[0] == "number rows =150000", err
+    # malformed lines are reported with the same (1-based, physical) line number by both parsers, also deep inside a large file
+    for bad_at, bad in ((3, "1::2::3"), (100001, "12 x 3"), (149999, "7 8")):
+        lines = list(big)
+        lines[bad_at - 1] = bad
+        rc, out, err, dump = both(lines, f"bad{bad_at}")
+        assert rc == 1 and f"malformed rating line {bad_at} " in err, err
