@@ -395,7 +395,7 @@ int main(int argc, char** argv)
             if (first_iter + T > cfg.burn_in) ck(sbmf_cuda_get_pred(h, pred.data()), h, "get_pred");
             std::ofstream o(cmd.get(p_out, "").c_str());
             if (!o.is_open()) throw "unable to open " + cmd.get(p_out, "");
-            for (float v : pred) o << (double)v << std::endl;                               // DVector::save, matrix.h:268-277
+            for (float v : pred) o << (double)v << "\n";   // the bytes of DVector::save (matrix.h:268-277), without its flush per line
         }
         if (cmd.has(p_save)) {
             sbmf_state st;
