@@ -27,6 +27,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <fstream>
 #include <iostream>
@@ -145,13 +146,18 @@ void read_binary(const std::string& path, Ratings& out)
     out.rating.resize(fh.num_rows);
     fy.read(reinterpret_cast<char*>(out.rating.data()), (std::streamsize)fh.num_rows * 4);
     if (!fy) throw "" + path + ".y: truncated";
-    for (uint32_t r = 0; r < fh.num_rows; ++r) {
-        struct { uint32_t size; uint32_t id0; float v0; uint32_t id1; float v1; } row;
-        static_assert(sizeof(row) == 20, "row layout");
-        fx.read(reinterpret_cast<char*>(&row), sizeof(row));
-        if (!fx || row.size != 2) throw "" + path + ".x: row " + std::to_string(r) + " does not have exactly two entries";
-        out.user[r] = row.id0;
-        out.item[r] = row.id1;
+    struct Row { uint32_t size; uint32_t id0; float v0; uint32_t id1; float v1; };
+    static_assert(sizeof(Row) == 20, "row layout");
+    std::vector<Row> rows(1u << 20);   // 20 MB at a time
+    for (uint64_t r0 = 0; r0 < fh.num_rows; r0 += rows.size()) {
+        const uint64_t cnt = std::min<uint64_t>(rows.size(), fh.num_rows - r0);
+        fx.read(reinterpret_cast<char*>(rows.data()), (std::streamsize)(cnt * sizeof(Row)));
+        const uint64_t got = (uint64_t)fx.gcount() / sizeof(Row);
+        for (uint64_t i = 0; i < cnt; ++i) {
+            if (i >= got || rows[i].size != 2) throw "" + path + ".x: row " + std::to_string(r0 + i) + " does not have exactly two entries";
+            out.user[r0 + i] = rows[i].id0;
+            out.item[r0 + i] = rows[i].id1;
+        }
     }
 }
 
