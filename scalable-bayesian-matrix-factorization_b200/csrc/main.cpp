@@ -20,7 +20,9 @@
 //                            in the CWD with one running-mean test RMSE per line; -task r; -verbosity n; -help
 //     extensions: -do_sampling 0 (conditional-mean updates; libFM's do_sample=false), -stdev_mode ref|sqrt,
 //       -burn_in n, -rebuild_every n, -device n, -item_offset n|auto (libFM text/binary: item feature id - offset = item id),
-//       -dump_triples F (write the parsed train triples), -dry_run 1 (parse, print the header lines, stop before touching a GPU)
+//       -dump_triples F (write the parsed train triples), -dry_run 1 (parse, print the header lines, stop before touching a GPU),
+//       -save_state F / -load_state F (checkpoint after the last sweep / continue a chain: sbmf_cuda_set_state, csrc/checkpoint.cpp),
+//       -dump_xt F (the transposed design matrix of the training data in libFM's binary format, as tools/transpose writes it)
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
