@@ -130,16 +130,50 @@ __device__ __forceinline__ int reduce_scatter_base(int lane)
 {
     return ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6 + ((lane >> 1) & 1) * 3;
 }
+#ifndef SBMF_FFMA2
+#define SBMF_FFMA2 0
+#endif
+// two independent fp32 additions in one instruction (sm_100 add.rn.f32x2, SASS FADD2): same sums as two FADD (FFMA2=2 builds)
+__device__ __forceinline__ void add2(float& x0, float& x1, float a0, float a1, float b0, float b1)
+{
+#if SBMF_FFMA2 >= 2
+    asm("{ .reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd; }"
+        : "=f"(x0), "=f"(x1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+#else
+    x0 = a0 + b0;
+    x1 = a1 + b1;
+#endif
+}
 template <int OFF, int HALF>
 __device__ __forceinline__ void reduce_scatter_step(float (&v)[48], int lane)
 {
     const bool up = (lane & OFF) != 0;
+#if SBMF_FFMA2 >= 2
+#pragma unroll
+    for (int i = 0; i + 1 < HALF; i += 2) {   // the packed build adds the kept and the received halves two at a time
+        const float s0 = up ? v[i] : v[i + HALF], s1 = up ? v[i + 1] : v[i + 1 + HALF];
+        const float k0 = up ? v[i + HALF] : v[i], k1 = up ? v[i + 1 + HALF] : v[i + 1];
+        add2(v[i], v[i + 1], k0, k1, __shfl_xor_sync(0xffffffffu, s0, OFF), __shfl_xor_sync(0xffffffffu, s1, OFF));
+    }
+    if (HALF & 1) {
+        constexpr int i = HALF - 1;
+        const float send = up ? v[i] : v[i + HALF];
+        const float keep = up ? v[i + HALF] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+#else
 #pragma unroll
     for (int i = 0; i < HALF; ++i) {
         const float send = up ? v[i] : v[i + HALF];
         const float keep = up ? v[i + HALF] : v[i];
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
     }
+#endif
 }
 __device__ __forceinline__ void warp_reduce_scatter48(float (&v)[48], int lane)
 {

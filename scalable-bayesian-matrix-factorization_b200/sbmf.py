@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsbmf_cuda.so")
+# SBMF_LIB_PATH: developer knob for A/B runs of differently built libraries (tools/r2_ffma2.sh); the product is lib/libsbmf_cuda.so
+LIB_PATH = os.environ.get("SBMF_LIB_PATH") or os.path.join(HERE, "lib", "libsbmf_cuda.so")
 
 SAMPLE_REF, SAMPLE_SQRT, SAMPLE_ZERO = 0, 1, 2
 HYPER_REF_T, HYPER_NG_S, HYPER_NG = 0, 1, 2

@@ -1,35 +1,41 @@
 #!/bin/bash
-# tools/r2_ffma2.sh -- A/B of the packed (FFMA2) Gram accumulation on one B200 (gpurun -- 'bash tools/r2_ffma2.sh'); outputs in gpurun_out/.
-# The two builds must produce IDENTICAL chains (the packed form performs the same fused multiply-adds per sum, csrc/gram.cuh):
-# the script compares the RMSE history and the final factors of both builds bit for bit before it compares their speed.
+# tools/r2_ffma2.sh -- A/B of the packed-FP32 builds (csrc/gram.cuh: FFMA2=1 packed FMAs, FFMA2=2 also packed adds) on one B200.
+#   here (no GPU):   bash tools/r2_ffma2.sh build      -> scalable-.../lib_f{0,1,2}/libsbmf_cuda.so (git-ignored, travel with gpurun)
+#   on the GPU box:  gpurun -- 'bash tools/r2_ffma2.sh' -> gpurun_out/ffma2_*
+# The builds must produce IDENTICAL chains (every sum receives the same fused multiply-adds / additions in the same order): the
+# script compares RMSE history and final factors bit for bit before it compares speed.
 set -u
-O=gpurun_out; mkdir -p $O
 P=scalable-bayesian-matrix-factorization_b200
-run_one() {   # $1 = tag
-  python - "$1" <<'PY'
+if [ "${1:-}" = "build" ]; then
+  for lvl in 0 1 2; do
+    make -C $P -j8 FFMA2=$lvl OBJ=build_f$lvl LIB=lib_f$lvl/libsbmf_cuda.so lib_f$lvl/libsbmf_cuda.so 2>&1 | grep -i "error" ; ls -la $P/lib_f$lvl/libsbmf_cuda.so
+  done
+  exit 0
+fi
+O=gpurun_out; mkdir -p $O
+for lvl in 0 1 2; do
+  export SBMF_LIB_PATH=$PWD/$P/lib_f$lvl/libsbmf_cuda.so
+  python - "$lvl" <<'PY'
 import sys, numpy as np
 sys.path.insert(0, "scalable-bayesian-matrix-factorization_b200"); import sbmf
-tag = sys.argv[1]
+lvl = sys.argv[1]
 d = sbmf.synth_generate(71567, 10681, 11111111)
 m = sbmf.SbmfModel(K=100, seed=5)
 m.set_train(d["train_user"], d["train_item"], d["train_rating"], 71567, 10681); m.set_test(d["test_user"], d["test_item"], d["test_rating"])
 m.init_factors(); m.sweep(4)
 st = m.get_state(with_E=False); r, _ = m.rmse_history(0, 4)
-np.savez(f"gpurun_out/ffma2_{tag}.npz", U=st["U"], V=st["V"], b_i=st["b_i"], b_j=st["b_j"], r=r)
-print(tag, "rmse", r)
+np.savez(f"gpurun_out/ffma2_chain_{lvl}.npz", U=st["U"], V=st["V"], b_i=st["b_i"], b_j=st["b_j"], r=r)
+print("FFMA2 =", lvl, "rmse", r)
 PY
-}
-make -C $P clean >/dev/null; make -C $P -j8 FFMA2=0 >/dev/null 2>&1; run_one scalar
-python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/ffma2_bench_scalar.json 2> $O/ffma2_bench_scalar.err
-make -C $P clean >/dev/null; make -C $P -j8 FFMA2=1 >/dev/null 2>&1; run_one packed
-python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/ffma2_bench_packed.json 2> $O/ffma2_bench_packed.err
-python -m pytest tests/test_parity_gpu.py -m gpu -x -q > $O/ffma2_parity_packed.log 2>&1; echo "parity (packed build) rc=$?"; tail -2 $O/ffma2_parity_packed.log
+  python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/ffma2_bench_$lvl.json 2> $O/ffma2_bench_$lvl.err
+done
 python - <<'PY'
 import json, numpy as np
-a, b = np.load("gpurun_out/ffma2_scalar.npz"), np.load("gpurun_out/ffma2_packed.npz")
-print("bit-identical chains:", all(np.array_equal(a[k], b[k]) for k in a.files))
-for t in ("scalar", "packed"):
-    d = json.loads(open(f"gpurun_out/ffma2_bench_{t}.json").read().strip().splitlines()[-1])
-    print(t, "%.3f ms/sweep" % d["ms_per_step"], d["phases_ms"])
+a = np.load("gpurun_out/ffma2_chain_0.npz")
+for lvl in (1, 2):
+    b = np.load(f"gpurun_out/ffma2_chain_{lvl}.npz")
+    print(f"FFMA2={lvl}: chain bit-identical to the scalar build:", all(np.array_equal(a[k], b[k]) for k in a.files))
+for lvl in (0, 1, 2):
+    d = json.loads(open(f"gpurun_out/ffma2_bench_{lvl}.json").read().strip().splitlines()[-1])
+    print(f"FFMA2={lvl}", "%.3f ms/sweep" % d["ms_per_step"], d["phases_ms"])
 PY
-make -C $P clean >/dev/null; make -C $P -j8 >/dev/null 2>&1   # back to the default build
