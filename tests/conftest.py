@@ -43,6 +43,16 @@ def ml100k():
     return out
 
 
+@pytest.fixture(scope="session")
+def ml100k_split():
+    """the reference's second real fixture, data/m1m/m100k (80k/20k split, item ids not re-based: items 0..942 are empty rows)"""
+    d = np.load(os.path.join(GOLDEN, "ml100k_split.npz"))
+    out = {k: d[k].astype(np.uint32 if "rating" not in k else np.float32) for k in d.files}
+    out["num_users"] = int(max(out["train_user"].max(), out["test_user"].max())) + 1
+    out["num_items"] = int(max(out["train_item"].max(), out["test_item"].max())) + 1
+    return out
+
+
 def _triples(path):
     a = np.loadtxt(path, dtype=np.float64, ndmin=2)
     return a[:, 0].astype(np.uint32), a[:, 1].astype(np.uint32), a[:, 2].astype(np.float32)
