@@ -10,6 +10,8 @@
  *   SBMF_SHIM_MODE=zero     the zero-noise definition of SURVEY.md 8(c): ran_gaussian(m,s) -> m, ran_gamma(a,b) -> a/b,
  *                           except the first SBMF_SHIM_LIVE_INIT two-argument gaussian calls (factor initialisation,
  *                           [T]:239-250), which stay live so the factors are not identically zero.
+ *   SBMF_SHIM_SEED=<n>      srand(n) before the first sampler call.  [T] and [S] never seed (glibc seed 1, the default here);
+ *                           libFM's main() calls srand(time(NULL)) ([L]:124-125), which this overrides so its runs repeat.
  * In the default mode (rand) the draws are the reference's own algorithms (rand_samplers.h restates [R]).
  */
 #ifndef SBMF_SHIM_RANDOM_H_
@@ -26,8 +28,12 @@ struct sbmf_shim_state {
     long live_init;
     long n_gauss2;
     FILE* log;
-    sbmf_shim_state() : zero(0), live_init(0), n_gauss2(0), log(NULL)
+    int seed_pending;
+    unsigned seed;
+    sbmf_shim_state() : zero(0), live_init(0), n_gauss2(0), log(NULL), seed_pending(0), seed(1)
     {
+        const char* sd = getenv("SBMF_SHIM_SEED");
+        if (sd && sd[0]) { seed_pending = 1; seed = (unsigned)strtoul(sd, NULL, 10); }
         const char* m = getenv("SBMF_SHIM_MODE");
         zero = (m && !strcmp(m, "zero"));
         const char* li = getenv("SBMF_SHIM_LIVE_INIT");
@@ -36,6 +42,7 @@ struct sbmf_shim_state {
         if (lp && lp[0]) log = fopen(lp, "wb");
     }
     ~sbmf_shim_state() { if (log) fclose(log); }
+    void first_use() { if (seed_pending) { srand(seed); seed_pending = 0; } }
     void rec(double tag, double a, double b)
     {
         /* flushed per record: the reference can die in its own cleanup ([T]:648-666 delete[]s never-allocated rows
@@ -49,6 +56,7 @@ inline double ran_uniform() { return ran_uniform_rand(); }
 inline double ran_gaussian() { return ran_gaussian_leva(); }
 inline double ran_gaussian(double mean, double stdev)
 {
+    sbmf_shim.first_use();
     sbmf_shim.rec(0.0, mean, stdev);
     long idx = sbmf_shim.n_gauss2++;
     if (sbmf_shim.zero && idx >= sbmf_shim.live_init) return mean;
@@ -58,6 +66,7 @@ inline double ran_gaussian(double mean, double stdev)
 inline double ran_gamma(double alpha) { return ran_gamma_mt_rand(alpha); }
 inline double ran_gamma(double alpha, double beta)
 {
+    sbmf_shim.first_use();
     sbmf_shim.rec(1.0, alpha, beta);
     if (sbmf_shim.zero) return alpha / beta;
     return ran_gamma_mt_rand(alpha) / beta;
