@@ -63,6 +63,21 @@ class SynthSpec(C.Structure):
                 ("reserved0", C.c_int32)]
 
 
+FM_SAMPLE_LIVE, FM_SAMPLE_ZERO = 0, 1
+
+
+class FmConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("num_attr", C.c_uint32), ("num_groups", C.c_uint32), ("K", C.c_uint32), ("k0", C.c_int32),
+                ("k1", C.c_int32), ("do_sample", C.c_int32), ("do_multilevel", C.c_int32), ("sample_mode", C.c_int32), ("device", C.c_int32),
+                ("seed", C.c_uint64), ("init_stdev", C.c_double), ("reg0", C.c_double), ("regw", C.c_double), ("regv", C.c_double)]
+
+
+class FmState(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("v", C.c_void_p), ("w_mu", C.c_void_p), ("w_lambda", C.c_void_p), ("v_mu", C.c_void_p),
+                ("v_lambda", C.c_void_p), ("e", C.c_void_p), ("pred_sum", C.c_void_p), ("w0", C.c_double), ("alpha", C.c_double),
+                ("iterations", C.c_uint32)]
+
+
 class SbmfError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"sbmf_cuda error {code}: {msg}")
@@ -120,6 +135,24 @@ def load_library(path=None):
     lib.sbmf_cuda_synth_host_free.argtypes = [C.c_void_p]
     lib.sbmf_cuda_synth_host_free.restype = None
     lib.sbmf_cuda_synth_host_last_error.restype = C.c_char_p
+    # general FM Gibbs (include/sbmf_fm_cuda.h)
+    lib.sbmf_fm_config_default.argtypes = [P(FmConfig)]
+    lib.sbmf_fm_create.argtypes = [P(FmConfig), P(C.c_void_p)]
+    lib.sbmf_fm_destroy.argtypes = [C.c_void_p]
+    lib.sbmf_fm_last_error.argtypes = [C.c_void_p]
+    lib.sbmf_fm_last_error.restype = C.c_char_p
+    lib.sbmf_fm_set_groups.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_set_train.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
+    lib.sbmf_fm_set_test.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
+    lib.sbmf_fm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_learn.argtypes = [C.c_void_p, C.c_uint32]
+    lib.sbmf_fm_rmse_history.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_predict.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_get_state.argtypes = [C.c_void_p, P(FmState)]
+    lib.sbmf_fm_get_columns.argtypes = [C.c_void_p] + [C.c_void_p] * 3
+    lib.sbmf_fm_get_runs.argtypes = [C.c_void_p, P(C.c_uint32), C.c_void_p]
+    lib.sbmf_fm_plan_runs.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_plan_runs.restype = C.c_uint32
     if path is None:
         _lib = lib
     return lib
@@ -272,6 +305,107 @@ class SbmfModel:
 
     def synchronize(self):
         self._ck(self.lib.sbmf_cuda_synchronize(self.h))
+
+
+class FmModel:
+    """One handle of the general FM Gibbs sampler (include/sbmf_fm_cuda.h): libFM's fm_learn interface -- init / learn / predict
+    (src/libfm/src/fm_learn.h:80, 150, 191) -- on a design matrix in row form: dict(row_ptr int64, attr uint32, x float32, y float32)."""
+
+    def __init__(self, num_attr, K, attr_group=None, **kw):
+        self.lib = load_library()
+        self.cfg = FmConfig()
+        self.lib.sbmf_fm_config_default(C.byref(self.cfg))
+        self.group = None if attr_group is None else _u32(attr_group)
+        self.cfg.num_attr, self.cfg.K = int(num_attr), int(K)
+        self.cfg.num_groups = 1 if self.group is None else int(self.group.max()) + 1
+        for k, v in kw.items():
+            setattr(self.cfg, k, v)
+        self.h = C.c_void_p()
+        rc = self.lib.sbmf_fm_create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            raise SbmfError(rc, self.lib.sbmf_fm_last_error(None).decode())
+        self.p, self.K, self.G = self.cfg.num_attr, self.cfg.K, self.cfg.num_groups
+        self.n = self.nt = self.nnz = 0
+        if self.group is not None:
+            self._ck(self.lib.sbmf_fm_set_groups(self.h, _ptr(self.group)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SbmfError(rc, self.lib.sbmf_fm_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.sbmf_fm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _mat(m):
+        return (np.ascontiguousarray(m["row_ptr"], dtype=np.int64), _u32(m["attr"]), _f32(m["x"]), _f32(m["y"]))
+
+    def set_train(self, m):
+        rp, at, x, y = self._mat(m)
+        self._ck(self.lib.sbmf_fm_set_train(self.h, y.size, _ptr(rp), _ptr(at), _ptr(x), _ptr(y)))
+        self.n, self.nnz = int(y.size), int(rp[-1])
+
+    def set_test(self, m):
+        rp, at, x, y = self._mat(m)
+        self._ck(self.lib.sbmf_fm_set_test(self.h, y.size, _ptr(rp), _ptr(at), _ptr(x), _ptr(y)))
+        self.nt = int(y.size)
+
+    def init(self, w=None, v=None):
+        w = None if w is None else _f32(w)
+        v = None if v is None else _f32(v)
+        assert w is None or w.shape == (self.p,)
+        assert v is None or v.shape == (self.K, self.p)
+        self._ck(self.lib.sbmf_fm_init(self.h, _ptr(w), _ptr(v)))
+
+    def learn(self, iters=1):
+        self._ck(self.lib.sbmf_fm_learn(self.h, iters))
+
+    def rmse_history(self, first, count):
+        a, b = np.zeros(count), np.zeros(count)
+        self._ck(self.lib.sbmf_fm_rmse_history(self.h, first, count, _ptr(a), _ptr(b)))
+        return a, b
+
+    def predict(self):
+        out = np.zeros(self.nt, dtype=np.float32)
+        self._ck(self.lib.sbmf_fm_predict(self.h, _ptr(out)))
+        return out
+
+    def get_state(self):
+        arr = {"w": np.zeros(self.p, dtype=np.float32), "v": np.zeros((self.K, self.p), dtype=np.float32), "w_mu": np.zeros(self.G),
+               "w_lambda": np.zeros(self.G), "v_mu": np.zeros((self.G, self.K)), "v_lambda": np.zeros((self.G, self.K)),
+               "e": np.zeros(self.n, dtype=np.float32), "pred_sum": np.zeros(max(self.nt, 1))}
+        st = FmState()
+        for k, a in arr.items():
+            setattr(st, k, a.ctypes.data)
+        self._ck(self.lib.sbmf_fm_get_state(self.h, C.byref(st)))
+        arr["pred_sum"] = arr["pred_sum"][:self.nt]
+        arr.update(w0=st.w0, alpha=st.alpha, iterations=st.iterations)
+        return arr
+
+    def get_columns(self):
+        cp, ci, x = np.zeros(self.p + 1, dtype=np.int64), np.zeros(max(self.nnz, 1), dtype=np.uint32), np.zeros(max(self.nnz, 1), dtype=np.float32)
+        self._ck(self.lib.sbmf_fm_get_columns(self.h, _ptr(cp), _ptr(ci), _ptr(x)))
+        return {"col_ptr": cp, "case": ci[:self.nnz], "x": x[:self.nnz]}
+
+    def get_runs(self):
+        n, rb = C.c_uint32(0), np.zeros(self.p + 1, dtype=np.uint32)
+        self._ck(self.lib.sbmf_fm_get_runs(self.h, C.byref(n), _ptr(rb)))
+        return rb[:n.value + 1]
+
+
+def fm_plan_runs(next_attr):
+    next_attr = _u32(next_attr)
+    out = np.zeros(next_attr.size + 1, dtype=np.uint32)
+    n = load_library().sbmf_fm_plan_runs(next_attr.size, _ptr(next_attr), _ptr(out))
+    return out[:n + 1]
 
 
 def _state_shapes(I, J, K, N):

@@ -18,17 +18,23 @@ def built():
     return os.path.join(PKG, "lib", "libsbmf_cuda.so")
 
 
+FM_HEADER = os.path.join(ROOT, "include", "sbmf_fm_cuda.h")
+
+
 def declared_symbols():
-    src = open(HEADER).read()
+    src = open(HEADER).read() + open(FM_HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(sbmf_cuda_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(sbmf_(?:cuda|fm)_\w+)\s*\(", src)))
 
 
 def test_header_declares_the_boundary():
     syms = declared_symbols()
     for s in ("sbmf_cuda_create", "sbmf_cuda_set_train", "sbmf_cuda_set_test", "sbmf_cuda_get_layout", "sbmf_cuda_init_factors",
               "sbmf_cuda_sweep", "sbmf_cuda_eval", "sbmf_cuda_get_state", "sbmf_cuda_get_pred", "sbmf_cuda_get_timing",
-              "sbmf_cuda_last_error", "sbmf_cuda_destroy"):
+              "sbmf_cuda_last_error", "sbmf_cuda_destroy",
+              # general FM Gibbs: libFM's fm_learn interface (init / learn / predict)
+              "sbmf_fm_create", "sbmf_fm_set_groups", "sbmf_fm_set_train", "sbmf_fm_set_test", "sbmf_fm_init", "sbmf_fm_learn", "sbmf_fm_predict",
+              "sbmf_fm_rmse_history", "sbmf_fm_get_state", "sbmf_fm_get_columns", "sbmf_fm_get_runs", "sbmf_fm_last_error", "sbmf_fm_destroy"):
         assert s in syms
 
 
@@ -41,7 +47,7 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_header_compiles_as_c(tmp_path):
     c = tmp_path / "t.c"
-    c.write_text('#include "sbmf_cuda.h"\nint main(void){ sbmf_config c; return (int)sizeof(c) == 0; }\n')
+    c.write_text('#include "sbmf_cuda.h"\n#include "sbmf_fm_cuda.h"\nint main(void){ sbmf_config c; sbmf_fm_config f; return (int)(sizeof(c) + sizeof(f)) == 0; }\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(c), "-o", str(tmp_path / "t.o")], check=True)
 
 
@@ -61,6 +67,19 @@ def test_ctypes_struct_layout_matches_header(built, tmp_path):
     assert got == want
 
 
+def test_fm_ctypes_struct_layout_matches_header(built, tmp_path):
+    import sys
+    sys.path.insert(0, PKG)
+    import sbmf
+    c = tmp_path / "szfm.c"
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sbmf_fm_cuda.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(sbmf_fm_config),'
+                 ' sizeof(sbmf_fm_state), offsetof(sbmf_fm_config, seed), offsetof(sbmf_fm_config, regv), offsetof(sbmf_fm_state, w0));return 0;}\n')
+    exe = tmp_path / "szfm"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [ctypes.sizeof(sbmf.FmConfig), ctypes.sizeof(sbmf.FmState), sbmf.FmConfig.seed.offset, sbmf.FmConfig.regv.offset, sbmf.FmState.w0.offset]
+
+
 def test_no_cpu_fallback(built):
     """Without a visible GPU, create must FAIL with a message (never silently compute on the CPU)."""
     if os.path.exists("/dev/nvidia0"):
@@ -70,6 +89,9 @@ def test_no_cpu_fallback(built):
     import sbmf
     with pytest.raises(sbmf.SbmfError) as e:
         sbmf.SbmfModel(K=8)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+    with pytest.raises(sbmf.SbmfError) as e:
+        sbmf.FmModel(10, 4)
     assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
 
 

@@ -1,0 +1,25 @@
+"""GPU parity of the general FM Gibbs path (csrc/fm.cu behind include/sbmf_fm_cuda.h) against the fp64 restatement
+of libFM's MCMC learner, which tests/test_fm_oracle.py pins to the unmodified libFM: the transposed design matrix bit-exact,
+zero-noise state within 1e-4 after 10 iterations (MF and general design matrices, K = 0 / 3 / 4 / 20, -method als, no w0 / no w,
+columns of every kernel tier), live chains as distributions, error behaviour.  Cases live in tests/fm_gpu_cases.py and run in a
+process of their own each.
+
+Status: this path was written after the round's GPU budget was spent, so these cases have NOT run on a B200 yet (the formulas and
+the run schedule are checked on the CPU by tests/test_fm_emulation.py).  Until their first hardware run they are non-strict
+xfail: a failure is reported as xfailed, a pass as xpassed, and neither hides behind the rest of the suite."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = ["columns", "zero_mf", "zero_general", "zero_general_k20", "zero_als", "zero_variants", "long_columns", "live", "errors"]
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first run on a B200 pending (written without GPU access)", strict=False)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fm_gpu_case(case):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "fm_gpu_cases.py"), case], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:] + r.stderr[-4000:])
