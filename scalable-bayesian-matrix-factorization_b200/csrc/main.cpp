@@ -18,6 +18,7 @@
 //       -method sbmf|mcmc    sbmf (default): [T]'s stdout.  mcmc: libFM's MCMC front-end outputs instead (fm_learn_mcmc_simultaneous.h:
 //                            57-62, 143-147, 244-245): "#Iter=%3d\tTrain=..\tTest=.." per sweep and the file test_rmse_<k0><k1><K>_mcmc
 //                            in the CWD with one running-mean test RMSE per line; -task r; -verbosity n; -help
+//       -method fm_mcmc|fm_als   libFM's GENERAL FM Gibbs sampler (its -method mcmc / als) on any design matrix: csrc/fm_main.h
 //     extensions: -do_sampling 0 (conditional-mean updates; libFM's do_sample=false), -stdev_mode ref|sqrt,
 //       -burn_in n, -rebuild_every n, -device n, -item_offset n|auto (libFM text/binary: item feature id - offset = item id),
 //       -dump_triples F (write the parsed train triples), -dry_run 1 (parse, print the header lines, stop before touching a GPU),
@@ -39,6 +40,7 @@
 
 #include "rating_reader.h"
 #include "sbmf_cuda.h"
+#include "fm_main.h"
 
 namespace {
 
@@ -222,7 +224,7 @@ int main(int argc, char** argv)
         const std::string p_dim = cmd.reg("dim", "'k0,k1,k2': k2=number of latent dimensions; default=1,1,20");
         const std::string p_init = cmd.reg("init_stdev", "stdev for initialization of the factors; default=0.1");
         const std::string p_iter = cmd.reg("iter", "number of Gibbs sweeps; default=100");
-        const std::string p_method = cmd.reg("method", "learning method (mcmc | sbmf); default=sbmf");
+        const std::string p_method = cmd.reg("method", "learning method (sbmf | mcmc | fm_mcmc | fm_als); default=sbmf");
         const std::string p_verb = cmd.reg("verbosity", "how much infos to print; default=0");
         const std::string p_rlog = cmd.reg("rlog", "write measurements within iterations to a file; default=''");
         const std::string p_seed = cmd.reg("seed", "integer value, default=1");
@@ -239,13 +241,20 @@ int main(int argc, char** argv)
         const std::string p_load = cmd.reg("load_state", "continue the chain from this checkpoint instead of initialising; -iter = number of further sweeps");
         const std::string p_xt = cmd.reg("dump_xt", "write the transposed design matrix of the training data (libFM binary .xt, as tools/transpose writes it) from the device-built layout");
         const std::string p_dry = cmd.reg("dry_run", "1 = parse the inputs, print the header lines and stop (no GPU needed)");
+        // general FM Gibbs (-method fm_mcmc | fm_als, csrc/fm_main.h): libFM's own flags for -method mcmc / als
+        cmd.reg("meta", "fm_mcmc / fm_als: filename with the group id of every attribute, one per line");
+        cmd.reg("regular", "fm_mcmc / fm_als: 'r' or 'r0,r1,r2' = prior precision of w0, start value of the w / v group precisions");
+        cmd.reg("do_multilevel", "fm_mcmc / fm_als: 0 = fixed hyper-parameters; default=1 (fm_als: 0)");
+        cmd.reg("dump_design", "fm_mcmc / fm_als: write the parsed training design matrix (case attribute value target) to this file");
         if (cmd.has(p_help)) {
             cmd.print_help();
             return 0;
         }
         cmd.check();
         const std::string method = cmd.get(p_method, "sbmf");
-        if (method != "sbmf" && method != "mcmc" && method != "MCMC") throw "unknown method " + method + " (this program is the SBMF Gibbs sampler)";
+        if (method == "fm_mcmc" || method == "fm_als") return fm_front::run(cmd, method);   // libFM's general FM Gibbs sampler
+        if (method != "sbmf" && method != "mcmc" && method != "MCMC")
+            throw "unknown method " + method + " (sbmf | mcmc: the SBMF Gibbs sampler; fm_mcmc | fm_als: libFM's general FM Gibbs sampler)";
         if (cmd.get(p_task, "r") != "r") throw std::string("only -task r is supported");
         uint32_t K = 20;
         if (cmd.has(p_dim)) {

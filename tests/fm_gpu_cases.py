@@ -206,6 +206,34 @@ def case_errors():
     m.close()
 
 
+def case_cli():
+    """bin/sbmf -method fm_mcmc: libFM's command line and outputs ("#Iter=" lines, test_rmse_<k0><k1><K>_mcmc, -out) carry the chain of
+    the binding with the same seed, value for value"""
+    import re
+    import subprocess
+    import tempfile
+    tr, te, group = load_fixture("fm_general")
+    p = fmo.num_attributes(tr, te)
+    m = sbmf.FmModel(p, 3, attr_group=group, seed=3)
+    m.set_train(tr)
+    m.set_test(te)
+    m.init()
+    m.learn(5)
+    a, b = m.rmse_history(0, 5)
+    pred = m.predict()
+    m.close()
+    cli = os.path.join(ROOT, "scalable-bayesian-matrix-factorization_b200", "bin", "sbmf")
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([cli, "-method", "fm_mcmc", "-train", os.path.join(GOLDEN, "fm_general.train"), "-test", os.path.join(GOLDEN, "fm_general.test"),
+                            "-meta", os.path.join(GOLDEN, "fm_general.meta"), "-dim", "1,1,3", "-iter", "5", "-seed", "3", "-out", "pred.txt"],
+                           capture_output=True, text=True, cwd=tmp)
+        assert r.returncode == 0, r.stderr
+        rows = re.findall(r"^#Iter=\s*(\d+)\tTrain=(\S+)\tTest=(\S+)$", r.stdout, flags=re.M)
+        assert [x[1] for x in rows] == [f"{v:g}" for v in a] and [x[2] for x in rows] == [f"{v:g}" for v in b], (rows, a, b)
+        assert open(os.path.join(tmp, "test_rmse_113_mcmc")).read().split() == [f"{v:g}" for v in b]
+        assert open(os.path.join(tmp, "pred.txt")).read().split() == [f"{float(v):g}" for v in pred]
+
+
 CASES = {k[5:]: v for k, v in dict(globals()).items() if k.startswith("case_")}
 
 if __name__ == "__main__":

@@ -189,3 +189,63 @@ def test_text_reader_fast_path_equals_sscanf(cli, tmp_path):
         lines[bad_at - 1] = bad
         rc, out, err, dump = both(lines, f"bad{bad_at}")
         assert rc == 1 and f"malformed rating line {bad_at} " in err, err
+
+
+# ---- general FM Gibbs front-end (-method fm_mcmc | fm_als, csrc/fm_main.h): the readers, on CPU ----------------------------------
+def _dump(cli, tmp_path, *args):
+    out = str(tmp_path / "design.txt")
+    r = run(cli, *args, "-dry_run", "1", "-dump_design", out, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    return r.stdout, np.loadtxt(out, ndmin=2)
+
+
+def test_fm_front_end_reads_general_libfm_text(cli, tmp_path):
+    """the design matrix parsed by the host program == the reader the parity tests use (Data.h:184-278 semantics), attribute
+    count = libFM's max id + 2 ([L]:326), groups from -meta"""
+    import fm_oracle_py as fmo
+    G = os.path.join(ROOT, "tests", "golden")
+    tr = fmo.read_libfm(os.path.join(G, "fm_general.train"))
+    te = fmo.read_libfm(os.path.join(G, "fm_general.test"))
+    stdout, d = _dump(cli, tmp_path, "-method", "fm_mcmc", "-train", os.path.join(G, "fm_general.train"), "-test", os.path.join(G, "fm_general.test"),
+                      "-meta", os.path.join(G, "fm_general.meta"), "-dim", "1,1,3")
+    assert f"#cases train=600\ttest=150\t#attr={fmo.num_attributes(tr, te)}\t#groups=4" in stdout
+    rows = np.repeat(np.arange(600), np.diff(tr["row_ptr"]))
+    assert np.array_equal(d[:, 0], rows) and np.array_equal(d[:, 1], tr["attr"])
+    assert np.array_equal(d[:, 2].astype(np.float32), tr["x"]) and np.array_equal(d[:, 3].astype(np.float32), tr["y"][rows])
+    # comments, blank lines and trailing blanks are skipped like Data.h:196-197, 209-212; garbage is an error like libFM's throw
+    t = tmp_path / "c.train"
+    t.write_text("# header\n\n4.5 3:1 7:0.5  \n  2 0:1\t#tail\n")
+    _, d = _dump(cli, tmp_path, "-method", "fm_als", "-train", str(t), "-test", str(t))
+    assert d.tolist() == [[0, 3, 1, 4.5], [0, 7, 0.5, 4.5], [1, 0, 1, 2]]
+    t.write_text("4.5 3:1 oops\n")
+    r = run(cli, "-method", "fm_mcmc", "-train", str(t), "-test", str(t), "-dry_run", "1")
+    assert r.returncode == 1 and "ERROR: cannot parse line" in r.stderr
+    r = run(cli, "-method", "fm_mcmc", "-train", os.path.join(G, "fm_general.train"), "-test", os.path.join(G, "fm_general.test"), "-regular", "1,2",
+            "-dry_run", "1")
+    assert r.returncode == 1 and "-regular" in r.stderr
+
+
+def test_fm_front_end_reads_general_libfm_binary(cli, tmp_path):
+    """F.x / F.y in the format of fmatrix.h:34-52 (rows of any length) parse to the same design matrix as the text file"""
+    import struct
+    import fm_oracle_py as fmo
+    G = os.path.join(ROOT, "tests", "golden")
+    tr = fmo.read_libfm(os.path.join(G, "fm_general.train"))
+    base = str(tmp_path / "bin.train")
+    with open(base + ".x", "wb") as f:
+        f.write(struct.pack("<IIQII", 2, 4, int(tr["row_ptr"][-1]), tr["y"].size, int(tr["attr"].max()) + 1))
+        for r in range(tr["y"].size):
+            a, b = tr["row_ptr"][r], tr["row_ptr"][r + 1]
+            f.write(struct.pack("<I", b - a))
+            for k in range(a, b):
+                f.write(struct.pack("<If", int(tr["attr"][k]), float(tr["x"][k])))
+    with open(base + ".y", "wb") as f:
+        f.write(struct.pack("<III", 1, 4, tr["y"].size))
+        f.write(tr["y"].astype("<f4").tobytes())
+    _, d_bin = _dump(cli, tmp_path, "-method", "fm_mcmc", "-train", base, "-test", base)
+    _, d_txt = _dump(cli, tmp_path, "-method", "fm_mcmc", "-train", os.path.join(G, "fm_general.train"), "-test", os.path.join(G, "fm_general.test"))
+    assert np.array_equal(d_bin, d_txt)
+    with open(base + ".x", "r+b") as f:
+        f.truncate(200)
+    r = run(cli, "-method", "fm_mcmc", "-train", base, "-test", base, "-dry_run", "1")
+    assert r.returncode == 1 and "truncated" in r.stderr
