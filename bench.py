@@ -338,6 +338,9 @@ def main():
         prof = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if os.path.exists(prof):
             roof["traffic"] = json.load(open(prof)).get("heavy_accumulate_kernel<2,2>", {}).get("dram_bytes_per_launch")
+            if roof["traffic"]:   # what the kernel really moves through HBM (ncu dram bytes of one launch) at the live launch time
+                roof["dram_achieved_gbs"] = roof["traffic"] / (us * 1e-6) / 1e9
+                roof["dram_frac"] = roof["dram_achieved_gbs"] / peak
         # the bound this kernel actually runs against: random 32-byte sector gathers from an L2-resident table, one LDG.E.256 per
         # lane.  tools/gather_probe.cu measures that access form alone on B200: 0.88-0.90 sectors per clock per SM (8.2-8.3 TB/s).
         try:
