@@ -44,8 +44,28 @@ enum FmSite : uint32_t {
 };
 
 constexpr double ALPHA_0 = 1.0, GAMMA_0 = 1.0, BETA_0 = 1.0, MU_0 = 0.0, W0_MEAN_0 = 0.0;   // [G]:1099-1106
-constexpr uint32_t WARP_COL_MAX = 512, BLOCK_COL_MAX = 16384, SLICE_LEN = 8192, HYPER_CHUNK = 4096, HIST_CAP = 1u << 16;
-constexpr int BLOCK_T = 256;
+// tier limits; the CPU execution of these kernels (tools/simt_emu.h, tests/test_fm_simt_emulation.py) shrinks them with -D so that
+// the small fixtures reach every tier
+#ifndef FM_WARP_COL_MAX
+#define FM_WARP_COL_MAX 512
+#define FM_BLOCK_COL_MAX 16384
+#define FM_SLICE_LEN 8192
+#define FM_HYPER_CHUNK 4096
+#endif
+#ifndef FM_BLOCK_T
+#define FM_BLOCK_T 256
+#endif
+constexpr uint32_t WARP_COL_MAX = FM_WARP_COL_MAX, BLOCK_COL_MAX = FM_BLOCK_COL_MAX, SLICE_LEN = FM_SLICE_LEN, HYPER_CHUNK = FM_HYPER_CHUNK,
+                   HIST_CAP = 1u << 16;
+constexpr int BLOCK_T = FM_BLOCK_T;   // threads per CTA of the streaming kernels (a multiple of 32)
+
+// kernel launch: <<<grid, block, 0, stream>>> on the GPU; under SBMF_SIMT_EMU (a test-only host build of this file against
+// tools/emu_include) the same kernel body is executed block by block on host threads
+#ifdef SBMF_SIMT_EMU
+#define FM_LAUNCH(kernel, grid, block, stream, ...) simt::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#else
+#define FM_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
 
 struct Scal {
     double w0, alpha, w0_delta;
@@ -679,18 +699,18 @@ static int build_matrix(Model& m, RowForm& r, uint32_t n, const int64_t* row_ptr
     CKC(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
     const uint32_t g = grid_for(m, nnz);
     CKC(cudaMemsetAsync(d_dup, 0, 4, st));
-    fill_u32_kernel<<<(m.p + 255) / 256, 256, 0, st>>>(d_next, m.p, UINT32_MAX);
+    FM_LAUNCH(fill_u32_kernel, (m.p + 255) / 256, 256, st, d_next, m.p, UINT32_MAX);
     if (nnz) {
-        entry_row_kernel<<<g, BLOCK_T, 0, st>>>(r.row_ptr, n, nnz, d_row);
-        iota_kernel<<<g, BLOCK_T, 0, st>>>(d_iota, nnz);
+        FM_LAUNCH(entry_row_kernel, g, BLOCK_T, st, r.row_ptr, n, nnz, d_row);
+        FM_LAUNCH(iota_kernel, g, BLOCK_T, st, d_iota, nnz);
         // column form: stable sort of the entries by attribute (entries are in case order)
         CKC(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_attr, d_key, d_iota, d_ord, (int)nnz, 0, 32, st));
-        gather_u32_kernel<<<g, BLOCK_T, 0, st>>>(d_row, d_ord, d_case, nnz);
-        gather_f32_kernel<<<g, BLOCK_T, 0, st>>>(d_x, d_ord, d_xc, nnz);
+        FM_LAUNCH(gather_u32_kernel, g, BLOCK_T, st, d_row, d_ord, d_case, nnz);
+        FM_LAUNCH(gather_f32_kernel, g, BLOCK_T, st, d_x, d_ord, d_xc, nnz);
     }
     if (train) {
         CKC(dmalloc(&m.col_ptr, (size_t)m.p + 1)); CKC(dmalloc(&m.case_id, z)); CKC(dmalloc(&m.xc, z));
-        seg_ptr_kernel<<<(m.p + 1 + 255) / 256, 256, 0, st>>>(d_key, nnz, m.p, m.col_ptr);
+        FM_LAUNCH(seg_ptr_kernel, (m.p + 1 + 255) / 256, 256, st, d_key, nnz, m.p, m.col_ptr);
         if (nnz) {
             CKC(cudaMemcpyAsync(m.case_id, d_case, z * 4, cudaMemcpyDeviceToDevice, st));
             CKC(cudaMemcpyAsync(m.xc, d_xc, z * 4, cudaMemcpyDeviceToDevice, st));
@@ -700,10 +720,10 @@ static int build_matrix(Model& m, RowForm& r, uint32_t n, const int64_t* row_ptr
         // row form with ascending attributes: stable sort of the column form by case (d_key = attribute of every column-form entry)
         uint32_t* d_case_sorted = d_attr;   // reuse: the caller's attribute order is no longer needed
         CKC(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_case, d_case_sorted, d_iota, d_ord, (int)nnz, 0, 32, st));
-        gather_u32_kernel<<<g, BLOCK_T, 0, st>>>(d_key, d_ord, r.attr, nnz);
-        gather_f32_kernel<<<g, BLOCK_T, 0, st>>>(d_xc, d_ord, r.x, nnz);
+        FM_LAUNCH(gather_u32_kernel, g, BLOCK_T, st, d_key, d_ord, r.attr, nnz);
+        FM_LAUNCH(gather_f32_kernel, g, BLOCK_T, st, d_xc, d_ord, r.x, nnz);
         // the sorted case keys ARE the row of every entry of the new row form
-        next_attr_kernel<<<g, BLOCK_T, 0, st>>>(r.attr, d_case_sorted, nnz, d_next, d_dup);
+        FM_LAUNCH(next_attr_kernel, g, BLOCK_T, st, r.attr, d_case_sorted, nnz, d_next, d_dup);
     }
     CKC(cudaGetLastError());
     uint32_t dup = 0;
@@ -802,17 +822,17 @@ static void launch_run(Model& m, const ColArgs& a, const Run& R)
 {
     cudaStream_t st = m.st;
     if (R.w_cnt) {
-        col_warp_kernel<COORD><<<(R.w_cnt + BLOCK_T / 32 - 1) / (BLOCK_T / 32), BLOCK_T, 0, st>>>(a, m.wl_cols + R.w_off, R.w_cnt);
+        FM_LAUNCH(col_warp_kernel<COORD>, (R.w_cnt + BLOCK_T / 32 - 1) / (BLOCK_T / 32), BLOCK_T, st, a, m.wl_cols + R.w_off, R.w_cnt);
         m.launches++;
     }
     if (R.c_cnt) {
-        col_block_kernel<COORD><<<R.c_cnt, BLOCK_T, 0, st>>>(a, m.wl_cols + R.c_off);
+        FM_LAUNCH(col_block_kernel<COORD>, R.c_cnt, BLOCK_T, st, a, m.wl_cols + R.c_off);
         m.launches++;
     }
     if (R.g_cnt) {
-        slice_reduce_kernel<COORD><<<R.s_cnt, BLOCK_T, 0, st>>>(a, m.wl_slices + R.s_off, m.wl_long + R.g_off, m.slice_part);
-        slice_draw_kernel<COORD><<<(R.g_cnt + 127) / 128, 128, 0, st>>>(a, m.wl_long + R.g_off, R.g_cnt, R.s_off, m.slice_part, m.long_scratch);
-        slice_apply_kernel<COORD><<<R.s_cnt, BLOCK_T, 0, st>>>(a, m.wl_slices + R.s_off, m.long_scratch);
+        FM_LAUNCH(slice_reduce_kernel<COORD>, R.s_cnt, BLOCK_T, st, a, m.wl_slices + R.s_off, m.wl_long + R.g_off, m.slice_part);
+        FM_LAUNCH(slice_draw_kernel<COORD>, (R.g_cnt + 127) / 128, 128, st, a, m.wl_long + R.g_off, R.g_cnt, R.s_off, m.slice_part, m.long_scratch);
+        FM_LAUNCH(slice_apply_kernel<COORD>, R.s_cnt, BLOCK_T, st, a, m.wl_slices + R.s_off, m.long_scratch);
         m.launches += 3;
     }
 }
@@ -823,14 +843,17 @@ static void launch_predict(Model& m, const RowForm& r, bool train, int accumulat
     nblocks = (uint32_t)(((uint64_t)r.n * lanes + BLOCK_T - 1) / BLOCK_T);
     if (nblocks == 0) return;
 #define PREDICT(Gv, TRv)                                                                                                             \
-    predict_kernel<Gv, TRv><<<nblocks, BLOCK_T, 0, m.st>>>(r.row_ptr, r.attr, r.x, r.y, r.n, m.w, m.V, m.K, m.cfg.k0, m.cfg.k1, m.sc, m.e, \
-                                                            m.pred_this, m.pred_sum, accumulate, part)
+    {                                                                                                                                \
+        auto kfn = predict_kernel<Gv, TRv>;                                                                                          \
+        FM_LAUNCH(kfn, nblocks, BLOCK_T, m.st, r.row_ptr, r.attr, r.x, r.y, r.n, m.w, m.V, m.K, m.cfg.k0, m.cfg.k1, m.sc, m.e,       \
+                  m.pred_this, m.pred_sum, accumulate, part);                                                                        \
+    }
     if (lanes == 8) {
-        if (train) PREDICT(8, true);
-        else PREDICT(8, false);
+        if (train) PREDICT(8, true)
+        else PREDICT(8, false)
     } else {
-        if (train) PREDICT(32, true);
-        else PREDICT(32, false);
+        if (train) PREDICT(32, true)
+        else PREDICT(32, false)
     }
 #undef PREDICT
     m.launches++;
@@ -851,36 +874,36 @@ static int enqueue_iteration(Model& m)
     const int live = live_noise(m);
     const uint32_t n = m.tr.n;
     double* part_stats = m.red_part;
-    stats_kernel<<<m.red_blocks, BLOCK_T, 0, st>>>(m.e, n, part_stats);
-    global_draw_kernel<<<1, 32, 0, st>>>(m.sc, part_stats, m.red_blocks, n, c.k0, c.do_sample, c.do_multilevel, zero, c.reg0, c.seed);
+    FM_LAUNCH(stats_kernel, m.red_blocks, BLOCK_T, st, m.e, n, part_stats);
+    FM_LAUNCH(global_draw_kernel, 1, 32, st, m.sc, part_stats, m.red_blocks, n, c.k0, c.do_sample, c.do_multilevel, zero, c.reg0, c.seed);
     m.launches += 2;
     if (c.k0) {
-        shift_kernel<<<grid_for(m, n), BLOCK_T, 0, st>>>(m.e, n, m.sc);
+        FM_LAUNCH(shift_kernel, grid_for(m, n), BLOCK_T, st, m.e, n, m.sc);
         m.launches++;
     }
     ColArgs a;
     a.col_ptr = m.col_ptr; a.case_id = m.case_id; a.xc = m.xc; a.e = m.e; a.q = m.q; a.group = m.group; a.sc = m.sc; a.seed = c.seed; a.live = live;
     if (c.k1) {
-        if (m.nchunks) hyper_reduce_kernel<<<dim3(m.nchunks, 1), BLOCK_T, 0, st>>>(m.w, 1, m.gs_attr, m.chunk_begin, m.group, m.w_mu, 1, m.hyper_part);
-        hyper_draw_kernel<<<(m.G + 127) / 128, 128, 0, st>>>(m.w_mu, m.w_lambda, m.hyper_part, m.gchunk_ptr, m.n_per_group, m.G, 1, m.sc, c.do_sample,
+        if (m.nchunks) FM_LAUNCH(hyper_reduce_kernel, dim3(m.nchunks, 1), BLOCK_T, st, m.w, 1, m.gs_attr, m.chunk_begin, m.group, m.w_mu, 1, m.hyper_part);
+        FM_LAUNCH(hyper_draw_kernel, (m.G + 127) / 128, 128, st, m.w_mu, m.w_lambda, m.hyper_part, m.gchunk_ptr, m.n_per_group, m.G, 1, m.sc, c.do_sample,
                                                             c.do_multilevel, zero, c.seed, SITE_FM_W_LAMBDA, SITE_FM_W_MU);
         m.launches += 2;
         a.theta = m.w; a.stride = 1; a.f = 0; a.mu = m.w_mu; a.lambda = m.w_lambda; a.hstride = 1; a.site = SITE_FM_W;
         for (const Run& R : m.runs) launch_run<COORD_W>(m, a, R);
     }
     if (m.K > 0) {
-        if (m.nchunks) hyper_reduce_kernel<<<dim3(m.nchunks, m.K), BLOCK_T, 0, st>>>(m.V, m.K, m.gs_attr, m.chunk_begin, m.group, m.v_mu, m.K, m.hyper_part);
-        hyper_draw_kernel<<<(m.G * m.K + 127) / 128, 128, 0, st>>>(m.v_mu, m.v_lambda, m.hyper_part, m.gchunk_ptr, m.n_per_group, m.G, m.K, m.sc,
+        if (m.nchunks) FM_LAUNCH(hyper_reduce_kernel, dim3(m.nchunks, m.K), BLOCK_T, st, m.V, m.K, m.gs_attr, m.chunk_begin, m.group, m.v_mu, m.K, m.hyper_part);
+        FM_LAUNCH(hyper_draw_kernel, (m.G * m.K + 127) / 128, 128, st, m.v_mu, m.v_lambda, m.hyper_part, m.gchunk_ptr, m.n_per_group, m.G, m.K, m.sc,
                                                                   c.do_sample, c.do_multilevel, zero, c.seed, SITE_FM_V_LAMBDA, SITE_FM_V_MU);
         m.launches += 2;
         a.theta = m.V; a.stride = m.K; a.mu = m.v_mu; a.lambda = m.v_lambda; a.hstride = m.K; a.site = SITE_FM_V;
         const double avg_row = n ? (double)m.tr.nnz / n : 0.0;
         for (uint32_t f = 0; f < m.K; ++f) {
-            if (avg_row <= 4.0) q_rebuild_kernel<1><<<(n + BLOCK_T - 1) / BLOCK_T, BLOCK_T, 0, st>>>(m.tr.row_ptr, m.tr.attr, m.tr.x, n, m.V, m.K, f, m.q);
+            if (avg_row <= 4.0) FM_LAUNCH(q_rebuild_kernel<1>, (n + BLOCK_T - 1) / BLOCK_T, BLOCK_T, st, m.tr.row_ptr, m.tr.attr, m.tr.x, n, m.V, m.K, f, m.q);
             else if (avg_row <= 64.0)
-                q_rebuild_kernel<8><<<(uint32_t)(((uint64_t)n * 8 + BLOCK_T - 1) / BLOCK_T), BLOCK_T, 0, st>>>(m.tr.row_ptr, m.tr.attr, m.tr.x, n, m.V, m.K, f, m.q);
+                FM_LAUNCH(q_rebuild_kernel<8>, (uint32_t)(((uint64_t)n * 8 + BLOCK_T - 1) / BLOCK_T), BLOCK_T, st, m.tr.row_ptr, m.tr.attr, m.tr.x, n, m.V, m.K, f, m.q);
             else
-                q_rebuild_kernel<32><<<(uint32_t)(((uint64_t)n * 32 + BLOCK_T - 1) / BLOCK_T), BLOCK_T, 0, st>>>(m.tr.row_ptr, m.tr.attr, m.tr.x, n, m.V, m.K, f, m.q);
+                FM_LAUNCH(q_rebuild_kernel<32>, (uint32_t)(((uint64_t)n * 32 + BLOCK_T - 1) / BLOCK_T), BLOCK_T, st, m.tr.row_ptr, m.tr.attr, m.tr.x, n, m.V, m.K, f, m.q);
             m.launches++;
             a.f = f;
             for (const Run& R : m.runs) launch_run<COORD_V>(m, a, R);
@@ -891,7 +914,7 @@ static int enqueue_iteration(Model& m)
     uint32_t nb_train = 0, nb_test = 0;
     launch_predict(m, m.tr, true, 0, part_train, nb_train);
     if (m.have_test) launch_predict(m, m.te, false, 1, part_test, nb_test);
-    finish_iteration_kernel<<<1, 32, 0, st>>>(m.sc, part_train, nb_train, m.tr.n, part_test, nb_test, m.have_test ? m.te.n : 0, m.hist);
+    FM_LAUNCH(finish_iteration_kernel, 1, 32, st, m.sc, part_train, nb_train, m.tr.n, part_test, nb_test, m.have_test ? m.te.n : 0, m.hist);
     m.launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -1111,7 +1134,7 @@ int sbmf_fm_init(sbmf_fm_handle* h, const float* w_init, const float* v_init)
     API_CK(cudaSetDevice(m.cfg.device));
     cudaStream_t st = m.st;
     const uint32_t p = m.p, K = m.K, G = m.G, F = std::max<uint32_t>(K, 1);
-    init_params_kernel<<<grid_for(m, (int64_t)p * (K + 1)), BLOCK_T, 0, st>>>(m.w, m.V, p, K, m.cfg.seed, (float)m.cfg.init_stdev, w_init == nullptr,
+    FM_LAUNCH(init_params_kernel, grid_for(m, (int64_t)p * (K + 1)), BLOCK_T, st, m.w, m.V, p, K, m.cfg.seed, (float)m.cfg.init_stdev, w_init == nullptr,
                                                                              v_init == nullptr);
     if (w_init) API_CK(cudaMemcpyAsync(m.w, w_init, (size_t)p * 4, cudaMemcpyHostToDevice, st));
     std::vector<float> vt;

@@ -87,6 +87,45 @@ class SbmfError(RuntimeError):
 _lib = None
 
 
+def _bind_fm(lib):
+    """argument types of the general FM Gibbs entry points (include/sbmf_fm_cuda.h)"""
+    P = C.POINTER
+    lib.sbmf_fm_config_default.argtypes = [P(FmConfig)]
+    lib.sbmf_fm_create.argtypes = [P(FmConfig), P(C.c_void_p)]
+    lib.sbmf_fm_destroy.argtypes = [C.c_void_p]
+    lib.sbmf_fm_last_error.argtypes = [C.c_void_p]
+    lib.sbmf_fm_last_error.restype = C.c_char_p
+    lib.sbmf_fm_set_groups.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_set_train.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
+    lib.sbmf_fm_set_test.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
+    lib.sbmf_fm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_learn.argtypes = [C.c_void_p, C.c_uint32]
+    lib.sbmf_fm_rmse_history.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_predict.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_get_state.argtypes = [C.c_void_p, P(FmState)]
+    lib.sbmf_fm_get_columns.argtypes = [C.c_void_p] + [C.c_void_p] * 3
+    lib.sbmf_fm_get_runs.argtypes = [C.c_void_p, P(C.c_uint32), C.c_void_p]
+    lib.sbmf_fm_plan_runs.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.sbmf_fm_plan_runs.restype = C.c_uint32
+
+
+_fm_lib = None
+
+
+def load_fm_library():
+    """The library that serves sbmf_fm_*: libsbmf_cuda.so.  SBMF_FM_LIB_PATH is a test knob: tests/test_fm_simt_emulation.py points it
+    at a host build of csrc/fm.cu whose kernels execute on CPU threads (tools/emu_include) -- never set in production."""
+    global _fm_lib
+    if _fm_lib is None:
+        alt = os.environ.get("SBMF_FM_LIB_PATH")
+        if alt:
+            _fm_lib = C.CDLL(alt)
+            _bind_fm(_fm_lib)
+        else:
+            _fm_lib = load_library()
+    return _fm_lib
+
+
 def load_library(path=None):
     """Load libsbmf_cuda.so; raises OSError if it has not been built (there is no fallback)."""
     global _lib
@@ -135,24 +174,7 @@ def load_library(path=None):
     lib.sbmf_cuda_synth_host_free.argtypes = [C.c_void_p]
     lib.sbmf_cuda_synth_host_free.restype = None
     lib.sbmf_cuda_synth_host_last_error.restype = C.c_char_p
-    # general FM Gibbs (include/sbmf_fm_cuda.h)
-    lib.sbmf_fm_config_default.argtypes = [P(FmConfig)]
-    lib.sbmf_fm_create.argtypes = [P(FmConfig), P(C.c_void_p)]
-    lib.sbmf_fm_destroy.argtypes = [C.c_void_p]
-    lib.sbmf_fm_last_error.argtypes = [C.c_void_p]
-    lib.sbmf_fm_last_error.restype = C.c_char_p
-    lib.sbmf_fm_set_groups.argtypes = [C.c_void_p, C.c_void_p]
-    lib.sbmf_fm_set_train.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
-    lib.sbmf_fm_set_test.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
-    lib.sbmf_fm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.sbmf_fm_learn.argtypes = [C.c_void_p, C.c_uint32]
-    lib.sbmf_fm_rmse_history.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
-    lib.sbmf_fm_predict.argtypes = [C.c_void_p, C.c_void_p]
-    lib.sbmf_fm_get_state.argtypes = [C.c_void_p, P(FmState)]
-    lib.sbmf_fm_get_columns.argtypes = [C.c_void_p] + [C.c_void_p] * 3
-    lib.sbmf_fm_get_runs.argtypes = [C.c_void_p, P(C.c_uint32), C.c_void_p]
-    lib.sbmf_fm_plan_runs.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
-    lib.sbmf_fm_plan_runs.restype = C.c_uint32
+    _bind_fm(lib)
     if path is None:
         _lib = lib
     return lib
@@ -312,7 +334,7 @@ class FmModel:
     (src/libfm/src/fm_learn.h:80, 150, 191) -- on a design matrix in row form: dict(row_ptr int64, attr uint32, x float32, y float32)."""
 
     def __init__(self, num_attr, K, attr_group=None, **kw):
-        self.lib = load_library()
+        self.lib = load_fm_library()
         self.cfg = FmConfig()
         self.lib.sbmf_fm_config_default(C.byref(self.cfg))
         self.group = None if attr_group is None else _u32(attr_group)
@@ -404,7 +426,7 @@ class FmModel:
 def fm_plan_runs(next_attr):
     next_attr = _u32(next_attr)
     out = np.zeros(next_attr.size + 1, dtype=np.uint32)
-    n = load_library().sbmf_fm_plan_runs(next_attr.size, _ptr(next_attr), _ptr(out))
+    n = load_fm_library().sbmf_fm_plan_runs(next_attr.size, _ptr(next_attr), _ptr(out))
     return out[:n + 1]
 
 

@@ -172,6 +172,40 @@ def case_live():
     assert np.all(dev.std(0)[2:] <= 3 * ref.std(0)[2:] + 1e-3)
 
 
+def case_live_small():
+    """live sampling on the small general fixture (also what the CPU execution of the kernels runs): the Philox-driven chains have
+    the mean test-RMSE trajectory of libFM's rand()-driven ones within 4 standard errors (+0.003), and one seed repeats bit for bit"""
+    tr, te, group = load_fixture("fm_general")
+    p = fmo.num_attributes(tr, te)
+    K, T, nd, nr = 3, 6, int(os.environ.get("FM_LIVE_SEEDS", "16")), 64
+    dev = []
+    for seed in range(nd):
+        m = sbmf.FmModel(p, K, attr_group=group, seed=200 + seed)
+        m.set_train(tr)
+        m.set_test(te)
+        m.init()
+        m.learn(T)
+        dev.append(m.rmse_history(0, T)[1])
+        if seed == 0:
+            m.init()
+            m.learn(T)
+            assert np.array_equal(dev[0], m.rmse_history(0, T)[1]), "same seed, different chain"
+        m.close()
+    ref = []
+    for seed in range(nr):
+        o = fmo.FmOracle(tr, te, K, num_attr=p, attr_group=group)
+        o.srand(3000 + seed)
+        o.init()
+        ref.append(o.learn(T)[1])
+        o.close()
+    dev, ref = np.array(dev), np.array(ref)
+    assert np.std(dev[:, -1]) > 1e-4, "no noise in live mode?"
+    diff = np.abs(dev.mean(0) - ref.mean(0))
+    se = np.sqrt(dev.var(0, ddof=1) / dev.shape[0] + ref.var(0, ddof=1) / ref.shape[0])
+    assert np.all(diff <= 4 * se + 0.003), (diff, se, dev.mean(0), ref.mean(0))
+    assert np.all(dev.std(0) <= 3 * ref.std(0) + 1e-3) and np.all(dev.std(0) >= ref.std(0) / 3 - 1e-3), (dev.std(0), ref.std(0))
+
+
 def case_errors():
     tr, te, group = load_fixture("fm_general")
     p = fmo.num_attributes(tr, te)

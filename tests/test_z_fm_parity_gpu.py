@@ -14,7 +14,7 @@ import sys
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = ["columns", "zero_mf", "zero_general", "zero_general_k20", "zero_als", "zero_variants", "long_columns", "live", "errors", "cli"]
+CASES = ["columns", "zero_mf", "zero_general", "zero_general_k20", "zero_als", "zero_variants", "long_columns", "live", "live_small", "errors", "cli"]
 
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first run on a B200 pending (written without GPU access)", strict=False)]
 

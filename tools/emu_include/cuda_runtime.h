@@ -1,0 +1,205 @@
+// tools/emu_include/cuda_runtime.h -- TEST INFRASTRUCTURE: a host stand-in for the CUDA runtime and the SIMT execution model, just
+// large enough to compile csrc/fm.cu with g++ (-DSBMF_SIMT_EMU -I tools/emu_include) and EXECUTE its kernels on the CPU:
+//   * device memory = host memory (cudaMalloc -> malloc, cudaMemcpy -> memcpy), streams are synchronous;
+//   * a kernel launch runs the kernel body once per (block, thread): the threads of a block are real host threads from a pool,
+//     blocks run one after the other; __syncthreads() is a block barrier, __shfl_xor_sync() exchanges through a per-block buffer
+//     between two warp barriers, __shared__ is a function-local static (one block at a time), atomics are __atomic builtins.
+// What it checks: indexing, work lists, launch geometry, reduction trees, barrier placement, the host orchestration -- everything
+// except the hardware itself.  Never part of the product; used by tests/test_fm_simt_emulation.py only.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+struct float2 { float x, y; };
+struct double2 { double x, y; };
+inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+
+// ---- runtime API ----------------------------------------------------------------------------------------------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1 };
+typedef struct emu_stream* cudaStream_t;
+struct cudaDeviceProp { int major, minor, multiProcessorCount; };
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { return cudaMemset(d, v, n); }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(1); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated error"; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->major = 10; p->minor = 0; p->multiProcessorCount = 2; return cudaSuccess; }
+
+// ---- SIMT execution -------------------------------------------------------------------------------------------------------------
+namespace simt {
+struct Idx { unsigned x, y, z; };
+struct Barrier {   // reusable sense-reversing barrier; waiters yield (far more host threads than cores, and episodes are short)
+    std::atomic<int> waiting{0};
+    std::atomic<unsigned> gen{0};
+    int n = 0;
+    void wait()
+    {
+        const unsigned g = gen.load(std::memory_order_acquire);
+        if (waiting.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+            waiting.store(0, std::memory_order_relaxed);
+            gen.store(g + 1, std::memory_order_release);
+        } else {
+            int spins = 0;
+            while (gen.load(std::memory_order_acquire) == g) {
+                if (++spins > 16) std::this_thread::yield();
+            }
+        }
+    }
+};
+struct Block {
+    Barrier all;
+    Barrier warp[32];
+    uint64_t xch[1024];
+};
+inline Block& block()
+{
+    static Block b;
+    return b;
+}
+struct Pool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_start, cv_done;
+    uint64_t gen = 0;
+    int active = 0, remaining = 0;
+    bool stop = false;
+    std::function<void(int)> job;
+    void worker(int i)
+    {
+        uint64_t last = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_start.wait(lk, [&] { return stop || gen != last; });
+                if (stop) return;
+                last = gen;
+                if (i >= active) continue;
+            }
+            job(i);
+            std::unique_lock<std::mutex> lk(m);
+            if (--remaining == 0) cv_done.notify_one();
+        }
+    }
+    void run(int n, const std::function<void(int)>& f)
+    {
+        while ((int)th.size() < n) {
+            const int i = (int)th.size();
+            th.emplace_back([this, i] { worker(i); });
+        }
+        {
+            std::unique_lock<std::mutex> lk(m);
+            job = f;
+            active = remaining = n;
+            ++gen;
+        }
+        cv_start.notify_all();
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return remaining == 0; });
+    }
+    ~Pool()
+    {
+        {
+            std::unique_lock<std::mutex> lk(m);
+            stop = true;
+        }
+        cv_start.notify_all();
+        for (auto& t : th) t.join();
+    }
+};
+inline Pool& pool()
+{
+    static Pool p;
+    return p;
+}
+inline thread_local Idx t_thread{0, 0, 0}, t_block{0, 0, 0};
+inline thread_local dim3 t_bdim, t_gdim;
+
+template <class F>
+inline void launch(dim3 grid, dim3 blk, F&& body)
+{
+    const int nt = (int)blk.x;
+    if (nt <= 0 || nt > 1024 || blk.y != 1 || blk.z != 1 || grid.x == 0 || grid.y == 0) abort();
+    Block& b = block();
+    b.all.n = nt;
+    for (int w = 0; w < 32; ++w) b.warp[w].n = std::max(0, std::min(32, nt - 32 * w));
+    pool().run(nt, [&](int t) {
+        t_bdim = blk;
+        t_gdim = grid;
+        t_thread = Idx{(unsigned)t, 0, 0};
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                t_block = Idx{bx, by, 0};
+                body();
+                b.all.wait();   // one block at a time (function-local __shared__ statics, exchange buffer)
+            }
+    });
+}
+}  // namespace simt
+
+#define threadIdx simt::t_thread
+#define blockIdx simt::t_block
+#define blockDim simt::t_bdim
+#define gridDim simt::t_gdim
+
+inline void __syncthreads() { simt::block().all.wait(); }
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
+{
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    simt::Block& b = simt::block();
+    const unsigned t = threadIdx.x, w = t >> 5;
+    uint64_t bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    b.xch[t] = bits;
+    b.warp[w].wait();
+    const uint64_t got = b.xch[(t & ~31u) | ((t ^ (unsigned)lane_mask) & 31u)];
+    b.warp[w].wait();
+    T r;
+    memcpy(&r, &got, sizeof(T));
+    return r;
+}
+inline uint32_t atomicMin(uint32_t* a, uint32_t v)
+{
+    uint32_t old = __atomic_load_n(a, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+inline uint32_t atomicExch(uint32_t* a, uint32_t v) { return __atomic_exchange_n(a, v, __ATOMIC_RELAXED); }
