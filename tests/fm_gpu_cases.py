@@ -240,6 +240,51 @@ def case_errors():
     m.close()
 
 
+def _preload_env(**extra):
+    """child processes that LINK libsbmf_cuda.so (the host CLI, libFM with the CUDA learner) follow this process onto the CPU
+    execution of the kernels when the tests run there (SBMF_FM_LIB_PATH, tests/test_fm_simt_emulation.py)"""
+    env = dict(os.environ, **extra)
+    if os.environ.get("SBMF_FM_LIB_PATH"):
+        env["LD_PRELOAD"] = os.environ["SBMF_FM_LIB_PATH"]
+    return env
+
+
+def case_libfm_learner():
+    """oracle/_ref/libFM_cuda = libFM's own main(), loader, meta groups, initial draws, predict() and -out around fm_learn_cuda::learn
+    (oracle/libfm_cuda_learner.h): its "#Iter=" lines and prediction file are those of the binding started from
+    the same initial w, v (libFM's rand() draws under SBMF_SHIM_SEED, reproduced by the pinned restatement)"""
+    import re
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "libFM_cuda")
+    if not os.path.exists(exe):
+        print("skipped: oracle/_ref/libFM_cuda not built (needs /root/reference at build time)")
+        return
+    tr, te, group = load_fixture("fm_general")
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([exe, "-task", "r", "-train", os.path.join(GOLDEN, "fm_general.train"), "-test", os.path.join(GOLDEN, "fm_general.test"),
+                            "-meta", os.path.join(GOLDEN, "fm_general.meta"), "-dim", "1,1,3", "-iter", "5", "-method", "mcmc", "-out", "pred.txt"],
+                           capture_output=True, text=True, cwd=tmp, env=_preload_env(SBMF_SHIM_SEED="7"))
+        assert r.returncode == 0 and "ERROR" not in r.stderr, r.stderr[-2000:]
+        rows = re.findall(r"^#Iter=\s*(\d+)\tTrain=(\S+)\tTest=(\S+)$", r.stdout, flags=re.M)
+        assert len(rows) == 5, r.stdout[-1000:]
+        got = np.array([float(x) for x in open(os.path.join(tmp, "pred.txt")).read().split()])   # libFM's own predict() / DVector::save
+    o = fmo.FmOracle(tr, te, 3, attr_group=group)
+    o.srand(7)
+    o.init()
+    s0 = o.state()
+    m = sbmf.FmModel(o.p, 3, attr_group=group)
+    m.set_train(tr)
+    m.set_test(te)
+    m.init(s0["w"].astype(np.float32), s0["v"].astype(np.float32))
+    m.learn(5)
+    a, b = m.rmse_history(0, 5)
+    assert [x[1] for x in rows] == [f"{v:g}" for v in a] and [x[2] for x in rows] == [f"{v:g}" for v in b], (rows, a, b)
+    assert got.size == te["y"].size and np.max(np.abs(got - m.predict())) <= 2e-5
+    m.close()
+    o.close()
+
+
 def case_cli():
     """bin/sbmf -method fm_mcmc: libFM's command line and outputs ("#Iter=" lines, test_rmse_<k0><k1><K>_mcmc, -out) carry the chain of
     the binding with the same seed, value for value"""
@@ -260,7 +305,7 @@ def case_cli():
     with tempfile.TemporaryDirectory() as tmp:
         r = subprocess.run([cli, "-method", "fm_mcmc", "-train", os.path.join(GOLDEN, "fm_general.train"), "-test", os.path.join(GOLDEN, "fm_general.test"),
                             "-meta", os.path.join(GOLDEN, "fm_general.meta"), "-dim", "1,1,3", "-iter", "5", "-seed", "3", "-out", "pred.txt"],
-                           capture_output=True, text=True, cwd=tmp)
+                           capture_output=True, text=True, cwd=tmp, env=_preload_env())
         assert r.returncode == 0, r.stderr
         rows = re.findall(r"^#Iter=\s*(\d+)\tTrain=(\S+)\tTest=(\S+)$", r.stdout, flags=re.M)
         assert [x[1] for x in rows] == [f"{v:g}" for v in a] and [x[2] for x in rows] == [f"{v:g}" for v in b], (rows, a, b)

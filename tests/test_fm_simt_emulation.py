@@ -55,6 +55,15 @@ def test_kernels_on_cpu_threads_all_tiers(emu_shrunk, case):
     run_case(emu_shrunk, case)
 
 
+def test_front_ends_on_cpu_threads(emu_shrunk):
+    """the programs that LINK the library follow onto the CPU execution through LD_PRELOAD: the host CLI (-method fm_mcmc: "#Iter="
+    lines, test_rmse_* file, -out) and libFM's own main() with the CUDA learner spliced in (oracle/_ref/libFM_cuda) print the
+    binding's chain"""
+    subprocess.run(["make", "-C", PKG], check=True, capture_output=True)
+    run_case(emu_shrunk, "cli")
+    run_case(emu_shrunk, "libfm_learner")
+
+
 def test_kernels_on_cpu_threads_live_sampling(emu_shrunk):
     run_case(emu_shrunk, "live_small", FM_LIVE_SEEDS="8")
 

@@ -68,35 +68,8 @@ def test_patched_libfm_reaches_the_library(patched, tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.xfail(reason="general FM Gibbs path: first run on a B200 pending (written without GPU access)", strict=False)
-def test_patched_libfm_prints_the_binding_trajectory(patched, tmp_path):
-    """libFM's main(), loader, meta groups and initial draws + fm_learn_cuda::learn == the ctypes binding started from the same
-    initial w, v (libFM's rand() draws under SBMF_SHIM_SEED, reproduced by the pinned restatement): the same "#Iter=" lines"""
-    import re
-    import numpy as np
-    sys.path.insert(0, PKG)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import fm_oracle_py as fmo
-    import sbmf
-    from test_fm_oracle import load_fixture
-    if not os.path.exists(LIBFM_CUDA):
-        pytest.skip("oracle/_ref/libFM_cuda not built")
-    r = subprocess.run([LIBFM_CUDA] + FM_ARGS + ["-out", "pred.txt"], capture_output=True, text=True, cwd=tmp_path, env=dict(os.environ, SBMF_SHIM_SEED="7"))
-    assert r.returncode == 0 and "ERROR" not in r.stderr, r.stderr[-2000:]
-    rows = re.findall(r"^#Iter=\s*(\d+)\tTrain=(\S+)\tTest=(\S+)$", r.stdout, flags=re.M)
-    assert len(rows) == 5, r.stdout[-1000:]
-    tr, te, group = load_fixture("fm_general")
-    o = fmo.FmOracle(tr, te, 3, attr_group=group)
-    o.srand(7)
-    o.init()
-    s0 = o.state()
-    m = sbmf.FmModel(o.p, 3, attr_group=group)
-    m.set_train(tr)
-    m.set_test(te)
-    m.init(s0["w"].astype(np.float32), s0["v"].astype(np.float32))
-    m.learn(5)
-    a, b = m.rmse_history(0, 5)
-    assert [x[1] for x in rows] == [f"{v:g}" for v in a] and [x[2] for x in rows] == [f"{v:g}" for v in b]
-    got = np.array([float(x) for x in open(tmp_path / "pred.txt").read().split()])     # libFM's own predict() / DVector::save on pred_sum_all
-    assert got.size == te["y"].size and np.max(np.abs(got - m.predict())) <= 2e-5
-    m.close()
-    o.close()
+def test_patched_libfm_prints_the_binding_trajectory(patched):
+    """tests/fm_gpu_cases.py::case_libfm_learner in a process of its own (the CPU suite runs the same case on the CPU execution of the
+    kernels, tests/test_fm_simt_emulation.py)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fm_gpu_cases.py"), "libfm_learner"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ok libfm_learner" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
