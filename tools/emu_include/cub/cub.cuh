@@ -27,4 +27,20 @@ struct DeviceRadixSort {
         return cudaSuccess;
     }
 };
+struct DeviceSelect {
+    // stable compaction of the items the predicate accepts
+    template <class T, class Pred>
+    static cudaError_t If(void* tmp, size_t& tmp_bytes, const T* in, T* out, int* num_selected, int n, Pred pred, cudaStream_t)
+    {
+        if (!tmp) {
+            tmp_bytes = 1;
+            return cudaSuccess;
+        }
+        int k = 0;
+        for (int i = 0; i < n; ++i)
+            if (pred(in[i])) out[k++] = in[i];
+        *num_selected = k;
+        return cudaSuccess;
+    }
+};
 }  // namespace cub

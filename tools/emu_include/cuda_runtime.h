@@ -62,32 +62,83 @@ inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ?
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->major = 10; p->minor = 0; p->multiProcessorCount = 2; return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
+inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
+inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
+#define __constant__
+#define cudaMemcpyToSymbol(sym, src, n) (memcpy((void*)&(sym), (src), (n)), cudaSuccess)
+// events: no timing on the host; graphs, memory pools and IPC are refused, which the library treats as "not available"
+enum { cudaErrorNotSupported = 801, cudaEventDisableTiming = 2, cudaStreamCaptureModeThreadLocal = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
+typedef struct emu_event* cudaEvent_t;
+typedef struct emu_graph* cudaGraph_t;
+typedef struct emu_graph_exec* cudaGraphExec_t;
+typedef struct emu_pool* cudaMemPool_t;
+struct cudaIpcMemHandle_t { char reserved[64]; };
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(1); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t*, int) { return cudaErrorNotSupported; }
+inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaErrorNotSupported; }
+inline cudaError_t cudaMemPoolTrimTo(cudaMemPool_t, size_t) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
 
 // ---- SIMT execution -------------------------------------------------------------------------------------------------------------
 namespace simt {
 struct Idx { unsigned x, y, z; };
-struct Barrier {   // reusable sense-reversing barrier; waiters yield (far more host threads than cores, and episodes are short)
-    std::atomic<int> waiting{0};
+struct Barrier {   // reusable barrier; waiters yield (far more host threads than cores, and episodes are short).  A thread that leaves the
+                   // kernel early drops out of the barriers of its CTA and warp, like an exited thread on the GPU
+    std::atomic<bool> lock{false};
     std::atomic<unsigned> gen{0};
-    int n = 0;
+    int n = 0, waiting = 0;
+    void acquire() { while (lock.exchange(true, std::memory_order_acquire)) std::this_thread::yield(); }
+    void release() { lock.store(false, std::memory_order_release); }
     void wait()
     {
-        const unsigned g = gen.load(std::memory_order_acquire);
-        if (waiting.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
-            waiting.store(0, std::memory_order_relaxed);
+        acquire();
+        const unsigned g = gen.load(std::memory_order_relaxed);
+        if (++waiting >= n) {
+            waiting = 0;
             gen.store(g + 1, std::memory_order_release);
-        } else {
-            int spins = 0;
-            while (gen.load(std::memory_order_acquire) == g) {
-                if (++spins > 16) std::this_thread::yield();
-            }
+            release();
+            return;
         }
+        release();
+        int spins = 0;
+        while (gen.load(std::memory_order_acquire) == g)
+            if (++spins > 16) std::this_thread::yield();
+    }
+    void drop()
+    {
+        acquire();
+        --n;
+        if (n > 0 && waiting >= n) {
+            waiting = 0;
+            gen.store(gen.load(std::memory_order_relaxed) + 1, std::memory_order_release);
+        }
+        release();
     }
 };
 struct Block {
-    Barrier all;
+    Barrier all, done;
     Barrier warp[32];
     uint64_t xch[1024];
+    std::vector<unsigned char> dyn_smem;
 };
 inline Block& block()
 {
@@ -153,13 +204,23 @@ inline thread_local Idx t_thread{0, 0, 0}, t_block{0, 0, 0};
 inline thread_local dim3 t_bdim, t_gdim;
 
 template <class F>
-inline void launch(dim3 grid, dim3 blk, F&& body)
+inline void launch(dim3 grid, dim3 blk, F&& body, size_t dyn_smem_bytes = 0)
 {
     const int nt = (int)blk.x;
     if (nt <= 0 || nt > 1024 || blk.y != 1 || blk.z != 1 || grid.x == 0 || grid.y == 0) abort();
     Block& b = block();
-    b.all.n = nt;
-    for (int w = 0; w < 32; ++w) b.warp[w].n = std::max(0, std::min(32, nt - 32 * w));
+    b.dyn_smem.assign(dyn_smem_bytes + 16, 0);
+    auto arm = [&] {
+        b.all.n = nt;
+        b.all.waiting = 0;
+        for (int w = 0; w < 32; ++w) {
+            b.warp[w].n = std::max(0, std::min(32, nt - 32 * w));
+            b.warp[w].waiting = 0;
+        }
+    };
+    arm();
+    b.done.n = nt;
+    b.done.waiting = 0;
     pool().run(nt, [&](int t) {
         t_bdim = blk;
         t_gdim = grid;
@@ -168,7 +229,11 @@ inline void launch(dim3 grid, dim3 blk, F&& body)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 t_block = Idx{bx, by, 0};
                 body();
-                b.all.wait();   // one block at a time (function-local __shared__ statics, exchange buffer)
+                b.all.drop();            // exited: later __syncthreads / shuffles of this CTA no longer wait for this thread
+                b.warp[t >> 5].drop();
+                b.done.wait();           // one CTA at a time (function-local __shared__ statics, exchange buffer)
+                if (t == 0) arm();
+                b.done.wait();
             }
     });
 }
@@ -180,8 +245,9 @@ inline void launch(dim3 grid, dim3 blk, F&& body)
 #define gridDim simt::t_gdim
 
 inline void __syncthreads() { simt::block().all.wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::block().warp[threadIdx.x >> 5].wait(); }
 template <class T>
-inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
+inline T simt_exchange(T v, unsigned src_lane)
 {
     static_assert(sizeof(T) <= 8, "shuffle payload");
     simt::Block& b = simt::block();
@@ -190,16 +256,40 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
     memcpy(&bits, &v, sizeof(T));
     b.xch[t] = bits;
     b.warp[w].wait();
-    const uint64_t got = b.xch[(t & ~31u) | ((t ^ (unsigned)lane_mask) & 31u)];
+    const uint64_t got = b.xch[(t & ~31u) | (src_lane & 31u)];
     b.warp[w].wait();
     T r;
     memcpy(&r, &got, sizeof(T));
     return r;
 }
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask, int width = 32)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned src = lane ^ (unsigned)lane_mask;
+    if ((src & ~(unsigned)(width - 1)) != (lane & ~(unsigned)(width - 1))) src = lane;   // outside the segment: own value
+    return simt_exchange(v, src);
+}
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src_lane, int width = 32)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    return simt_exchange(v, (lane & ~(unsigned)(width - 1)) | ((unsigned)src_lane & (unsigned)(width - 1)));
+}
+template <class T>
+inline T __ldg(const T* p) { return *p; }
 inline uint32_t atomicMin(uint32_t* a, uint32_t v)
 {
     uint32_t old = __atomic_load_n(a, __ATOMIC_RELAXED);
     while (v < old && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     return old;
 }
+inline uint32_t atomicMax(uint32_t* a, uint32_t v)
+{
+    uint32_t old = __atomic_load_n(a, __ATOMIC_RELAXED);
+    while (v > old && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 inline uint32_t atomicExch(uint32_t* a, uint32_t v) { return __atomic_exchange_n(a, v, __ATOMIC_RELAXED); }
+inline uint32_t atomicAdd(uint32_t* a, uint32_t v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
