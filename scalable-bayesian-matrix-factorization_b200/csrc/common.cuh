@@ -98,6 +98,11 @@ __device__ __forceinline__ double draw_gamma_f64(int mode, uint64_t seed, uint32
 // 256-bit global access (LDG.E.256 / STG.E.256 on sm_100): one K8 factor block of one row per instruction
 struct __align__(32) f8 { float v[8]; };
 
+#ifdef SBMF_SIMT_EMU   // test-only host build (launch.h): plain loads and stores
+__device__ __forceinline__ f8 ld256_nc(const float* p) { return *reinterpret_cast<const f8*>(p); }
+__device__ __forceinline__ f8 ld256(const float* p) { return *reinterpret_cast<const f8*>(p); }
+__device__ __forceinline__ void st256(float* p, const f8& r) { *reinterpret_cast<f8*>(p) = r; }
+#else
 __device__ __forceinline__ f8 ld256_nc(const float* p)
 {
     f8 r;
@@ -121,6 +126,7 @@ __device__ __forceinline__ void st256(float* p, const f8& r)
                  :: "l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
                  : "memory");
 }
+#endif
 
 // Reduce 48 per-lane values over the warp with 48 shuffles instead of 48*5: each step halves the vector a lane
 // still carries (the lane keeps one half and ships the other to its partner).  On return v[0..2] of every lane

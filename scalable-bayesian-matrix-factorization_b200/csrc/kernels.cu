@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "gram.cuh"
+#include "launch.h"
 #include "model.h"
 
 namespace sbmf {
@@ -245,6 +246,8 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
                 e[r] += shift;
                 t += e[r];
             }
+        // every thread of the row reads the old bias BEFORE the reduction (shuffles / barriers): thread 0 overwrites it below
+        const float bo = a.bias[row], sb = a.sigma_b[row], mb = a.mu_b[row];
         t = warp_sum(t);
         if (WARPS > 1) {
             if (lane == 0) s_part[warp][0] = t;
@@ -254,7 +257,6 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
             for (int w = 0; w < WARPS; ++w) t += s_part[w][0];
             __syncthreads();
         }
-        const float bo = a.bias[row], sb = a.sigma_b[row], mb = a.mu_b[row];
         const float s = 1.0f / (sb + alpha * (float)c);
         const float mean = s * (sb * mb + alpha * (t + (float)c * bo));
         float z = 0.f;
@@ -471,9 +473,10 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
                 e[r] += shift;
                 t += e[r];
             }
+        // read before the (warp-wide) shuffles: lane 0 of the group overwrites the bias below (idle groups alias the last row)
+        const float bo = have_row ? a.bias[row] : 0.f, sb = a.sigma_b[row], mb = a.mu_b[row];
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        const float bo = a.bias[row], sb = a.sigma_b[row], mb = a.mu_b[row];
         const float s = 1.0f / (sb + alpha * (float)c);
         const float mean = s * (sb * mb + alpha * (t + (float)c * bo));
         float z = 0.f;
@@ -491,7 +494,7 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
     float zq = 0.f;
     for (int b = b_begin; b < b_end; ++b) {
         const size_t foff = ((size_t)b * ns_self + row) * 8;
-        const bool live = (uint32_t)(b * 8 + kq) < K;
+        const bool live = have_row && (uint32_t)(b * 8 + kq) < K;   // idle groups alias the last row: they must not read what its owner writes
         const float uo = live ? a.Fself[foff + kq] : 0.f;
         const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
         // this row's noise, ZB blocks at a time: lane lg of the group draws dimension 8 * ZB * (b / ZB) + lg
@@ -726,6 +729,7 @@ heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const u
         float z = 0.f;
         if (a.mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
         const float bn = draw_f32(a.mode, mean, s, z);
+        __syncwarp();   // every lane has read the old bias (all lanes compute the same value, lane 0 stores it)
         if (lane == 0) {
             for (int q = 0; q < a.nrep; ++q) a.brep[q][row] = bn;
             hbias_delta[hrow] = bo - bn;
@@ -763,6 +767,7 @@ heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const u
         f8 un;
         float d[8];
         solve_block(s_tot, uo, z, a.sigma_kf + b * 8, a.mu_kf + b * 8, alpha, a.mode, (int)a.K - b * 8, un, d);
+        __syncwarp();   // every lane has read the old factors
         if (lane == 0) {
             for (int q = 0; q < a.nrep; ++q) st256(a.Frep[q] + foff, un);
 #pragma unroll
@@ -1145,48 +1150,48 @@ static inline uint32_t grid_for(uint64_t n, int threads, int cap)
 void launch_init_factors(Model& m, Side& s, uint32_t site, cudaStream_t st)
 {
     const uint64_t total = (uint64_t)m.KB * (s.n + 1) * 8;
-    init_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, s.n + 1, m.K, m.KB, m.cfg.seed, site, (float)m.cfg.init_stdev);
+    SBMF_LAUNCH((init_factors_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, st, s.F, s.n + 1, m.K, m.KB, m.cfg.seed, site, (float)m.cfg.init_stdev);
     m.launches++;
 }
 
 void launch_load_factors(Model& m, Side& s, const float* d_src, bool dim_major, cudaStream_t st)
 {
     const uint64_t total = (uint64_t)m.KB * (s.n + 1) * 8;
-    load_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, d_src, s.n + 1, m.K, m.KB, dim_major ? 1 : 0);
+    SBMF_LAUNCH((load_factors_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, st, s.F, d_src, s.n + 1, m.K, m.KB, dim_major ? 1 : 0);
     m.launches++;
 }
 
 void launch_export_factors(Model& m, const Side& s, float* d_out, bool dim_major, cudaStream_t st)
 {
     const uint64_t total = (uint64_t)s.n * m.K;
-    export_factors_kernel<<<grid_for(total, 256, m.sm_count * 16), 256, 0, st>>>(s.F, d_out, s.n, m.K, dim_major ? 1 : 0);
+    SBMF_LAUNCH((export_factors_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, st, s.F, d_out, s.n, m.K, dim_major ? 1 : 0);
     m.launches++;
 }
 
 void launch_rebuild(Model& m, cudaStream_t st)
 {
-    rebuild_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.csr_urow, m.us.idx, m.csr_r, m.us.e, m.us.F, m.it.F, m.us.bias, m.it.bias, m.sc, m.I + 1,
+    SBMF_LAUNCH((rebuild_kernel), m.red_blocks, RED_THREADS, 0, st, m.csr_urow, m.us.idx, m.csr_r, m.us.e, m.us.F, m.it.F, m.us.bias, m.it.bias, m.sc, m.I + 1,
                                                          m.J + 1, m.KB, m.n_csr, m.red_part);
     m.launches++;
 }
 
 void launch_stats(Model& m, cudaStream_t st, bool from_csc)
 {
-    stats_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(from_csc ? m.it.e : m.us.e, from_csc ? m.n_csc : m.n_csr, m.red_part);
+    SBMF_LAUNCH((stats_kernel), m.red_blocks, RED_THREADS, 0, st, from_csc ? m.it.e : m.us.e, from_csc ? m.n_csc : m.n_csr, m.red_part);
     m.launches++;
 }
 
 void launch_global_hypers(Model& m, cudaStream_t st)
 {
-    global_hypers_kernel<<<1, 32, 0, st>>>(m.sc, m.red2, m.N, m.cfg.priors, m.cfg.sample_mode, m.cfg.hyper_mode, m.cfg.seed);
+    SBMF_LAUNCH((global_hypers_kernel), 1, 32, 0, st, m.sc, m.red2, m.N, m.cfg.priors, m.cfg.sample_mode, m.cfg.hyper_mode, m.cfg.seed);
     m.launches++;
 }
 
 static void dim_hypers_side(Model& m, Side& s, cudaStream_t st)
 {
     const sbmf_priors& p = m.cfg.priors;
-    dim_hyper_partial_kernel<<<dim3(s.hyp_chunks, m.KB), 256, 0, st>>>(s.F, s.n, s.n + 1, s.mu_k, s.hyp_part, s.hyp_chunks);
-    dim_hyper_final_kernel<<<m.KB, 32, 0, st>>>(s.hyp_part, s.hyp_chunks, s.n, m.K, s.sigma_k, s.mu_k, s.sigma_kf, s.mu_kf, m.sc, p.alpha[s.prior],
+    SBMF_LAUNCH((dim_hyper_partial_kernel), dim3(s.hyp_chunks, m.KB), 256, 0, st, s.F, s.n, s.n + 1, s.mu_k, s.hyp_part, s.hyp_chunks);
+    SBMF_LAUNCH((dim_hyper_final_kernel), m.KB, 32, 0, st, s.hyp_part, s.hyp_chunks, s.n, m.K, s.sigma_k, s.mu_k, s.sigma_kf, s.mu_kf, m.sc, p.alpha[s.prior],
                                                 p.beta[s.prior], p.mu[s.prior], p.sigma[s.prior], m.cfg.sample_mode, m.cfg.seed, s.site_sigma_k,
                                                 s.site_mu_k, m.cfg.hyper_mode, p, s.post_var,
                                                 (m.cfg.hyper_mode == SBMF_HYPER_NG_S && &s == &m.it) ? m.us.post_var : nullptr);
@@ -1203,7 +1208,7 @@ void launch_bias_hypers(Model& m, cudaStream_t st)
 {
     const sbmf_priors& p = m.cfg.priors;
     for (Side* s : {&m.us, &m.it}) {
-        bias_hyper_kernel<<<(s->n + 255) / 256, 256, 0, st>>>(s->bias, s->mu_b, s->sigma_b, s->n, m.sc, p.alpha[s->prior_b], p.beta[s->prior_b],
+        SBMF_LAUNCH((bias_hyper_kernel), (s->n + 255) / 256, 256, 0, st, s->bias, s->mu_b, s->sigma_b, s->n, m.sc, p.alpha[s->prior_b], p.beta[s->prior_b],
                                                               p.mu[s->prior_b], p.sigma[s->prior_b], m.cfg.sample_mode, m.cfg.seed,
                                                               s->site_sigma_b, s->site_mu_b);
         m.launches++;
@@ -1221,23 +1226,23 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
         if (no_group) {
             constexpr int R1 = kBins[BIN].cap / 32;
             const dim3 grid1((n + 3) / 4);
-            if (refresh) row_resident_kernel<R1, 1, true><<<grid1, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-            else row_resident_kernel<R1, 1, false><<<grid1, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            if (refresh) SBMF_LAUNCH((row_resident_kernel<R1, 1, true>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            else SBMF_LAUNCH((row_resident_kernel<R1, 1, false>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
             m.launches++;
             return;
         }
         constexpr int G = kBins[BIN].cap / (RPL > 0 ? RPL : 1) >= 16 ? 16 : 8;
         const uint32_t rows_per_cta = 4 * (32 / G);
         const dim3 grid((n + rows_per_cta - 1) / rows_per_cta);
-        if (refresh) row_group_kernel<RPL, G, true><<<grid, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-        else row_group_kernel<RPL, G, false><<<grid, 128, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        if (refresh) SBMF_LAUNCH((row_group_kernel<RPL, G, true>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else SBMF_LAUNCH((row_group_kernel<RPL, G, false>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         m.launches++;
         return;
     }
     if constexpr (WARPS > 0) {
         const dim3 grid(WARPS == 1 ? (n + 3) / 4 : n), block(WARPS == 1 ? 128 : WARPS * 32);
-        if (refresh) row_resident_kernel<RPL, WARPS, true><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
-        else row_resident_kernel<RPL, WARPS, false><<<grid, block, 0, st>>>(a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        if (refresh) SBMF_LAUNCH((row_resident_kernel<RPL, WARPS, true>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else SBMF_LAUNCH((row_resident_kernel<RPL, WARPS, false>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         m.launches++;
     }
 }
@@ -1330,14 +1335,14 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     // 2 ratings per thread x 64 threads per slice CTA measured best on B200 (profiles/): small CTAs, ~20 warps per SM
 #define HEAVY_ACC(PREV, CUR, PB, B)                                                                                                              \
     do {                                                                                                                                         \
-        if (refresh) heavy_accumulate_kernel<PREV, CUR, 2, 64, true><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);  \
-        else heavy_accumulate_kernel<PREV, CUR, 2, 64, false><<<ns, 64, 0, sh>>>(a, self.slices, self.hdelta, hbias, self.hpart, PB, B);         \
+        if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, PB, B);  \
+        else SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, false>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, PB, B);         \
     } while (0)
         const bool wide_solve = ns >= 8u * nh;   // >= 8 slices per heavy row on average
 #define HEAVY_SOLVE(CUR, B)                                                                                                                       \
     do {                                                                                                                                         \
-        if (wide_solve) heavy_solve_kernel<CUR, 8><<<gs, 256, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, B); \
-        else heavy_solve_kernel<CUR, 2><<<gs, 64, 0, sh>>>(a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, B);   \
+        if (wide_solve) SBMF_LAUNCH((heavy_solve_kernel<CUR, 8>), gs, 256, 0, sh, a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, B); \
+        else SBMF_LAUNCH((heavy_solve_kernel<CUR, 2>), gs, 64, 0, sh, a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, B);   \
     } while (0)
         if (with_bias) {
             HEAVY_ACC(0, 1, 0, 0);
@@ -1394,7 +1399,7 @@ static bool ensure_inverse(Model& m, const uint32_t* perm, uint32_t** inv, uint6
         cudaGetLastError();
         return false;   // fall back to the scatter form
     }
-    invert_perm_kernel<<<grid_for(n, 256, m.sm_count * 16), 256, 0, st>>>(perm, *inv, n);
+    SBMF_LAUNCH((invert_perm_kernel), grid_for(n, 256, m.sm_count * 16), 256, 0, st, perm, *inv, n);
     return true;
 }
 
@@ -1404,9 +1409,9 @@ int launch_permute(Model& m, bool csr_to_csc, Side* gather_side, cudaStream_t st
 {
     if (m.world == 1) {
         const uint32_t g = grid_for(m.N, 256, m.sm_count * 16);
-        if (csr_to_csc) permute_gather_kernel<<<g, 256, 0, st>>>(m.us.e, m.perm, m.it.e, m.N);
-        else if (ensure_inverse(m, m.perm, &m.perm_inv, m.N, st)) permute_gather_kernel<<<g, 256, 0, st>>>(m.it.e, m.perm_inv, m.us.e, m.N);
-        else permute_scatter_kernel<<<g, 256, 0, st>>>(m.it.e, m.perm, m.us.e, m.N);
+        if (csr_to_csc) SBMF_LAUNCH((permute_gather_kernel), g, 256, 0, st, m.us.e, m.perm, m.it.e, m.N);
+        else if (ensure_inverse(m, m.perm, &m.perm_inv, m.N, st)) SBMF_LAUNCH((permute_gather_kernel), g, 256, 0, st, m.it.e, m.perm_inv, m.us.e, m.N);
+        else SBMF_LAUNCH((permute_scatter_kernel), g, 256, 0, st, m.it.e, m.perm, m.us.e, m.N);
         m.launches++;
         return 0;
     }
@@ -1416,21 +1421,21 @@ int launch_permute(Model& m, bool csr_to_csc, Side* gather_side, cudaStream_t st
     const uint32_t gs = grid_for(m.n_csr, 256, m.sm_count * 16), gr = grid_for(m.n_csc, 256, m.sm_count * 16);
     int rc = 0;
     if (csr_to_csc) {
-        permute_gather_kernel<<<gs, 256, 0, st>>>(m.us.e, m.send_idx, m.sendbuf, m.n_csr);
+        SBMF_LAUNCH((permute_gather_kernel), gs, 256, 0, st, m.us.e, m.send_idx, m.sendbuf, m.n_csr);
         rc |= comm_group_begin(m.err);
         rc |= comm_alltoallv_f32(m.comm, m.sendbuf, m.send_off.data(), m.send_cnt.data(), m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), st, m.err);
         if (gather_side) rc |= launch_allgather_side(m, *gather_side, st);
         rc |= comm_group_end(m.err);
-        permute_gather_kernel<<<gr, 256, 0, st>>>(m.recvbuf, m.recv_pos, m.it.e, m.n_csc);
+        SBMF_LAUNCH((permute_gather_kernel), gr, 256, 0, st, m.recvbuf, m.recv_pos, m.it.e, m.n_csc);
     } else {
-        if (ensure_inverse(m, m.recv_pos, &m.recv_pos_inv, m.n_csc, st)) permute_gather_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos_inv, m.recvbuf, m.n_csc);
-        else permute_scatter_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos, m.recvbuf, m.n_csc);
+        if (ensure_inverse(m, m.recv_pos, &m.recv_pos_inv, m.n_csc, st)) SBMF_LAUNCH((permute_gather_kernel), gr, 256, 0, st, m.it.e, m.recv_pos_inv, m.recvbuf, m.n_csc);
+        else SBMF_LAUNCH((permute_scatter_kernel), gr, 256, 0, st, m.it.e, m.recv_pos, m.recvbuf, m.n_csc);
         rc |= comm_group_begin(m.err);
         rc |= comm_alltoallv_f32(m.comm, m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), m.sendbuf, m.send_off.data(), m.send_cnt.data(), st, m.err);
         if (gather_side) rc |= launch_allgather_side(m, *gather_side, st);
         rc |= comm_group_end(m.err);
-        if (ensure_inverse(m, m.send_idx, &m.send_idx_inv, m.n_csr, st)) permute_gather_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx_inv, m.us.e, m.n_csr);
-        else permute_scatter_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx, m.us.e, m.n_csr);
+        if (ensure_inverse(m, m.send_idx, &m.send_idx_inv, m.n_csr, st)) SBMF_LAUNCH((permute_gather_kernel), gs, 256, 0, st, m.sendbuf, m.send_idx_inv, m.us.e, m.n_csr);
+        else SBMF_LAUNCH((permute_scatter_kernel), gs, 256, 0, st, m.sendbuf, m.send_idx, m.us.e, m.n_csr);
     }
     m.launches += 2;
     return rc;
@@ -1475,9 +1480,9 @@ static int permute_peer(Model& m, bool csr_to_csc, cudaStream_t st)
             pa.dst_off[q] = m.fwd_dst_off[q];
         }
         pa.seg_off[m.world] = m.n_csr;
-        push_kernel<<<gs, 256, 0, st>>>(m.us.e, m.send_idx, pa, m.n_csr);
+        SBMF_LAUNCH((push_kernel), gs, 256, 0, st, m.us.e, m.send_idx, pa, m.n_csr);
         int rc = launch_barrier(m, st);   // also: every peer has finished its user phase, so all U rows / biases have landed here
-        permute_gather_kernel<<<gr, 256, 0, st>>>(m.recvbuf, m.recv_pos, m.it.e, m.n_csc);
+        SBMF_LAUNCH((permute_gather_kernel), gr, 256, 0, st, m.recvbuf, m.recv_pos, m.it.e, m.n_csc);
         m.launches += 2;
         return rc;
     }
@@ -1492,16 +1497,16 @@ static int permute_peer(Model& m, bool csr_to_csc, cudaStream_t st)
     }
     pa.seg_off[m.world] = m.n_csc;
     // position i of my receive order holds local CSC slot recv_pos_inv[i]; it returns to the rank it came from
-    push_kernel<<<gr, 256, 0, st>>>(m.it.e, m.recv_pos_inv, pa, m.n_csc);
+    SBMF_LAUNCH((push_kernel), gr, 256, 0, st, m.it.e, m.recv_pos_inv, pa, m.n_csc);
     int rc = launch_barrier(m, st);       // also: all V rows / item biases have landed
-    permute_gather_kernel<<<gs, 256, 0, st>>>(m.sendbuf, m.send_idx_inv, m.us.e, m.n_csr);
+    SBMF_LAUNCH((permute_gather_kernel), gs, 256, 0, st, m.sendbuf, m.send_idx_inv, m.us.e, m.n_csr);
     m.launches += 2;
     return rc;
 }
 
 int launch_reduce_pair(Model& m, cudaStream_t st)
 {
-    reduce_pair_kernel<<<1, RED_THREADS, 0, st>>>(m.red_part, m.red_blocks, m.red2);
+    SBMF_LAUNCH((reduce_pair_kernel), 1, RED_THREADS, 0, st, m.red_part, m.red_blocks, m.red2);
     m.launches++;
     if (m.world > 1) return comm_allreduce_sum_f64(m.comm, m.red2, 2, st, m.err);
     return 0;
@@ -1527,7 +1532,7 @@ int launch_allgather_side(Model& m, Side& s, cudaStream_t st)
 void launch_eval(Model& m, cudaStream_t st)
 {
     const uint64_t t0 = m.t_begin, nt = m.t_end - m.t_begin;   // this rank's slice of the test set
-    eval_kernel<<<m.red_blocks, RED_THREADS, 0, st>>>(m.t_user + t0, m.t_item + t0, m.t_r + t0, m.t_sum + t0, m.us.F, m.it.F, m.us.bias, m.it.bias,
+    SBMF_LAUNCH((eval_kernel), m.red_blocks, RED_THREADS, 0, st, m.t_user + t0, m.t_item + t0, m.t_r + t0, m.t_sum + t0, m.us.F, m.it.F, m.us.bias, m.it.bias,
                                                       m.sc, m.I + 1, m.J + 1, m.KB, nt, m.cfg.burn_in, (float)m.cfg.clamp_lo, (float)m.cfg.clamp_hi,
                                                       m.red_part);
     m.launches++;
@@ -1541,13 +1546,13 @@ pred_mean_kernel(const double* __restrict__ tsum, float* __restrict__ out, uint6
 
 void launch_pred_mean(Model& m, float* d_out, double denom, cudaStream_t st)
 {
-    pred_mean_kernel<<<grid_for(m.Nt, 256, m.sm_count * 8), 256, 0, st>>>(m.t_sum, d_out, m.Nt, denom);
+    SBMF_LAUNCH((pred_mean_kernel), grid_for(m.Nt, 256, m.sm_count * 8), 256, 0, st, m.t_sum, d_out, m.Nt, denom);
     m.launches++;
 }
 
 void launch_eval_final(Model& m, cudaStream_t st)
 {
-    eval_final_kernel<<<1, 32, 0, st>>>(m.sc, m.red2, m.Nt, m.rmse_hist, m.hist_cap);
+    SBMF_LAUNCH((eval_final_kernel), 1, 32, 0, st, m.sc, m.red2, m.Nt, m.rmse_hist, m.hist_cap);
     m.launches++;
 }
 

@@ -18,6 +18,7 @@
 #include <cub/cub.cuh>
 #include <vector>
 
+#include "launch.h"
 #include "model.h"
 
 namespace sbmf {
@@ -400,7 +401,11 @@ __device__ __forceinline__ int owner_of(const int64_t* b, int world, int64_t slo
 __global__ void __launch_bounds__(256)
 pair_count_kernel(const uint32_t* __restrict__ perm, uint64_t n, ShardBounds b, unsigned long long* __restrict__ counts)
 {
+#ifdef SBMF_SIMT_EMU
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(simt::block().dyn_smem.data());
+#else
     extern __shared__ uint32_t s_hist[];   // [world * world]
+#endif
     const int W = b.world;
     for (int i = threadIdx.x; i < W * W; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
@@ -480,16 +485,16 @@ static int plan_exchange_device(Model& m, cudaStream_t st, uint64_t N, const uin
     CKP(talloc(&d_tmp, std::max(sel_bytes, sort_bytes)));
     // traffic matrix
     CKP(cudaMemsetAsync(d_pc, 0, (size_t)G * G * 8, st));
-    if (N) pair_count_kernel<<<grid, T, (size_t)G * G * 4, st>>>(d_perm, N, b, d_pc);
+    if (N) SBMF_LAUNCH((pair_count_kernel), grid, T, (size_t)G * G * 4, st, d_perm, N, b, d_pc);
     // send order
     CKP(cub::DeviceSelect::If(d_tmp, sel_bytes, d_perm, d_send_idx, d_nsel, (int)N, in_shard, st));
-    if (n_csr) subtract_kernel<<<grid, T, 0, st>>>(d_send_idx, n_csr, (uint32_t)c0);
+    if (n_csr) SBMF_LAUNCH((subtract_kernel), grid, T, 0, st, d_send_idx, n_csr, (uint32_t)c0);
     // receive order
     if (n_csc) {
-        source_rank_kernel<<<grid_l, T, 0, st>>>(d_perm + t0, n_csc, b, d_key);
-        iota_kernel<<<grid_l, T, 0, st>>>(d_iota, n_csc);
+        SBMF_LAUNCH((source_rank_kernel), grid_l, T, 0, st, d_perm + t0, n_csc, b, d_key);
+        SBMF_LAUNCH((iota_kernel), grid_l, T, 0, st, d_iota, n_csc);
         CKP(cub::DeviceRadixSort::SortPairs(d_tmp, sort_bytes, d_key, d_key_out, d_iota, d_order, (int)n_csc, 0, bits_for((uint32_t)G), st));
-        invert_kernel<<<grid_l, T, 0, st>>>(d_order, d_recv_pos, n_csc);
+        SBMF_LAUNCH((invert_kernel), grid_l, T, 0, st, d_order, d_recv_pos, n_csc);
     }
     CKP(cudaGetLastError());
     std::vector<unsigned long long> pc((size_t)G * G);
@@ -613,8 +618,8 @@ static int shard_storage(Model& m)
     CK(slice_inplace(m.us.idx, c0, m.n_csr, st)); CK(slice_inplace(m.us.e, c0, m.n_csr, st)); CK(slice_inplace(m.csr_urow, c0, m.n_csr, st));
     CK(slice_inplace(m.csr_r, c0, m.n_csr, st)); CK(slice_inplace(m.csr_id, c0, m.n_csr, st));
     CK(slice_inplace(m.it.idx, t0, m.n_csc, st)); CK(slice_inplace(m.it.e, t0, m.n_csc, st)); CK(slice_inplace(m.csc_id, t0, m.n_csc, st));
-    rebase_kernel<<<(m.I + 256) / 256, 256, 0, m.s_main>>>(m.us.ptr, m.I, (int64_t)c0);
-    rebase_kernel<<<(m.J + 256) / 256, 256, 0, m.s_main>>>(m.it.ptr, m.J, (int64_t)t0);
+    SBMF_LAUNCH((rebase_kernel), (m.I + 256) / 256, 256, 0, m.s_main, m.us.ptr, m.I, (int64_t)c0);
+    SBMF_LAUNCH((rebase_kernel), (m.J + 256) / 256, 256, 0, m.s_main, m.it.ptr, m.J, (int64_t)t0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(m.s_main));
     return SBMF_OK;
@@ -688,7 +693,7 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     CKC(cudaMemcpyAsync(d_rating, rating, n * 4, cudaMemcpyHostToDevice, st));
     tr.lap("alloc + H2D");
     CKC(cudaMemsetAsync(d_max, 0, 8, st));
-    if (n) max_id_kernel<<<G, T, 0, st>>>(d_user, d_item, n, d_max);
+    if (n) SBMF_LAUNCH((max_id_kernel), G, T, 0, st, d_user, d_item, n, d_max);
     uint32_t h_max[2] = {0, 0};
     CKC(cudaMemcpyAsync(h_max, d_max, 8, cudaMemcpyDeviceToHost, st));
     CKC(cudaStreamSynchronize(st));
@@ -707,18 +712,18 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     size_t tmp_bytes = 0;
     CKC(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_user, d_keys, d_iota, m.csr_id, (int)n, 0, 32, st));
     CKC(talloc(&d_tmp, tmp_bytes));
-    iota_kernel<<<G, T, 0, st>>>(d_iota, n);
+    SBMF_LAUNCH((iota_kernel), G, T, 0, st, d_iota, n);
     // CSR: stable sort of the rating index by user
     CKC(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_user, m.csr_urow, d_iota, m.csr_id, (int)n, 0, bits_for(num_users), st));
-    row_ptr_kernel<<<(num_users + 1 + T - 1) / T, T, 0, st>>>(m.csr_urow, n, num_users, m.us.ptr);
-    gather_u32_kernel<<<G, T, 0, st>>>(d_item, m.csr_id, m.us.idx, n);
-    gather_f32_kernel<<<G, T, 0, st>>>(d_rating, m.csr_id, m.csr_r, n);
-    invert_kernel<<<G, T, 0, st>>>(m.csr_id, d_inv, n);
+    SBMF_LAUNCH((row_ptr_kernel), (num_users + 1 + T - 1) / T, T, 0, st, m.csr_urow, n, num_users, m.us.ptr);
+    SBMF_LAUNCH((gather_u32_kernel), G, T, 0, st, d_item, m.csr_id, m.us.idx, n);
+    SBMF_LAUNCH((gather_f32_kernel), G, T, 0, st, d_rating, m.csr_id, m.csr_r, n);
+    SBMF_LAUNCH((invert_kernel), G, T, 0, st, m.csr_id, d_inv, n);
     // CSC: stable sort of the rating index by item
     CKC(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_item, d_keys, d_iota, m.csc_id, (int)n, 0, bits_for(num_items), st));
-    row_ptr_kernel<<<(num_items + 1 + T - 1) / T, T, 0, st>>>(d_keys, n, num_items, m.it.ptr);
-    gather_u32_kernel<<<G, T, 0, st>>>(d_user, m.csc_id, m.it.idx, n);
-    gather_u32_kernel<<<G, T, 0, st>>>(d_inv, m.csc_id, m.perm, n);
+    SBMF_LAUNCH((row_ptr_kernel), (num_items + 1 + T - 1) / T, T, 0, st, d_keys, n, num_items, m.it.ptr);
+    SBMF_LAUNCH((gather_u32_kernel), G, T, 0, st, d_user, m.csc_id, m.it.idx, n);
+    SBMF_LAUNCH((gather_u32_kernel), G, T, 0, st, d_inv, m.csc_id, m.perm, n);
     CKC(cudaMemsetAsync(m.us.e, 0, (n ? n : 1) * 4, st));
     CKC(cudaMemsetAsync(m.it.e, 0, (n ? n : 1) * 4, st));
     CKC(cudaGetLastError());

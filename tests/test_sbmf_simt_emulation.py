@@ -1,0 +1,31 @@
+"""CPU: the kernels of the SBMF sweep (csrc/kernels.cu, storage.cu behind the C ABI of api.cu) executed without a GPU.
+
+tools/build_emu.sh compiles the library's own sources a second time with g++ against tools/emu_include (host stand-in for the CUDA
+runtime and the SIMT execution model: the threads of a CTA are host threads, barriers and shuffles are real synchronisation, see
+tests/test_fm_simt_emulation.py) and a selection of the GPU parity tests runs against that build unchanged (SBMF_LIB_PATH +
+SBMF_EMULATED): device-built CSR/CSC/permutation bit-exact, zero-noise parity with the pinned restatement on the small fixtures,
+edge cases, heavy (sliced) rows.  The kernels are GPU-validated already; what this adds is a second, independent
+execution of the same code -- and the build that tools/sbmf_sanitize.sh instruments with AddressSanitizer / ThreadSanitizer, the
+memory- and race-check that compute-sanitizer would do on a pool that allows it.  Test infrastructure only."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# fast members of tests/test_parity_gpu.py (~1 minute on host threads; all 8 heavy-row variants take 5, the ML-100K sweeps longer)
+SELECT = "layout_bit_exact or edge_ or error_behaviour or (zero_noise_heavy_rows and (8-False-1 or 8-True-0))"
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    r = subprocess.run(["bash", os.path.join(ROOT, "tools", "build_emu.sh")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return os.path.join(ROOT, "tools", "build", "libsbmf_cuda_emu.so")
+
+
+def test_sweep_kernels_on_cpu_threads(emu_lib):
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_parity_gpu.py"), "-x", "-q", "-k", SELECT],
+                       capture_output=True, text=True, timeout=3000, env=dict(os.environ, SBMF_EMULATED="1", SBMF_LIB_PATH=emu_lib))
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -31,6 +31,10 @@ struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 struct float2 { float x, y; };
 struct double2 { double x, y; };
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+template <class T> inline T min(T a, T b) { return b < a ? b : a; }
+template <class T> inline T max(T a, T b) { return a < b ? b : a; }
 inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
@@ -47,7 +51,15 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDe
 enum { cudaStreamNonBlocking = 1 };
 typedef struct emu_stream* cudaStream_t;
 struct cudaDeviceProp { int major, minor, multiProcessorCount; };
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// fresh "device" memory is filled with a byte pattern (SIMT_EMU_FILL, default 0xCD = garbage floats / huge indices): a kernel that
+// relies on cudaMalloc returning zeros -- which fresh GPU memory often happens to be -- shows up here
+inline cudaError_t cudaMalloc(void** p, size_t n)
+{
+    static const int fill = getenv("SIMT_EMU_FILL") ? (int)strtol(getenv("SIMT_EMU_FILL"), NULL, 0) : 0xCD;
+    *p = malloc(n ? n : 1);
+    if (*p) memset(*p, fill, n ? n : 1);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memcpy(d, s, n); return cudaSuccess; }
@@ -278,6 +290,8 @@ inline T __shfl_sync(unsigned, T v, int src_lane, int width = 32)
 }
 template <class T>
 inline T __ldg(const T* p) { return *p; }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline uint32_t atomicMin(uint32_t* a, uint32_t v)
 {
     uint32_t old = __atomic_load_n(a, __ATOMIC_RELAXED);
