@@ -71,5 +71,5 @@ def test_patched_libfm_reaches_the_library(patched, tmp_path):
 def test_patched_libfm_prints_the_binding_trajectory(patched):
     """tests/fm_gpu_cases.py::case_libfm_learner in a process of its own (the CPU suite runs the same case on the CPU execution of the
     kernels, tests/test_fm_simt_emulation.py)"""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fm_gpu_cases.py"), "libfm_learner"], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fm_gpu_cases.py"), "libfm_learner"], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "ok libfm_learner" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

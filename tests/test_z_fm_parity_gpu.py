@@ -21,5 +21,5 @@ pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first run on a B200 pen
 
 @pytest.mark.parametrize("case", CASES)
 def test_fm_gpu_case(case):
-    r = subprocess.run([sys.executable, os.path.join(HERE, "fm_gpu_cases.py"), case], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "fm_gpu_cases.py"), case], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, (r.stdout[-2000:] + r.stderr[-4000:])
