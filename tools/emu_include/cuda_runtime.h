@@ -114,36 +114,35 @@ inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; 
 namespace simt {
 struct Idx { unsigned x, y, z; };
 struct Barrier {   // reusable barrier; waiters yield (far more host threads than cores, and episodes are short).  A thread that leaves the
-                   // kernel early drops out of the barriers of its CTA and warp, like an exited thread on the GPU
-    std::atomic<bool> lock{false};
+                   // kernel early drops out of the barriers of its CTA and warp, like an exited thread on the GPU.
+                   // Lock-free: state = live threads << 32 | threads waiting.  Whoever makes waiting reach live (the last arrival,
+                   // or a drop that leaves only waiters) is alone at that moment -- every other live thread spins on gen -- so it
+                   // may reset the count with a plain store before it opens the next generation.
+    std::atomic<uint64_t> state{0};
     std::atomic<unsigned> gen{0};
-    int n = 0, waiting = 0;
-    void acquire() { while (lock.exchange(true, std::memory_order_acquire)) std::this_thread::yield(); }
-    void release() { lock.store(false, std::memory_order_release); }
+    void arm(int n) { state.store((uint64_t)(unsigned)n << 32, std::memory_order_relaxed); }
     void wait()
     {
-        acquire();
-        const unsigned g = gen.load(std::memory_order_relaxed);
-        if (++waiting >= n) {
-            waiting = 0;
+        const unsigned g = gen.load(std::memory_order_acquire);   // cannot advance before this thread has arrived
+        const uint64_t old = state.fetch_add(1, std::memory_order_acq_rel);
+        const uint64_t n = old >> 32, w = (old & 0xffffffffu) + 1;
+        if (w >= n) {
+            state.store(n << 32, std::memory_order_relaxed);
             gen.store(g + 1, std::memory_order_release);
-            release();
             return;
         }
-        release();
         int spins = 0;
         while (gen.load(std::memory_order_acquire) == g)
             if (++spins > 16) std::this_thread::yield();   // (sleeping -- futex or nanosleep back-off -- was measured 5-8x slower: episodes are short)
     }
     void drop()
     {
-        acquire();
-        --n;
-        if (n > 0 && waiting >= n) {
-            waiting = 0;
-            gen.store(gen.load(std::memory_order_relaxed) + 1, std::memory_order_release);
+        const uint64_t old = state.fetch_sub((uint64_t)1 << 32, std::memory_order_acq_rel);
+        const uint64_t n = (old >> 32) - 1, w = old & 0xffffffffu;
+        if (n > 0 && w >= n) {
+            state.store(n << 32, std::memory_order_relaxed);
+            gen.fetch_add(1, std::memory_order_release);
         }
-        release();
     }
 };
 struct Block {
@@ -224,16 +223,11 @@ inline void launch(dim3 grid, dim3 blk, F&& body, size_t dyn_smem_bytes = 0)
     Block& b = block();
     b.dyn_smem.assign(dyn_smem_bytes + 16, 0);
     auto arm = [&] {
-        b.all.n = nt;
-        b.all.waiting = 0;
-        for (int w = 0; w < 32; ++w) {
-            b.warp[w].n = std::max(0, std::min(32, nt - 32 * w));
-            b.warp[w].waiting = 0;
-        }
+        b.all.arm(nt);
+        for (int w = 0; w < 32; ++w) b.warp[w].arm(std::max(0, std::min(32, nt - 32 * w)));
     };
     arm();
-    b.done.n = nt;
-    b.done.waiting = 0;
+    b.done.arm(nt);
     pool().run(nt, [&](int t) {
         t_bdim = blk;
         t_gdim = grid;
