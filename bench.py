@@ -232,6 +232,8 @@ def main():
            "sample_mode": "reference (x = mu + (1/lambda) z)"}
 
     import sbmf
+    if os.environ.get("SBMF_EMULATED") or hasattr(sbmf.load_library(), "sbmf_simt_host_emulation"):
+        raise SystemExit("bench.py measures the CUDA library on a B200; the host-emulation build of the kernels is test infrastructure")
     if a.impl == "reference":
         if rank != 0:
             return

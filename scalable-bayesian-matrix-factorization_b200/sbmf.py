@@ -132,6 +132,10 @@ def load_library(path=None):
     if _lib is not None and path is None:
         return _lib
     lib = C.CDLL(path or LIB_PATH)
+    # tools/build_emu.sh (test infrastructure: the kernels on host threads, for the race / memory checks) marks its output with this
+    # symbol; such a library is only accepted when the test harness asks for it by name, never by accident
+    if hasattr(lib, "sbmf_simt_host_emulation") and os.environ.get("SBMF_EMULATED") != "1":
+        raise OSError(f"{path or LIB_PATH} is the host-emulation test build of the kernels, not the CUDA library (there is no CPU path)")
     P = C.POINTER
     lib.sbmf_cuda_abi_version.restype = C.c_int
     lib.sbmf_cuda_config_default.argtypes = [P(Config)]

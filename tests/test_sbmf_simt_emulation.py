@@ -38,3 +38,15 @@ def test_smoke_job_on_cpu_threads(emu_lib):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1500,
                        env=dict(os.environ, SBMF_EMULATED="1", SBMF_LIB_PATH=emu_lib))
     assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_bindings_refuse_the_emulation_build_unasked(emu_lib):
+    """The host build is reachable only when the harness names it AND says so (SBMF_EMULATED=1): the binding and bench.py refuse it."""
+    env = {k: v for k, v in os.environ.items() if k != "SBMF_EMULATED"}
+    code = ("import sys; sys.path.insert(0, %r); import sbmf\n"
+            "try:\n    sbmf.load_library()\nexcept OSError as e:\n    print('refused:', e)\n" % os.path.join(ROOT, "scalable-bayesian-matrix-factorization_b200"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(env, SBMF_LIB_PATH=emu_lib))
+    assert "refused:" in r.stdout and "no CPU path" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       env=dict(os.environ, SBMF_EMULATED="1", SBMF_LIB_PATH=emu_lib))
+    assert r.returncode != 0 and "test infrastructure" in r.stderr and "{" not in r.stdout, r.stdout + r.stderr

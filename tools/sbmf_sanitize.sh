@@ -2,7 +2,7 @@
 # tools/sbmf_sanitize.sh -- the SBMF sweep kernels (csrc/kernels.cu, storage.cu behind the C ABI of api.cu) under AddressSanitizer /
 # ThreadSanitizer.  compute-sanitizer is closed on this GPU pool, so this is the memory- and race-check of the hot path: the host
 # build of the library's own sources (tools/build_emu.sh: CTAs on host threads, barriers and shuffles are real synchronisation),
-# instrumented by g++ and driven by members of tests/test_parity_gpu.py (SBMF_EMULATED=1 + SBMF_LIB_PATH).  CPU only, ~15 minutes.
+# instrumented by g++ and driven by members of tests/test_parity_gpu.py (SBMF_EMULATED=1 + SBMF_LIB_PATH).  CPU only, ~5 minutes.
 #   ASan: out-of-bounds / use-after-free in kernels and host orchestration ("device" memory is malloc'ed and filled with 0xCD, so
 #         a kernel that relies on cudaMalloc returning zeros fails the parity check as well)
 #   TSan: races between the threads of a CTA -- a read that is only ordered before another lane's write by warp lock-step, a
