@@ -2,7 +2,7 @@
 # tools/sbmf_sanitize.sh -- the SBMF sweep kernels (csrc/kernels.cu, storage.cu behind the C ABI of api.cu) under AddressSanitizer /
 # ThreadSanitizer.  compute-sanitizer is closed on this GPU pool, so this is the memory- and race-check of the hot path: the host
 # build of the library's own sources (tools/build_emu.sh: CTAs on host threads, barriers and shuffles are real synchronisation),
-# instrumented by g++ and driven by members of tests/test_parity_gpu.py (SBMF_EMULATED=1 + SBMF_LIB_PATH).  CPU only, ~5 minutes.
+# instrumented by g++ and driven by members of tests/test_parity_gpu.py (SBMF_EMULATED=1 + SBMF_LIB_PATH).  CPU only, ~7 minutes.
 #   ASan: out-of-bounds / use-after-free in kernels and host orchestration ("device" memory is malloc'ed and filled with 0xCD, so
 #         a kernel that relies on cudaMalloc returning zeros fails the parity check as well)
 #   TSan: races between the threads of a CTA -- a read that is only ordered before another lane's write by warp lock-step, a
@@ -25,5 +25,9 @@ if ls tools/build/asan_rep.* > /dev/null 2>&1; then grep -h "^SUMMARY" tools/bui
 SBMF_EMULATED=1 TSAN_OPTIONS="report_signal_unsafe=0 history_size=2 log_path=$PWD/tools/build/tsan_rep" LD_PRELOAD=$TSAN SBMF_LIB_PATH=$PWD/tools/build/libsbmf_cuda_emu_tsan.so \
   python -m pytest tests/test_parity_gpu.py -q -x -k "edge_latent or edge_single or (zero_noise_heavy_rows and (8-False-1 or 8-True-0))" 2>&1 | tail -2 | tee tools/build/tsan_pytest.log
 grep -q " passed" tools/build/tsan_pytest.log && ! grep -q "failed" tools/build/tsan_pytest.log || { echo "tsan: cases failed"; rc=1; }
+# the smoke job (ML-100K, K = 20: every resident-row bin of a real data set, zero-noise and live Philox sampling) under TSan
+SBMF_EMULATED=1 TSAN_OPTIONS="report_signal_unsafe=0 history_size=2 log_path=$PWD/tools/build/tsan_rep" LD_PRELOAD=$TSAN SBMF_LIB_PATH=$PWD/tools/build/libsbmf_cuda_emu_tsan.so \
+  python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee tools/build/tsan_smoke.log
+grep -q "smoke ok" tools/build/tsan_smoke.log || { echo "tsan: smoke job failed"; rc=1; }
 if ls tools/build/tsan_rep.* > /dev/null 2>&1; then grep -h "^SUMMARY" tools/build/tsan_rep.* | sort | uniq -c; echo "tsan: findings"; rc=1; fi
 echo "sbmf_sanitize rc=$rc"; exit $rc
