@@ -251,6 +251,50 @@ def tiny_case(I, J, pairs, ratings, test_pairs=((0, 0),), test_ratings=(3.0,)):
             "test_rating": np.array(test_ratings, np.float32), "num_users": I, "num_items": J}
 
 
+def ragged_case(seed):
+    """Random small rating file the way [T] would read it: unsorted, users and items without ratings (leading, trailing and in
+    between), the same (user, item) pair rated more than once (two entries of the jagged rows, [T]:209-214), row lengths from 1
+    to a few hundred so that several resident bins and both row-group widths occur in one matrix."""
+    rs = np.random.RandomState(1000 + seed)
+    I, J = int(rs.randint(1, 70)), int(rs.randint(1, 400))
+    alive_u = np.flatnonzero(rs.rand(I) < 0.8)
+    if alive_u.size == 0:
+        alive_u = np.array([I - 1])
+    us, its = [], []
+    for u in alive_u:
+        dg = int(min(J, max(1, rs.geometric(1.0 / rs.choice([2, 12, 60, 250])))))
+        it = rs.choice(J, dg, replace=False)
+        us.append(np.full(dg, u)); its.append(it)
+    u = np.concatenate(us); i = np.concatenate(its)
+    dup = rs.randint(0, u.size, max(1, u.size // 20))       # repeated pairs
+    u = np.concatenate([u, u[dup]]); i = np.concatenate([i, i[dup]])
+    order = rs.permutation(u.size)
+    u, i = u[order].astype(np.uint32), i[order].astype(np.uint32)
+    r = rs.randint(1, 11, u.size).astype(np.float32) / 2
+    nt = int(rs.randint(1, 20))
+    return {"train_user": u, "train_item": i, "train_rating": r, "test_user": rs.randint(0, I, nt).astype(np.uint32),
+            "test_item": rs.randint(0, J, nt).astype(np.uint32), "test_rating": rs.randint(1, 6, nt).astype(np.float32),
+            "num_users": I, "num_items": J}
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_ragged_random_files(seed):
+    """Layout bit-exact and 3 zero-noise sweeps within 1e-4 on random ragged inputs (empty rows, repeated pairs, unsorted)."""
+    d = ragged_case(seed)
+    K = [3, 8, 20, 33][seed % 4]
+    m, o = make_pair(d, K, 2, residual_mode=seed % 2)
+    got, want = m.get_layout(), o.layout()
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    init_both(m, o, d, K)
+    m.sweep(3)
+    r_o, _ = o.sweep(3)
+    check_state(m.get_state(), o.state(), 1e-4)
+    r_g, _ = m.rmse_history(0, 3)
+    assert np.max(np.abs(r_g - r_o)) <= 1e-5
+    m.close()
+
+
 @pytest.mark.parametrize("K", [1, 7, 8, 9, 64, 256])
 def test_edge_latent_dimensions(K, tiny):
     """K not a multiple of the 8-wide factor block, K = 1 and K = SBMF_MAX_K."""

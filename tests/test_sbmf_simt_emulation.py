@@ -15,7 +15,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # fast members of tests/test_parity_gpu.py (~1 minute on host threads; all 8 heavy-row variants take 5, the ML-100K sweeps longer)
-SELECT = "layout_bit_exact or edge_ or error_behaviour or (zero_noise_heavy_rows and (8-False-1 or 8-True-0))"
+SELECT = "layout_bit_exact or ragged_random or edge_ or error_behaviour or (zero_noise_heavy_rows and (8-False-1 or 8-True-0))"
 
 
 @pytest.fixture(scope="module")

@@ -15,7 +15,7 @@ cd "$(dirname "$0")/.."
 bash tools/build_emu.sh libsbmf_cuda_emu_asan.so -fsanitize=address -fno-omit-frame-pointer -g > /dev/null || exit 1
 bash tools/build_emu.sh libsbmf_cuda_emu_tsan.so -fsanitize=thread -g > /dev/null 2>&1 || exit 1
 ASAN=$(gcc -print-file-name=libasan.so); TSAN=$(gcc -print-file-name=libtsan.so)
-SEL="layout_bit_exact or edge_ or error_behaviour or (zero_noise_heavy_rows and (8-False-1 or 8-True-0 or 20-False-0))"
+SEL="layout_bit_exact or ragged_random or edge_ or error_behaviour or (zero_noise_heavy_rows and (8-False-1 or 8-True-0 or 20-False-0))"
 rc=0
 rm -f tools/build/asan_rep.* tools/build/tsan_rep.*
 SBMF_EMULATED=1 ASAN_OPTIONS="detect_leaks=0 log_path=$PWD/tools/build/asan_rep" LD_PRELOAD=$ASAN SBMF_LIB_PATH=$PWD/tools/build/libsbmf_cuda_emu_asan.so \
@@ -23,7 +23,7 @@ SBMF_EMULATED=1 ASAN_OPTIONS="detect_leaks=0 log_path=$PWD/tools/build/asan_rep"
 grep -q " passed" tools/build/asan_pytest.log && ! grep -q "failed" tools/build/asan_pytest.log || { echo "asan: cases failed"; rc=1; }
 if ls tools/build/asan_rep.* > /dev/null 2>&1; then grep -h "^SUMMARY" tools/build/asan_rep.* | sort | uniq -c; echo "asan: findings"; rc=1; fi
 SBMF_EMULATED=1 TSAN_OPTIONS="report_signal_unsafe=0 history_size=2 log_path=$PWD/tools/build/tsan_rep" LD_PRELOAD=$TSAN SBMF_LIB_PATH=$PWD/tools/build/libsbmf_cuda_emu_tsan.so \
-  python -m pytest tests/test_parity_gpu.py -q -x -k "edge_latent or edge_single or (zero_noise_heavy_rows and (8-False-1 or 8-True-0))" 2>&1 | tail -2 | tee tools/build/tsan_pytest.log
+  python -m pytest tests/test_parity_gpu.py -q -x -k "ragged_random or edge_latent or edge_single or (zero_noise_heavy_rows and (8-False-1 or 8-True-0))" 2>&1 | tail -2 | tee tools/build/tsan_pytest.log
 grep -q " passed" tools/build/tsan_pytest.log && ! grep -q "failed" tools/build/tsan_pytest.log || { echo "tsan: cases failed"; rc=1; }
 # the smoke job (ML-100K, K = 20: every resident-row bin of a real data set, zero-noise and live Philox sampling) under TSan
 SBMF_EMULATED=1 TSAN_OPTIONS="report_signal_unsafe=0 history_size=2 log_path=$PWD/tools/build/tsan_rep" LD_PRELOAD=$TSAN SBMF_LIB_PATH=$PWD/tools/build/libsbmf_cuda_emu_tsan.so \
