@@ -30,4 +30,13 @@ SBMF_EMULATED=1 TSAN_OPTIONS="report_signal_unsafe=0 history_size=2 log_path=$PW
   python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee tools/build/tsan_smoke.log
 grep -q "smoke ok" tools/build/tsan_smoke.log || { echo "tsan: smoke job failed"; rc=1; }
 if ls tools/build/tsan_rep.* > /dev/null 2>&1; then grep -h "^SUMMARY" tools/build/tsan_rep.* | sort | uniq -c; echo "tsan: findings"; rc=1; fi
+# WIDE=1: more of the GPU suite on the plain (uninstrumented) host build, ~4 minutes -- tiny-fixture parity in every mode, incremental
+# residual, determinism, re-initialisation, burn-in / sqrt mode, live chains on shared Philox streams, checkpoint / resume
+if [ "${WIDE:-0}" = 1 ]; then
+  bash tools/build_emu.sh > /dev/null || exit 1
+  SBMF_EMULATED=1 SBMF_LIB_PATH=$PWD/tools/build/libsbmf_cuda_emu.so python -m pytest tests/test_parity_gpu.py tests/test_state_resume.py -q \
+    -k "((zero_noise_10_sweeps or ng_mode_zero_noise) and tiny) or incremental_residual or determinism or reset_by_init or burn_in_and_sqrt or live_same_philox or (resume and not cli)" \
+    2>&1 | tail -2 | tee tools/build/wide_pytest.log
+  grep -q " passed" tools/build/wide_pytest.log && ! grep -q "failed" tools/build/wide_pytest.log || { echo "wide: cases failed"; rc=1; }
+fi
 echo "sbmf_sanitize rc=$rc"; exit $rc
