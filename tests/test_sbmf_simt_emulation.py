@@ -50,3 +50,11 @@ def test_bindings_refuse_the_emulation_build_unasked(emu_lib):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                        env=dict(os.environ, SBMF_EMULATED="1", SBMF_LIB_PATH=emu_lib))
     assert r.returncode != 0 and "test infrastructure" in r.stderr and "{" not in r.stdout, r.stdout + r.stderr
+
+
+def test_host_cli_on_cpu_threads(emu_lib):
+    """The product's host program (bin/sbmf, linked against libsbmf_cuda.so) with the emulation build preloaded over it: -dump_xt writes
+    the device-built layout byte-identical to the reference's transpose tool, for libFM text, libFM binary and triple input."""
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_xt_format.py"), "-x", "-q", "-m", "gpu", "-k", "cli_dump_xt"],
+                       capture_output=True, text=True, timeout=1500, env=dict(os.environ, SBMF_EMULATED="1", SBMF_LIB_PATH=emu_lib, LD_PRELOAD=emu_lib))
+    assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

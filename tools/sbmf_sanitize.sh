@@ -38,5 +38,9 @@ if [ "${WIDE:-0}" = 1 ]; then
     -k "((zero_noise_10_sweeps or ng_mode_zero_noise) and tiny) or incremental_residual or determinism or reset_by_init or burn_in_and_sqrt or live_same_philox or (resume and not cli)" \
     2>&1 | tail -2 | tee tools/build/wide_pytest.log
   grep -q " passed" tools/build/wide_pytest.log && ! grep -q "failed" tools/build/wide_pytest.log || { echo "wide: cases failed"; rc=1; }
+  # the host CLI (bin/sbmf) with the host build preloaded over libsbmf_cuda.so: CLI == binding, -dump_xt, -save_state / -load_state
+  SBMF_EMULATED=1 LD_PRELOAD=$PWD/tools/build/libsbmf_cuda_emu.so SBMF_LIB_PATH=$PWD/tools/build/libsbmf_cuda_emu.so python -m pytest \
+    tests/test_cli.py tests/test_xt_format.py tests/test_state_resume.py -q -m gpu -k cli 2>&1 | tail -2 | tee tools/build/wide_cli.log
+  grep -q " passed" tools/build/wide_cli.log && ! grep -q "failed" tools/build/wide_cli.log || { echo "wide: CLI cases failed"; rc=1; }
 fi
 echo "sbmf_sanitize rc=$rc"; exit $rc
