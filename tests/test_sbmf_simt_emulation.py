@@ -58,3 +58,12 @@ def test_host_cli_on_cpu_threads(emu_lib):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_xt_format.py"), "-x", "-q", "-m", "gpu", "-k", "cli_dump_xt"],
                        capture_output=True, text=True, timeout=1500, env=dict(os.environ, SBMF_EMULATED="1", SBMF_LIB_PATH=emu_lib, LD_PRELOAD=emu_lib))
     assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_planner_and_second_fixture_on_cpu_threads(emu_lib):
+    """Device-side exchange planner == host planner for every rank at world 2 / 3 / 8 (csrc/storage.cu), and the layout of the second
+    real fixture (975 empty item rows) bit-exact -- the GPU cases, on host threads."""
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_sharding.py"),
+                        os.path.join(ROOT, "tests", "test_y_parity_second_fixture.py"), "-x", "-q", "-m", "gpu", "-k", "device_planner or layout_bit_exact_second"],
+                       capture_output=True, text=True, timeout=1500, env=dict(os.environ, SBMF_EMULATED="1", SBMF_LIB_PATH=emu_lib))
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
