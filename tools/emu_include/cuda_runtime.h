@@ -56,8 +56,9 @@ struct cudaDeviceProp { int major, minor, multiProcessorCount; };
 inline cudaError_t cudaMalloc(void** p, size_t n)
 {
     static const int fill = getenv("SIMT_EMU_FILL") ? (int)strtol(getenv("SIMT_EMU_FILL"), NULL, 0) : 0xCD;
-    *p = malloc(n ? n : 1);
-    if (*p) memset(*p, fill, n ? n : 1);
+    const size_t bytes = ((n ? n : 1) + 255) / 256 * 256;
+    *p = aligned_alloc(256, bytes);   // cudaMalloc's alignment: the 256-bit accesses of the kernels are checked against it (UBSan)
+    if (*p) memset(*p, fill, bytes);
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }

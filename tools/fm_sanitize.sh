@@ -34,4 +34,12 @@ for c in zero_mf zero_general; do
   echo "$out" | grep "WARNING: ThreadSanitizer" && rc=1
   echo "tsan $c done"
 done
+# UBSan: misaligned accesses, signed overflow, shifts (first finding aborts the case)
+g++ $COMMON $SHRUNK -fsanitize=undefined -fno-sanitize-recover=undefined -o $B/libsbmf_fm_emu_ubsan.so $SRC || exit 1
+for c in zero_general zero_variants zero_als errors; do
+  out=$(LD_PRELOAD=$(gcc -print-file-name=libubsan.so) SBMF_FM_LIB_PATH=$PWD/$B/libsbmf_fm_emu_ubsan.so python tests/fm_gpu_cases.py $c 2>&1)
+  echo "$out" | grep -q "^ok $c" || { echo "ubsan $c: case failed"; rc=1; }
+  echo "$out" | grep "runtime error" && rc=1
+  echo "ubsan $c done"
+done
 echo "fm_sanitize rc=$rc"; exit $rc

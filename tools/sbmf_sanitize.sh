@@ -1,6 +1,6 @@
 #!/bin/bash
 # tools/sbmf_sanitize.sh -- the SBMF sweep kernels (csrc/kernels.cu, storage.cu behind the C ABI of api.cu) under AddressSanitizer /
-# ThreadSanitizer.  compute-sanitizer is closed on this GPU pool, so this is the memory- and race-check of the hot path: the host
+# ThreadSanitizer / UBSan.  compute-sanitizer is closed on this GPU pool, so this is the memory- and race-check of the hot path: the host
 # build of the library's own sources (tools/build_emu.sh: CTAs on host threads, barriers and shuffles are real synchronisation),
 # instrumented by g++ and driven by members of tests/test_parity_gpu.py (SBMF_EMULATED=1 + SBMF_LIB_PATH).  CPU only, ~7 minutes.
 #   ASan: out-of-bounds / use-after-free in kernels and host orchestration ("device" memory is malloc'ed and filled with 0xCD, so
@@ -30,6 +30,13 @@ SBMF_EMULATED=1 TSAN_OPTIONS="report_signal_unsafe=0 history_size=2 log_path=$PW
   python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee tools/build/tsan_smoke.log
 grep -q "smoke ok" tools/build/tsan_smoke.log || { echo "tsan: smoke job failed"; rc=1; }
 if ls tools/build/tsan_rep.* > /dev/null 2>&1; then grep -h "^SUMMARY" tools/build/tsan_rep.* | sort | uniq -c; echo "tsan: findings"; rc=1; fi
+# UBSan (-fno-sanitize-recover: the first finding aborts): misaligned 256-bit accesses (the host cudaMalloc returns 256-byte aligned
+# blocks like the real one, so sub-allocation offsets are checked), signed overflow, out-of-range shifts in index arithmetic
+bash tools/build_emu.sh libsbmf_cuda_emu_ubsan.so -fsanitize=undefined -fno-sanitize-recover=undefined -g > /dev/null 2>&1 || exit 1
+SBMF_EMULATED=1 LD_PRELOAD=$(gcc -print-file-name=libubsan.so) SBMF_LIB_PATH=$PWD/tools/build/libsbmf_cuda_emu_ubsan.so \
+  python -m pytest tests/test_parity_gpu.py -q -x -s -k "$SEL or live_same_philox" > tools/build/ubsan_pytest.log 2>&1
+tail -1 tools/build/ubsan_pytest.log
+grep -q " passed" tools/build/ubsan_pytest.log && ! grep -q "failed\|runtime error" tools/build/ubsan_pytest.log || { echo "ubsan: findings or failed cases"; grep -m3 "runtime error" tools/build/ubsan_pytest.log; rc=1; }
 # WIDE=1: more of the GPU suite on the plain (uninstrumented) host build, ~4 minutes -- tiny-fixture parity in every mode, incremental
 # residual, determinism, re-initialisation, burn-in / sqrt mode, live chains on shared Philox streams, checkpoint / resume
 if [ "${WIDE:-0}" = 1 ]; then
