@@ -59,6 +59,21 @@ SEED = 20151001 + 3
 METRIC = "gibbs_factor_updates_per_s"
 UNIT = "factor-updates/s"
 ALG_BYTES_PER_FU = 24.0          # 12 B per (rating, dimension) visit and half-step, two half-steps
+PKG = os.path.join(ROOT, "scalable-bayesian-matrix-factorization_b200")
+FULL_POINT = "ml10m_k100"        # BASELINE.json configs[1]: small enough for the reference's CPU program to run the WHOLE config
+
+
+def workload_config(name, world):
+    """The `config` object of the JSON line: a pure function of (workload, N), so that our arm and the reference arm print the
+    same object -- everything measured at run time (actual rating counts, generator seconds, ...) goes under "run"."""
+    I, J, NTRAIN, K = WORKLOADS[name]
+    return {"workload": f"{name}: synthetic Netflix/MovieLens-shaped Zipf rating matrix {I}x{J}, ~{NTRAIN} train ratings (+{int(TEST_FRAC * 100)}% test), K={K}; "
+                        "one step = one full Gibbs sweep (gibbs_sbpmf2.cpp:335-637); the reference arm / cpu_baseline time the reference's own "
+                        "program on a bounded sample of this matrix family (whole users, ~2M train ratings, all items, same K) -- see cpu_baseline.sample",
+            "users": I, "items": J, "K": K, "l2_policy": "working set per sweep (>2 GB) far exceeds the 126 MB L2; no flush needed",
+            "rebuild_every": 1, "residual_mode": "0: per-sweep residual rebuild of gibbs_sbpmf2.cpp:342-359 fused into the user phase",
+            "sample_mode": "reference (x = mu + (1/lambda) z)",
+            "parallelism": f"{world} GPU(s): users (CSR) and items (CSC) sharded by rating count, factors replicated" if world > 1 else "1 GPU"}
 
 
 def peaks():
@@ -112,7 +127,7 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's own gibbs_sbpmf2.cpp (oracle/_ref, built from /root/reference by
-# `make -C oracle ref`), else the oracle port.  A bounded sample of the workload: the first users of the same matrix.
+# `make -C oracle ref`), else the oracle port.  A bounded sample of the workload: the first users of the same matrix family.
 def write_triples(path, u, i, r):
     with open(path, "w") as f:
         np.savetxt(f, np.column_stack([u.astype(np.int64), i.astype(np.int64), r.astype(np.float64)]), fmt="%d\t%d\t%g")
@@ -131,32 +146,26 @@ def take_sample(d, n_target):
             "num_users": umax + 1, "num_items": d["num_items"]}
 
 
-def run_reference_binary(sample, K, threads, pairs=1, timeout=600):
-    """per-sweep seconds of the unmodified reference = (wall(T=Tb) - wall(T=1)) / (Tb - 1): load time cancels."""
+def ref_tools():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from run_ref import ref_binary, run_ref
-    Tb = 3 if ref_binary(K, 3) else 2
-    b1, b3 = ref_binary(K, 1), ref_binary(K, Tb)
-    if not b1 or not b3:
+    return ref_binary, run_ref
+
+
+def time_reference_files(train, test, K, threads, want_sweeps, timeout=900):
+    """Per-sweep seconds of the UNMODIFIED reference program on triple files: (wall(T=Tb) - wall(T=1)) / (Tb - 1), so reading and
+    indexing the files (identical in both runs) cancels.  Tb = the largest prebuilt sweep count with Tb - 1 <= want_sweeps."""
+    ref_binary, run_ref = ref_tools()
+    b1 = ref_binary(K, 1)
+    Tb = next((t for t in (21, 11, 6, 3, 2) if t - 1 <= max(want_sweeps, 1) and ref_binary(K, t)), None)
+    if not b1 or not Tb:
         return None
-    with tempfile.TemporaryDirectory(prefix="sbmf_bench_") as tmp:
-        tr, te = os.path.join(tmp, "train"), os.path.join(tmp, "test")
-        # the reference sizes its arrays by max id over train U test: make the item id space explicit with one test row
-        write_triples(tr, sample["train_user"], sample["train_item"], sample["train_rating"])
-        tu = np.append(sample["test_user"], sample["num_users"] - 1)
-        ti = np.append(sample["test_item"], sample["num_items"] - 1)
-        trr = np.append(sample["test_rating"], 3.0)
-        write_triples(te, tu, ti, trr)
-        per = []
-        rm = None
-        for _ in range(pairs):
-            r1 = run_ref(b1, tr, te, threads=threads, timeout=timeout)
-            r3 = run_ref(b3, tr, te, threads=threads, timeout=timeout)
-            if len(r1["rmse"]) != 1 or len(r3["rmse"]) != Tb:
-                return None
-            per.append((r3["wall_s"] - r1["wall_s"]) / (Tb - 1))
-            rm = r3["rmse"]
-    return {"s_per_sweep": float(np.median(per)), "sweeps_timed": pairs * (Tb - 1), "rmse": rm}
+    r1 = run_ref(b1, train, test, threads=threads, timeout=timeout)
+    rb = run_ref(ref_binary(K, Tb), train, test, threads=threads, timeout=timeout)
+    if len(r1["rmse"]) != 1 or len(rb["rmse"]) != Tb:
+        return None
+    return {"s_per_sweep": (rb["wall_s"] - r1["wall_s"]) / (Tb - 1), "sweeps_timed": Tb - 1, "rmse": rb["rmse"], "load_s": r1["wall_s"] - (rb["wall_s"] - r1["wall_s"]) / (Tb - 1),
+            "num_rows": rb["num_rows"], "num_users": rb["num_users"], "num_items": rb["num_items"]}
 
 
 def run_oracle_port(sample, K, steps, warmup):
@@ -172,42 +181,215 @@ def run_oracle_port(sample, K, steps, warmup):
     return {"s_per_sweep": dt / steps, "sweeps_timed": steps, "rmse": [float(x) for x in r]}
 
 
-def cpu_reference(sample, K, pairs=1, port_steps=2):
-    """Returns the cpu_baseline object: best of 1 thread and all host threads of the reference's OpenMP build."""
-    n = int(sample["train_user"].size)
+def cpu_reference_on_files(train, test, n_train, K, desc, want_sweeps, all_threads=True):
+    """cpu_baseline object from triple files: the reference binary at 1 thread and (optionally) at all host threads; best one wins."""
     ncpu = os.cpu_count() or 1
+    r1 = time_reference_files(train, test, K, 1, want_sweeps)
+    if not r1:
+        return None
+    runs = {1: r1}
+    if all_threads and ncpu > 1:
+        try:
+            rn = time_reference_files(train, test, K, ncpu, min(want_sweeps, 2), timeout=max(120.0, 40 * r1["s_per_sweep"] + 60))
+            if rn:
+                runs[ncpu] = rn
+        except Exception:   # noqa: BLE001 - glibc rand() lock contention can make the OpenMP run pathologically slow
+            desc += f"; OMP_NUM_THREADS={ncpu} run timed out (rand() lock contention, SURVEY.md 0.8)"
+    best = min(runs, key=lambda t: runs[t]["s_per_sweep"])
+    return {"value": n_train * K / runs[best]["s_per_sweep"], "unit": UNIT, "cores": best, "kind": "reference",
+            "sample": desc + "; unmodified gibbs_sbpmf2.cpp (g++ -O3 -fopenmp), per-sweep time = (wall(T=1+n) - wall(T=1)) / n so file loading cancels",
+            "by_threads": {str(t): n_train * K / v["s_per_sweep"] for t, v in runs.items()}, "host_cpus": ncpu,
+            "sweeps_timed": runs[best]["sweeps_timed"], "s_per_sweep": runs[best]["s_per_sweep"], "load_s": runs[best]["load_s"],
+            "n_train": int(n_train)}
+
+
+def cpu_reference(sample, K, want_sweeps=2):
+    """cpu_baseline of OUR arm: the reference binary on a sample cut from the matrix this run generated (port if the binaries are absent)."""
+    n = int(sample["train_user"].size)
     desc = f"first {sample['num_users']} users of the workload ({n} train ratings, {sample['num_items']} items, K={K})"
     out = None
     try:
-        r1 = run_reference_binary(sample, K, 1, pairs)
+        with tempfile.TemporaryDirectory(prefix="sbmf_bench_") as tmp:
+            tr, te = os.path.join(tmp, "train"), os.path.join(tmp, "test")
+            write_triples(tr, sample["train_user"], sample["train_item"], sample["train_rating"])
+            # the reference sizes its arrays by max id over train U test: make the item id space explicit with one test row
+            write_triples(te, np.append(sample["test_user"], sample["num_users"] - 1), np.append(sample["test_item"], sample["num_items"] - 1),
+                          np.append(sample["test_rating"], 3.0))
+            out = cpu_reference_on_files(tr, te, n, K, desc, want_sweeps)
     except Exception as e:   # noqa: BLE001 - the reference binary may be absent or time out; fall back to the port
-        r1 = None
         desc += f"; reference binary failed: {type(e).__name__}"
-    if r1:
-        runs = {1: r1}
-        if ncpu > 1:
-            try:
-                rn = run_reference_binary(sample, K, ncpu, 1, timeout=max(120.0, 40 * r1["s_per_sweep"] + 60))
-                if rn:
-                    runs[ncpu] = rn
-            except Exception:   # noqa: BLE001 - glibc rand() lock contention can make the OpenMP run pathologically slow
-                desc += f"; OMP_NUM_THREADS={ncpu} run timed out (rand() lock contention, SURVEY.md 0.8)"
-        best = min(runs, key=lambda t: runs[t]["s_per_sweep"])
-        out = {"value": n * K / runs[best]["s_per_sweep"], "unit": UNIT, "cores": best, "kind": "reference",
-               "sample": desc + f"; unmodified gibbs_sbpmf2.cpp (g++ -O3 -fopenmp), per-sweep time = (wall(T=3)-wall(T=1))/2",
-               "by_threads": {str(t): n * K / v["s_per_sweep"] for t, v in runs.items()}, "host_cpus": ncpu,
-               "sweeps_timed": runs[best]["sweeps_timed"], "s_per_sweep": runs[best]["s_per_sweep"]}
-    else:
-        r = run_oracle_port(sample, K, port_steps, 1)
+    if out is None:
+        r = run_oracle_port(sample, K, 2, 1)
         out = {"value": n * K / r["s_per_sweep"], "unit": UNIT, "cores": 1, "kind": "port",
                "sample": desc + "; oracle/sbmf_oracle.c (scalar C restatement of gibbs_sbpmf2.cpp), oracle/_ref binaries absent",
-               "host_cpus": ncpu, "sweeps_timed": r["sweeps_timed"], "s_per_sweep": r["s_per_sweep"]}
+               "host_cpus": os.cpu_count() or 1, "sweeps_timed": r["sweeps_timed"], "s_per_sweep": r["s_per_sweep"]}
     return out
+
+
+def synth_files(workload, tmp, max_train):
+    """bin/sbmf_synth (host generator, no CUDA, no libsbmf_cuda.so) -> triple files of (a whole-user prefix of) the workload."""
+    I, J, NTRAIN, _ = WORKLOADS[workload]
+    n = int(round(NTRAIN / (1 - TEST_FRAC)))
+    tr, te = os.path.join(tmp, f"{workload}.train"), os.path.join(tmp, f"{workload}.test")
+    exe = os.path.join(PKG, "bin", "sbmf_synth")
+    r = subprocess.run([exe, "-users", str(I), "-items", str(J), "-ratings", str(n), "-seed", str(SEED), "-test_frac", str(TEST_FRAC),
+                        "-max_train", str(max_train), "-train", tr, "-test", te], capture_output=True, text=True, check=True)
+    return tr, te, json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def reference_arm(a, world):
+    """bench.py --impl reference: the reference's own CPU program on the box's host cores.  This process loads NO library of this
+    repository: the sample comes from the stand-alone host generator (bin/sbmf_synth), the timed thing is a subprocess of the
+    unmodified reference binary.  Falls back to the oracle port (a C restatement) only if oracle/_ref was not built."""
+    I, J, NTRAIN, K = WORKLOADS[a.workload]
+    cfg = workload_config(a.workload, world)
+    with tempfile.TemporaryDirectory(prefix="sbmf_ref_arm_") as tmp:
+        t0 = time.perf_counter()
+        tr, te, info = synth_files(a.workload, tmp, a.cpu_sample)
+        gen_s = time.perf_counter() - t0
+        full = info["n_train"] == info["n_train_full"]
+        desc = (f"{'the WHOLE workload' if full else 'first ' + str(info['num_users']) + ' users of the workload'} ({info['n_train']} of {info['n_train_full']} train ratings, "
+                f"{info['num_items']} items, K={K}), matrix from the stand-alone host generator bin/sbmf_synth (same family, shape, seed and Zipf exponents as the GPU arm's device generator)")
+        cb = cpu_reference_on_files(tr, te, info["n_train"], K, desc, a.steps)
+        if cb is None:   # no reference binaries on this box: the oracle port
+            u, i, r = np.loadtxt(tr, dtype=np.float64, ndmin=2).T
+            su, si, sr = np.loadtxt(te, dtype=np.float64, ndmin=2).T
+            sample = {"train_user": u.astype(np.uint32), "train_item": i.astype(np.uint32), "train_rating": r.astype(np.float32), "test_user": su.astype(np.uint32),
+                      "test_item": si.astype(np.uint32), "test_rating": sr.astype(np.float32), "num_users": info["num_users"], "num_items": info["num_items"]}
+            rr = run_oracle_port(sample, K, max(1, min(a.steps, 5)), 1)
+            cb = {"value": info["n_train"] * K / rr["s_per_sweep"], "unit": UNIT, "cores": 1, "kind": "port", "sample": desc + "; oracle/sbmf_oracle.c, oracle/_ref binaries absent",
+                  "host_cpus": os.cpu_count() or 1, "sweeps_timed": rr["sweeps_timed"], "s_per_sweep": rr["s_per_sweep"], "n_train": info["n_train"]}
+        # one point where the reference runs the COMPLETE configuration (BASELINE.json configs[1], ML-10M-shaped K=100): the GPU
+        # arm prints the same key for the same workload, so this pair is a same-config ratio
+        full_point = None
+        if not a.no_full_point and a.workload != FULL_POINT:
+            try:
+                ftr, fte, finfo = synth_files(FULL_POINT, tmp, 0)
+                fK = WORKLOADS[FULL_POINT][3]
+                fr = time_reference_files(ftr, fte, fK, 1, 2, timeout=1200)
+                if fr:
+                    full_point = {"workload": FULL_POINT, "config": workload_config(FULL_POINT, 1), "value": finfo["n_train"] * fK / fr["s_per_sweep"], "unit": UNIT,
+                                  "s_per_sweep": fr["s_per_sweep"], "sweeps_timed": fr["sweeps_timed"], "n_train": finfo["n_train"], "cores": 1,
+                                  "load_s": fr["load_s"], "what": "unmodified gibbs_sbpmf2.cpp on the complete ML-10M-shaped K=100 configuration, 1 thread"}
+            except Exception as e:   # noqa: BLE001 - informational
+                full_point = {"workload": FULL_POINT, "error": f"{type(e).__name__}: {e}"}
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": cb["sweeps_timed"], "steps_requested": a.steps,
+            "warmup": a.warmup, "ms_per_step": cb["s_per_sweep"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "run": {"n_train_sample": info["n_train"], "n_train_workload": info["n_train_full"], "synth_seconds": round(gen_s, 2),
+                    "warmup_note": "the T=1 run of the pair is the warm-up: its sweep and the file loading are subtracted"},
+            "full_config_point": full_point}
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def load_traffic():
+    """measured DRAM bytes per rating of the dominant kernel (ncu --set full, profiles/): newest round first"""
+    for name in ("traffic_r2.json", "traffic_r1.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            t = json.load(open(p)).get("heavy_accumulate_kernel<2,2>", {})
+            if t.get("dram_bytes_per_rating"):
+                return float(t["dram_bytes_per_rating"]), name
+            if t.get("dram_bytes_per_launch") and t.get("ratings_per_launch"):
+                return float(t["dram_bytes_per_launch"]) / float(t["ratings_per_launch"]), name
+    return None, None
+
+
+def build_roofline(t, pr, peak_hbm, peak_src, K, KB, ms_per_step, n_test, world):
+    """Per launch of the dominant kernel and per sweep: streamed bytes against the HBM peak AND 32-byte sectors delivered by L2
+    against the gather rates sbmf_cuda_probe measured on this device a moment ago.  `bound` names the larger fraction."""
+    forms = pr["gather_sectors_per_s"]
+    best_form = max(forms, key=lambda k: forms[k])
+    same, best = forms["g32_lane"], forms[best_form]
+    roof = None
+    R = t["top_kernel_ratings"]
+    if t["top_kernel_launches"] and R:
+        us = t["ms_top_kernel"] / t["top_kernel_launches"] * 1e3
+        sec = us * 1e-6
+        sectors = 2.0 * R                       # block b-1 (delta apply) + block b (accumulate): one 32-byte sector each per rating
+        l2 = {"sectors_per_launch": sectors, "achieved_gbs": sectors * 32 / sec / 1e9, "achieved_sectors_per_clk_per_sm": sectors / sec / (pr["sm_count"] * pr["sm_clock_mhz_max"] * 1e6),
+              "peak_same_form_gbs": same * 32 / 1e9, "peak_best_form_gbs": best * 32 / 1e9, "best_form": best_form,
+              "frac_same_form": sectors / sec / same, "frac_best_form": sectors / sec / best,
+              "what": "factor-row gathers from the L2-resident K8 block (2 per rating); peaks = sbmf_cuda_probe on this device in this run: "
+                      "same_form = one random 32-byte sector per lane (how the kernel gathers), best_form = the fastest access form probed"}
+        stream = 12.0 * R                       # idx 4 B + e read 4 B + e write 4 B per rating per launch
+        hbm = {"algorithmic_bytes_per_launch": stream, "achieved_gbs": stream / sec / 1e9, "peak_gbs": peak_hbm, "peak_source": peak_src,
+               "peak_probe_copy_gbs": pr["hbm_copy_gbs"], "frac": stream / sec / 1e9 / peak_hbm}
+        per_rating, tsrc = load_traffic()
+        if per_rating:
+            hbm["traffic_bytes_per_rating"] = per_rating
+            hbm["traffic_source"] = f"profiles/{tsrc} (ncu dram__bytes_read+write of one launch / its ratings), scaled to this rank's {int(R)} ratings"
+        bound_l2 = l2["frac_best_form"] >= hbm["frac"]
+        survey = 12.0 * 8 * R / sec / 1e9 / peak_hbm
+        roof = {"kernel": "heavy_accumulate_kernel<2,2> (item-phase streaming block step)", "bound": "l2_gather" if bound_l2 else "hbm",
+                "achieved": l2["achieved_gbs"] if bound_l2 else hbm["achieved_gbs"], "peak": l2["peak_best_form_gbs"] if bound_l2 else peak_hbm,
+                "unit": "GB/s", "frac": l2["frac_best_form"] if bound_l2 else hbm["frac"],
+                "peak_source": "sbmf_cuda_probe (csrc/probe.cu), same device, same run" if bound_l2 else peak_src,
+                "traffic": per_rating * R if per_rating else None, "us_per_launch": us, "launches_timed": int(t["top_kernel_launches"]),
+                "units_per_launch": f"{int(R)} ratings x 8 dimensions (this rank)", "hbm": hbm, "l2_gather": l2,
+                "frac_survey_8d": survey,
+                "note": "frac_survey_8d prices the launch by SURVEY 8(d) (12 B per rating x DIMENSION, the reference's per-dimension "
+                        "formulation); the Gram-blocked kernel streams idx/e once per 8 dimensions, so that figure exceeds 1 and is kept only "
+                        "for comparison -- the binding resource is the L2 -> SM gather path"}
+    # whole sweep: sector gathers issued by the phases + evaluation against the same probed rates
+    sect_sweep = KB * (t["nnz_light_user"] + 2.0 * t["nnz_heavy_user"] + t["nnz_light_item"] + 2.0 * t["nnz_heavy_item"]) + 2.0 * KB * n_test / world
+    s = ms_per_step * 1e-3
+    sweep = {"l2_sectors_per_sweep": sect_sweep, "l2_achieved_gbs": sect_sweep * 32 / s / 1e9, "l2_frac_same_form": sect_sweep / s / same,
+             "l2_frac_best_form": sect_sweep / s / best,
+             "what": "K/8 sector gathers per rating and phase for register-resident rows, 2 K/8 for streamed rows (apply + accumulate), 2 K/8 per test pair; this rank"}
+    return roof, sweep
+
+
+def mgpu_parity(sbmf, dev, rank, world, new_id, max_over_ranks):
+    """N > 1: the G-GPU chain against a 1-GPU chain of the same seed on a small workload (ML-1M-shaped, K = 50, live sampling,
+    5 sweeps; draws are keyed by global row id, so the chains agree to fp32 summation order)."""
+    s = sbmf.synth_generate(6040, 3706, 1000209, seed=20151001, device=dev)
+    outs = []
+    for g in (True, False):
+        kw = dict(K=50, device=dev, sample_mode=sbmf.SAMPLE_REF, seed=11)
+        if g:
+            kw.update(rank=rank, world_size=world, nccl_id=new_id())
+        m = sbmf.SbmfModel(**kw)
+        m.set_train(s["train_user"], s["train_item"], s["train_rating"], 6040, 3706)
+        m.set_test(s["test_user"], s["test_item"], s["test_rating"])
+        m.init_factors()
+        m.set_timing_enabled(0)
+        m.sweep(5)
+        outs.append((m.get_state(with_E=False), m.rmse_history(0, 5)[0].copy()))
+        m.close()
+
+    def rel(a, b):
+        return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))) / max(float(np.max(np.abs(b))), 1e-30))
+    (a, ra), (b, rb) = outs
+    res = {k: max_over_ranks(rel(a[k], b[k])) for k in ("U", "V", "b_i", "b_j")}
+    res["rmse_history"] = max_over_ranks(float(np.max(np.abs(ra - rb))))
+    return {"workload": "ml1m-shaped synthetic 6040x3706, 1.0M ratings, K=50, live sampling, 5 sweeps", "against": "1-GPU chain of the same seed on each rank's own GPU",
+            "max_rel_diff": res, "ok": bool(max(res.values()) <= 1e-4)}
+
+
+def full_config_point(sbmf, dev):
+    """The GPU side of the reference arm's full_config_point: the complete ML-10M-shaped K=100 configuration on one GPU."""
+    I, J, _, K = WORKLOADS[FULL_POINT]
+    d = generate(sbmf, FULL_POINT, dev)
+    m = sbmf.SbmfModel(K=K, device=dev, sample_mode=sbmf.SAMPLE_REF, seed=1)
+    m.set_train(d["train_user"], d["train_item"], d["train_rating"], I, J)
+    m.set_test(d["test_user"], d["test_item"], d["test_rating"])
+    m.init_factors()
+    m.set_timing_enabled(0)
+    m.sweep(5)
+    m.synchronize()
+    m.sweep(20)
+    ms = m.last_sweep_call_ms() / 20
+    n = int(d["train_user"].size)
+    m.close()
+    return {"workload": FULL_POINT, "config": workload_config(FULL_POINT, 1), "value": n * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "sweeps_timed": 20,
+            "n_train": n, "what": "the complete ML-10M-shaped K=100 configuration on one B200, everything resident, CUDA events"}
 
 
 def main():
@@ -220,36 +402,25 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2000000, help="train ratings in the CPU baseline's sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-point", action="store_true", help="skip the ML-10M-shaped full-configuration point")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the G-GPU vs 1-GPU chain check")
+    ap.add_argument("--options", default="", help="name=value,... passed to sbmf_cuda_set_option on every handle (A/B measurements)")
     a = ap.parse_args()
     rank, local_rank, world = dist_env()
     if world != a.gpus and world != 1:
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
     I, J, NTRAIN, K = WORKLOADS[a.workload]
     W = max(a.warmup, 3) if a.impl == "ours" else a.warmup
-    cfg = {"workload": f"{a.workload}: synthetic Netflix/MovieLens-shaped Zipf rating matrix {I}x{J}, ~{NTRAIN} train ratings (+{int(TEST_FRAC * 100)}% test), K={K}",
-           "users": I, "items": J, "K": K, "l2_policy": "working set per sweep (>2 GB) far exceeds the 126 MB L2; no flush needed",
-           "rebuild_every": 1, "residual_mode": "0: per-sweep residual rebuild of gibbs_sbpmf2.cpp:342-359 fused into the user phase",
-           "sample_mode": "reference (x = mu + (1/lambda) z)"}
+    if a.impl == "reference":
+        if rank == 0:
+            reference_arm(a, max(world, a.gpus))
+        return
+    cfg = workload_config(a.workload, world)
+    opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in a.options.split(",") if kv}
 
     import sbmf
     if os.environ.get("SBMF_EMULATED") or hasattr(sbmf.load_library(), "sbmf_simt_host_emulation"):
         raise SystemExit("bench.py measures the CUDA library on a B200; the host-emulation build of the kernels is test infrastructure")
-    if a.impl == "reference":
-        if rank != 0:
-            return
-        # the sample is cut from the same generated matrix; generation needs the GPU only as a data source
-        d = generate(sbmf, a.workload, 0)
-        sample = take_sample(d, a.cpu_sample)
-        del d
-        pairs = max(1, (a.steps + 1) // 2)
-        cb = cpu_reference(sample, K, pairs=pairs, port_steps=max(1, a.steps))
-        cfg["n_train_sample"] = int(sample["train_user"].size)
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": cb["sweeps_timed"],
-                "warmup": 1, "ms_per_step": cb["s_per_sweep"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
-                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        emit(line)
-        return
 
     dist = None
     nccl_id = None
@@ -271,6 +442,8 @@ def main():
             return float(t.item())
         nccl_id = new_id()
     else:
+        new_id = None
+
         def max_over_ranks(x):
             return float(x)
 
@@ -283,15 +456,14 @@ def main():
             kw.update(rank=rank, world_size=world, nccl_id=kw.pop("nccl_id"))
         else:
             kw.pop("nccl_id", None)
-        return sbmf.SbmfModel(**kw)
+        return sbmf.SbmfModel(options=opts, **kw)
 
-    cfg["parallelism"] = f"{world} GPU(s): users (CSR) and items (CSC) sharded by rating count, factors replicated" if world > 1 else "1 GPU"
     dev = local_rank
     t0 = time.perf_counter()
     d = generate(sbmf, a.workload, dev)
     gen_s = time.perf_counter() - t0
     n_train, n_test = int(d["train_user"].size), int(d["test_user"].size)
-    cfg.update({"n_train": n_train, "n_test": n_test, "synth_seconds": round(gen_s, 2)})
+    run = {"n_train": n_train, "n_test": n_test, "synth_seconds": round(gen_s, 2), "options": opts}
     fu_per_sweep = float(n_train) * K
 
     # ---- value: K sweeps, everything resident, CUDA events on the library's stream
@@ -318,46 +490,26 @@ def main():
     value = fu_per_sweep / (ms_per_step * 1e-3)
     rmse = m.eval()[0]
 
-    # ---- roofline of the dominant kernel: per-launch CUDA events (detail timing), 3 more sweeps
+    # ---- roofline of the dominant kernel: per-launch CUDA events (detail timing), 3 more sweeps; then the probes on the same device
     m.set_timing_enabled(2)
     m.reset_timing()
     m.sweep(3)
     t = m.timing()
-    peak, peak_src = peaks()
-    roof = None
-    t_local_ratings = t["top_kernel_ratings"]
-    if t["top_kernel_launches"]:
-        us = t["ms_top_kernel"] / t["top_kernel_launches"] * 1e3
-        alg_bytes = 12.0 * 8 * t["top_kernel_ratings"]          # 12 B per (rating, dimension) visit x 8 dimensions per launch
-        ach = alg_bytes / (us * 1e-6) / 1e9
-        roof = {"kernel": "heavy_accumulate_kernel<2,2> (item-phase streaming block step)", "bound": "hbm", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "us_per_launch": us, "launches_timed": int(t["top_kernel_launches"]),
-                "units_per_launch": f"{int(t['top_kernel_ratings'])} ratings x 8 dimensions", "algorithmic_bytes_per_launch": alg_bytes,
-                "traffic": None,
-                "note": "algorithmic bytes follow SURVEY 8(d) (12 B per rating x DIMENSION visit, the reference's per-dimension formulation); "
-                        "the Gram-blocked kernel touches e/idx once per 8 dimensions, so frac > 1 is expected -- its real bound is the "
-                        "L1TEX gather rate (one 32 B sector per clock per SM), see DESIGN.md"}
-        prof = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if os.path.exists(prof):
-            roof["traffic"] = json.load(open(prof)).get("heavy_accumulate_kernel<2,2>", {}).get("dram_bytes_per_launch")
-            if roof["traffic"]:   # what the kernel really moves through HBM (ncu dram bytes of one launch) at the live launch time
-                roof["dram_achieved_gbs"] = roof["traffic"] / (us * 1e-6) / 1e9
-                roof["dram_frac"] = roof["dram_achieved_gbs"] / peak
-        # the bound this kernel actually runs against: random 32-byte sector gathers from an L2-resident table, one LDG.E.256 per
-        # lane.  tools/gather_probe.cu measures that access form alone on B200: 0.88-0.90 sectors per clock per SM (8.2-8.3 TB/s).
-        try:
-            props_sms, sm_mhz = 148, 1965.0
-            sectors = 2.0 * t["top_kernel_ratings"]             # previous block (delta apply) + current block (accumulate) per rating
-            spc = sectors / (us * 1e-6) / (props_sms * sm_mhz * 1e6)
-            roof["gather_path"] = {"sectors_per_launch": sectors, "achieved_sectors_per_clk_per_sm": spc, "probe_peak_sectors_per_clk_per_sm": 0.90,
-                                   "frac": spc / 0.90, "assumes": f"{props_sms} SMs at {sm_mhz:.0f} MHz (see clocks)",
-                                   "source": "tools/gather_probe.cu (profiles/gather_probe_r1.txt)"}
-        except Exception:   # noqa: BLE001 - informational only
-            pass
+    m.synchronize()
     phases = {k: round(t[k] / max(t["sweeps"], 1), 3) for k in ("ms_rebuild", "ms_hypers", "ms_user_phase", "ms_exchange", "ms_item_phase", "ms_eval", "ms_allgather", "ms_total")}
-    sweep_roof = {"algorithmic_bytes_per_sweep": ALG_BYTES_PER_FU * fu_per_sweep, "achieved_gbs_per_gpu": ALG_BYTES_PER_FU * value / 1e9 / world,
-                  "frac_of_peak": ALG_BYTES_PER_FU * value / 1e9 / peak / world}
     m.close()
+    peak, peak_src = peaks()
+    barrier()
+    pr = sbmf.probe(dev)                # every rank probes its own GPU at the same time (none of them is running a sweep)
+    barrier()
+    roof, sweep_gather = build_roofline(t, pr, peak, peak_src, K, (K + 7) // 8, ms_per_step, n_test, world)
+    sweep_roof = {"frac_survey_8d": ALG_BYTES_PER_FU * value / 1e9 / peak / world, "algorithmic_bytes_per_sweep_survey_8d": ALG_BYTES_PER_FU * fu_per_sweep,
+                  "survey_8d_gbs_per_gpu": ALG_BYTES_PER_FU * value / 1e9 / world}
+    sweep_roof.update(sweep_gather)
+    probes = {"hbm_copy_gbs": pr["hbm_copy_gbs"], "hbm_read_gbs": pr["hbm_read_gbs"], "table_mb": pr["table_bytes"] / 2 ** 20,
+              "gather_gbs": {k: v * 32 / 1e9 for k, v in pr["gather_sectors_per_s"].items()},
+              "gather_sectors_per_clk_per_sm": {k: v / (pr["sm_count"] * pr["sm_clock_mhz_max"] * 1e6) for k, v in pr["gather_sectors_per_s"].items()},
+              "sm_count": pr["sm_count"], "sm_clock_mhz_max": pr["sm_clock_mhz_max"], "source": "sbmf_cuda_probe (csrc/probe.cu): best of 5 launches per form, this device, this run"}
 
     # ---- e2e: the whole job through the C ABI from pinned host buffers
     e2e = None
@@ -389,24 +541,33 @@ def main():
         e2e_s = max_over_ranks(te4 - te0)
         breakdown = {"set_train_s": round(te1 - te0, 4), "set_test_init_s": round(te2 - te1, 4), "sweeps_s": round(te3 - te2, 4),
                      "get_pred_s": round(te4 - te3, 4)}
+        set_train_max = max_over_ranks(te1 - te0)
         h2d = 12.0 * (n_train + n_test)
         d2h = 16.0 * a.steps + 4.0 * n_test
         e2e = {"value": fu_per_sweep * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
-               "seconds_total": e2e_s, "sweeps": a.steps, "final_rmse": last[0], "breakdown_rank0": breakdown,
+               "seconds_total": e2e_s, "sweeps": a.steps, "final_rmse": last[0], "breakdown_rank0": breakdown, "set_train_s_max_over_ranks": round(set_train_max, 4),
                "what": "set_train(H2D COO + device CSR/CSC build) + set_test + init_factors + steps x (sweep + eval D2H) + get_pred D2H, wall clock"}
         m2.close()
+
+    parity = None
+    if world > 1 and not a.no_parity:
+        parity = mgpu_parity(sbmf, dev, rank, world, new_id, max_over_ranks)
 
     if rank != 0:
         return
     cb = None
+    fp = None
     if not a.no_cpu_baseline and world == 1:
-        cb = cpu_reference(take_sample(d, a.cpu_sample), K, pairs=1)
+        cb = cpu_reference(take_sample(d, a.cpu_sample), K)
+    if not a.no_full_point and world == 1 and a.workload != FULL_POINT:
+        del d
+        fp = full_config_point(sbmf, dev)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "run": run,
             "sweeps_per_s": 1e3 / ms_per_step, "wall_ms_per_step": wall_ms / a.steps, "rmse_after_timed": rmse, "clocks": clocks,
-            "gpu_launches": int(launches), "phases_ms": phases, "roofline": roof, "roofline_sweep": sweep_roof, "e2e": e2e, "cpu_baseline": cb,
-            "paper_i5_openmp_fu_per_s": 25.4e6}
+            "gpu_launches": int(launches), "phases_ms": phases, "roofline": roof, "roofline_sweep": sweep_roof, "probes": probes, "e2e": e2e,
+            "cpu_baseline": cb, "parity": parity, "full_config_point": fp, "paper_i5_openmp_fu_per_s": 25.4e6}
     emit(line)
 
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SBMF_CUDA_ABI_VERSION 1
+#define SBMF_CUDA_ABI_VERSION 2
 #define SBMF_MAX_K 256
 
 typedef struct sbmf_handle sbmf_handle;
@@ -136,6 +136,26 @@ const char* sbmf_cuda_last_error(const sbmf_handle* h);
 /* rank 0 of a multi-GPU job calls this and ships the 128 bytes to the other ranks (torch.distributed, MPI, ...) */
 int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
 
+/* Tuning / developer options of a handle, by name (they replace the process-wide environment knobs of ABI version 1; the
+   only environment variable the library reads is SBMF_OPTIONS="name=value,...", applied through this call inside
+   sbmf_cuda_create).  None of them changes the chain: results are identical up to fp32 summation order for every setting.
+     l2_budget_mb  (192)  resident rows: MB of gathered factor blocks one launch keeps in flight; small values split a phase
+                          into several launches that continue from the stored residual / partial predictions
+     max_blocks_per_launch (0)  additional cap on the factor blocks per launch of the resident rows (0: none)
+     resident_max  (2048) rows with more ratings stream through the sliced pipeline          [before set_train]
+     slice_len     (0)    ratings per slice of a streamed row; 0 = chosen from the shard size  [before set_train]
+     group_rows    (1)    short rows share a warp (0: one warp per row)
+     fold_user / fold_item (1 / 0)  one GPU: residual hand-over between the slot orders folded into the phase's first touch
+     graph         (1)    steady-state sweep replayed from a CUDA graph when per-phase timing is off
+     device_plan   (1)    multi-GPU: exchange plan computed on the device (0: host planner)  [before set_train]
+     mgpu_pool     (1)    multi-GPU: rating-sized arrays from the stream-ordered pool        [before set_train]
+     peer          (1)    multi-GPU: peer-mapped replicas + direct NVLink pushes (0: NCCL)   [before set_train]
+     sharded_build (1)    multi-GPU: each rank uploads / sorts only its slice of the COO      [before set_train]
+     trace         (0)    stage times of set_train on stderr
+   Unknown name or value out of range: SBMF_ERR_INVALID; a [before set_train] option after set_train: SBMF_ERR_STATE. */
+int sbmf_cuda_set_option(sbmf_handle* h, const char* name, int64_t value);
+int sbmf_cuda_get_option(sbmf_handle* h, const char* name, int64_t* value);
+
 /* ---- multi-GPU (one handle per rank = per GPU) --------------------------------------------
    Every rank passes the SAME full COO to set_train / set_test; the library keeps only the rank's shards: a contiguous
    user range with its CSR slots and a contiguous item range with its CSC slots (both cut to balance ratings), full
@@ -150,7 +170,7 @@ int sbmf_cuda_plan_exchange(uint64_t n, const uint32_t* perm, int world, int ran
                             const int64_t* csc_bounds, uint32_t* send_idx, int64_t* send_counts, uint32_t* recv_pos,
                             int64_t* recv_counts);
 /* The same plan computed on the device (csrc/storage.cu: pair-count histogram, stable compaction, stable sort by source
-   rank): what set_train uses with SBMF_DEVICE_PLAN=1 instead of downloading perm.  This entry takes HOST arrays and runs on
+   rank): what set_train uses (option device_plan, default on) instead of downloading perm.  This entry takes HOST arrays and runs on
    one GPU, so a single-GPU box can check it against sbmf_cuda_plan_exchange.  pair_counts[src * world + dst] = residuals
    whose user lives on rank src and whose item lives on rank dst (send_counts of rank r = row r, recv_counts = column r). */
 int sbmf_cuda_plan_exchange_device(uint64_t n, const uint32_t* perm, int world, int rank, const int64_t* csr_bounds,
@@ -217,21 +237,28 @@ int sbmf_cuda_set_state(sbmf_handle* h, const sbmf_state* in);
 int sbmf_cuda_get_pred_sum(sbmf_handle* h, double* sum);
 int sbmf_cuda_set_pred_sum(sbmf_handle* h, const double* sum);
 
-/* Checkpoint files (pure host code, csrc/checkpoint.cpp): a 96-byte little-endian header (magic "SBMFCKP1", the
-   dimensions below) followed by the arrays of sbmf_state in declaration order, then pred_sum; absent arrays have their
-   bit in `present` cleared.  write: NULL members of st / NULL pred_sum are recorded as absent.  read_dims: header only.
-   read: st's non-NULL members must be caller-allocated for the dimensions of the file; members absent from the file
-   are reported by clearing the pointer in st (and *pred_sum_present = 0). */
+/* Checkpoint files (pure host code, csrc/checkpoint.cpp): a 128-byte little-endian header (magic "SBMFCKP2", the
+   dimensions and chain flags below) followed by the arrays of sbmf_state in declaration order, then pred_sum; absent arrays
+   have their bit in `present` cleared.  write: NULL members of st / NULL pred_sum are recorded as absent.  read_dims: header
+   only.  read: `expect` holds the dimensions (num_users, num_items, K, n_train, n_test) st's non-NULL members and pred_sum
+   were allocated for; a file with other dimensions is refused with SBMF_ERR_INVALID before anything is copied.  Members
+   absent from the file are reported by clearing the pointer in st (and *pred_sum_present = 0).
+   seed / sample_mode / burn_in / residual_mode / rebuild_every: the sbmf_config values of the chain that wrote the file -- a
+   resumed chain only continues the interrupted one under the same values (the CLI's -load_state checks them). */
 typedef struct sbmf_checkpoint_dims {
     uint32_t num_users, num_items, K;
     int32_t hyper_mode;
     uint64_t n_train, n_test;
     uint32_t sweeps_done;
     uint32_t present;            /* bit i = i-th pointer member of sbmf_state (U = bit 0 ... E = bit 12), bit 13 = pred_sum */
+    uint64_t seed;
+    int32_t sample_mode;
+    uint32_t burn_in, residual_mode, rebuild_every;
 } sbmf_checkpoint_dims;
 int sbmf_cuda_checkpoint_write(const char* path, const sbmf_checkpoint_dims* dims, const sbmf_state* st, const double* pred_sum);
 int sbmf_cuda_checkpoint_read_dims(const char* path, sbmf_checkpoint_dims* dims);
-int sbmf_cuda_checkpoint_read(const char* path, sbmf_state* st, double* pred_sum, int* pred_sum_present);
+int sbmf_cuda_checkpoint_read(const char* path, const sbmf_checkpoint_dims* expect, sbmf_state* st, double* pred_sum,
+                              int* pred_sum_present);
 const char* sbmf_cuda_checkpoint_last_error(void);
 
 /* ---- instrumentation -------------------------------------------------------------------------------- */
@@ -248,6 +275,25 @@ int sbmf_cuda_last_sweep_call_ms(sbmf_handle* h, double* ms);
 /* Pinned host buffers for callers that want full-speed host<->device copies in set_train / set_test / get_*. */
 int sbmf_cuda_host_alloc(void** ptr, size_t bytes);
 int sbmf_cuda_host_free(void* ptr);
+
+/* ---- hardware probes: the denominators of bench.py's roofline, measured on the device the job runs on, in the same run ----
+   hbm_*: streaming kernels over 1 GiB buffers.  gather_sectors_per_s[form]: random row gathers from an L2-resident table of
+   table_bytes (0 = 15 MB = one K8 factor block of the Netflix-shaped user side), row ids streamed from HBM, n_gathers sectors
+   per launch (0 = 64 Mi); best of 5 launches each.  Forms: G32_LANE = one random 32-byte sector per lane with one LDG.E.256 --
+   the access form of the factor gathers in csrc/kernels.cu; G64_* / G128_* = the same bytes as contiguous 64-byte rows / full
+   128-byte lines, fetched per lane (2 / 4 loads) or by 2 / 4 cooperating adjacent lanes -- what a wider factor layout could reach. */
+enum { SBMF_PROBE_G32_LANE = 0, SBMF_PROBE_G64_LANE = 1, SBMF_PROBE_G64_COOP2 = 2, SBMF_PROBE_G128_LANE = 3, SBMF_PROBE_G128_COOP4 = 4,
+       SBMF_PROBE_FORMS = 5 };
+typedef struct sbmf_probe_result {
+    double hbm_copy_gbs;                            /* (bytes read + bytes written) / s */
+    double hbm_read_gbs;
+    double gather_sectors_per_s[8];                 /* [SBMF_PROBE_FORMS] 32-byte sectors delivered to the SMs per second */
+    double sm_clock_mhz_max;                        /* cudaDevAttrClockRate */
+    uint64_t table_bytes, n_gathers;
+    int32_t sm_count, reserved0;
+} sbmf_probe_result;
+int sbmf_cuda_probe(int device, uint64_t table_bytes, uint64_t n_gathers, sbmf_probe_result* out);
+const char* sbmf_cuda_probe_last_error(void);
 
 /* ---- synthetic workloads (bench / tests): MovieLens/Netflix-shaped Zipf rating matrices, generated on
    the device.  Distinct (user,item) pairs with Zipf(s_user) x Zipf(s_item) marginals over

@@ -102,8 +102,16 @@ double sbmf_oracle_philox_normal_f64(uint64_t seed, uint32_t site, uint32_t row,
 
 static double philox_gamma(uint64_t seed, uint32_t site, uint32_t row, uint32_t sweep, double shape)
 {
-    /* Marsaglia-Tsang as [R]:129-143 (shape >= 1 at every call site of [T]); attempt a uses
-       counter (row, a, site, sweep): normal from words 0/1, uniform from word 2. */
+    /* Marsaglia-Tsang as [R]:129-143; attempt a uses counter (row, a, site, sweep): normal from words 0/1,
+       uniform from word 2.  shape < 1 ([R]:120-125): Gamma(shape + 1) * u^(1/shape), u from word 3 of counter
+       (row, 0xffffffff, site, sweep) -- the same streams as the device's draw_gamma_f64 (csrc/common.cuh). */
+    double boost = 1.0;
+    if (shape < 1.0) {
+        uint32_t xb[4];
+        philox_site(seed, site, row, 0xffffffffu, sweep, xb);
+        boost = pow(((double)xb[3] + 0.5) * (1.0 / 4294967296.0), 1.0 / shape);
+        shape += 1.0;
+    }
     double d = shape - 1.0 / 3.0;
     double c = 1.0 / sqrt(9.0 * d);
     for (uint32_t a = 0;; ++a) {
@@ -114,8 +122,8 @@ static double philox_gamma(uint64_t seed, uint32_t site, uint32_t row, uint32_t 
         if (v <= 0.0) continue;
         v = v * v * v;
         double u = ((double)x[2] + 0.5) * (1.0 / 4294967296.0);
-        if (u < 1.0 - 0.0331 * (z * z) * (z * z)) return d * v;
-        if (log(u) < 0.5 * z * z + d * (1.0 - v + log(v))) return d * v;
+        if (u < 1.0 - 0.0331 * (z * z) * (z * z)) return d * v * boost;
+        if (log(u) < 0.5 * z * z + d * (1.0 - v + log(v))) return d * v * boost;
     }
 }
 

@@ -3,6 +3,7 @@
 // fallback -- sbmf_cuda_create fails if no CUDA device of compute capability 10.x is usable.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -25,6 +26,12 @@ static thread_local std::string g_create_err;
         }                                                                                          \
     } while (0)
 
+// frees a temporary device buffer on every exit path (API_CK returns early)
+struct DeviceTmp {
+    float* p = nullptr;
+    ~DeviceTmp() { if (p) cudaFree(p); }
+};
+
 static cudaError_t copy_out_widen(uint64_t* dst, const uint32_t* d_src, size_t n, std::vector<uint32_t>& tmp)
 {
     tmp.resize(n ? n : 1);
@@ -34,9 +41,113 @@ static cudaError_t copy_out_widen(uint64_t* dst, const uint32_t* d_src, size_t n
     return cudaSuccess;
 }
 
+struct OptionDesc {
+    const char* name;
+    int64_t Options::*field;
+    int64_t lo, hi;
+    bool before_train;   // shapes the layout / work lists: only accepted before set_train
+};
+static const OptionDesc kOptions[] = {
+    {"l2_budget_mb", &Options::l2_budget_mb, 1, 1 << 20, false},
+    {"max_blocks_per_launch", &Options::max_blocks_per_launch, 0, 1 << 20, false},
+    {"resident_max", &Options::resident_max, 1, RESIDENT_MAX, true},
+    {"slice_len", &Options::slice_len, 0, 1 << 24, true},
+    {"group_rows", &Options::group_rows, 0, 1, false},
+    {"fold_user", &Options::fold_user, 0, 1, false},
+    {"fold_item", &Options::fold_item, 0, 1, false},
+    {"graph", &Options::graph, 0, 1, false},
+    {"device_plan", &Options::device_plan, 0, 1, true},
+    {"mgpu_pool", &Options::mgpu_pool, 0, 1, true},
+    {"peer", &Options::peer, 0, 1, true},
+    {"trace", &Options::trace, 0, 2, false},
+    {"sharded_build", &Options::sharded_build, 0, 1, true},
+};
+
+static const OptionDesc* find_option(const char* name)
+{
+    if (!name) return nullptr;
+    for (const OptionDesc& d : kOptions)
+        if (!strcmp(d.name, name)) return &d;
+    return nullptr;
+}
+
 extern "C" {
 
 int sbmf_cuda_abi_version(void) { return SBMF_CUDA_ABI_VERSION; }
+
+int sbmf_cuda_set_option(sbmf_handle* h, const char* name, int64_t value)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    const OptionDesc* d = find_option(name);
+    if (!d) {
+        m.err = std::string("set_option: unknown option '") + (name ? name : "(null)") + "'";
+        return SBMF_ERR_INVALID;
+    }
+    if (value < d->lo || value > d->hi) {
+        m.err = std::string("set_option: ") + name + " must be in [" + std::to_string(d->lo) + ", " + std::to_string(d->hi) + "]";
+        return SBMF_ERR_INVALID;
+    }
+    if (d->before_train && m.have_train) {
+        m.err = std::string("set_option: ") + name + " shapes the layout and must be set before set_train";
+        return SBMF_ERR_STATE;
+    }
+    m.opt.*(d->field) = value;
+    if (m.graph_exec) {   // the captured sweep may embed the old choice
+        cudaSetDevice(m.device);
+        cudaStreamSynchronize(m.s_main);
+        cudaGraphExecDestroy(m.graph_exec);
+        m.graph_exec = nullptr;
+    }
+    m.graph_failed = false;
+    return SBMF_OK;
+}
+
+int sbmf_cuda_get_option(sbmf_handle* h, const char* name, int64_t* value)
+{
+    if (!h || !value) return SBMF_ERR_INVALID;
+    const OptionDesc* d = find_option(name);
+    if (!d) {
+        h->m.err = std::string("get_option: unknown option '") + (name ? name : "(null)") + "'";
+        return SBMF_ERR_INVALID;
+    }
+    *value = h->m.opt.*(d->field);
+    return SBMF_OK;
+}
+
+// SBMF_OPTIONS="name=value,name=value": the ONE environment variable of the library, read once per handle in
+// sbmf_cuda_create and applied through sbmf_cuda_set_option (A/B scripts); a malformed entry fails the create.
+static int apply_env_options(sbmf_handle* h)
+{
+    const char* ev = getenv("SBMF_OPTIONS");
+    if (!ev || !*ev) return SBMF_OK;
+    std::string s(ev);
+    size_t pos = 0;
+    while (pos < s.size()) {
+        size_t end = s.find(',', pos);
+        if (end == std::string::npos) end = s.size();
+        const std::string item = s.substr(pos, end - pos);
+        pos = end + 1;
+        if (item.empty()) continue;
+        const size_t eq = item.find('=');
+        if (eq == std::string::npos) {
+            g_create_err = "create: SBMF_OPTIONS entry '" + item + "' is not name=value";
+            return SBMF_ERR_INVALID;
+        }
+        char* endp = nullptr;
+        const long long v = strtoll(item.c_str() + eq + 1, &endp, 10);
+        if (!endp || *endp) {
+            g_create_err = "create: SBMF_OPTIONS entry '" + item + "': value is not an integer";
+            return SBMF_ERR_INVALID;
+        }
+        const int rc = sbmf_cuda_set_option(h, item.substr(0, eq).c_str(), (int64_t)v);
+        if (rc != SBMF_OK) {
+            g_create_err = "create: SBMF_OPTIONS: " + h->m.err;
+            return rc;
+        }
+    }
+    return SBMF_OK;
+}
 
 int sbmf_cuda_config_default(sbmf_config* cfg)
 {
@@ -87,6 +198,28 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
     if (cfg->sample_mode < 0 || cfg->sample_mode > 2 || cfg->hyper_mode < 0 || cfg->hyper_mode > 2) {
         g_create_err = "create: unknown sample_mode / hyper_mode";
         return SBMF_ERR_INVALID;
+    }
+    {
+        // Every Gamma draw of the sweep has shape = prior + a non-negative count and rate = prior + a non-negative sum of
+        // squares ([T]:366-511, [S]:339-413): positive, finite priors keep every shape and rate positive whatever the data
+        // (including an empty training set).  Anything else would hand ran_gamma a non-positive argument ([R]:119 asserts).
+        const sbmf_priors& p = cfg->priors;
+        bool ok = true;
+        auto pos = [&](double v) { ok = ok && v > 0.0 && v < 1e300; };
+        auto fin = [&](double v) { ok = ok && v > -1e300 && v < 1e300; };
+        for (int i = 0; i < 6; ++i) {
+            pos(p.alpha[i]); pos(p.beta[i]); pos(p.sigma[i]); fin(p.mu[i]);
+        }
+        pos(p.alpha_dash); pos(p.beta_dash);
+        pos(p.ng_a_0); pos(p.ng_b_0); pos(p.ng_alpha_0); pos(p.ng_beta_0); pos(p.ng_nu_0); fin(p.ng_mu_0);
+        if (!ok) {
+            g_create_err = "create: priors must be finite, and every shape / rate / precision prior (alpha, beta, sigma, *_dash, ng_*) > 0";
+            return SBMF_ERR_INVALID;
+        }
+        if (!(cfg->init_stdev >= 0.0) || !(cfg->clamp_lo <= cfg->clamp_hi)) {
+            g_create_err = "create: need init_stdev >= 0 and clamp_lo <= clamp_hi";
+            return SBMF_ERR_INVALID;
+        }
     }
     if (cfg->world_size < 1 || cfg->world_size > 64 || cfg->rank < 0 || cfg->rank >= cfg->world_size) {
         g_create_err = "create: need 0 <= rank < world_size <= 64";
@@ -191,6 +324,13 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
                 sbmf_cuda_destroy(h);
                 return SBMF_ERR_NCCL;
             }
+        }
+    }
+    {
+        const int orc = apply_env_options(h);
+        if (orc != SBMF_OK) {
+            sbmf_cuda_destroy(h);
+            return orc;
         }
     }
     *out = h;
@@ -314,7 +454,8 @@ int sbmf_cuda_init_factors(sbmf_handle* h, const float* U0, const float* V0)
     }
     API_CK(cudaSetDevice(m.device));
     cudaStream_t st = m.s_main;
-    float* d_tmp = nullptr;
+    DeviceTmp tmp;
+    float*& d_tmp = tmp.p;
     const size_t nu = (size_t)m.I * m.K, nv = (size_t)m.K * m.J;
     if (U0 || V0) API_CK(cudaMalloc((void**)&d_tmp, std::max(nu, nv) * 4));
     if (U0) {
@@ -331,7 +472,6 @@ int sbmf_cuda_init_factors(sbmf_handle* h, const float* U0, const float* V0)
     } else {
         launch_init_factors(m, m.it, SITE_INIT_V, st);
     }
-    cudaFree(d_tmp);
     // [T]:268-281, 315-318: biases, bias hypers, per-dimension hypers and the scalars start at 0
     for (Side* s : {&m.us, &m.it}) {
         API_CK(cudaMemsetAsync(s->bias, 0, (size_t)s->n * 4, st));
@@ -374,11 +514,9 @@ static int enqueue_sweep(Model& m, bool timing)
     // array (PhaseArgs::e_map), where the gather hides behind the factor gathers (measured on the Netflix-shaped matrix:
     // -0.9 ms for the pass, +0.4 ms in the phase).  The other direction stays a stand-alone pass by default: the item phase is
     // dominated by the streaming pipeline, whose first pass is pure streaming and turns HBM-sector-bound with the gather
-    // (-0.5 ms, +0.7 ms).  SBMF_NO_FOLD=1 / SBMF_FOLD_ITEM=1 switch either (A/B measurements).
-    static const bool no_fold = getenv("SBMF_NO_FOLD") != nullptr;
-    static const bool fold_item_env = getenv("SBMF_FOLD_ITEM") != nullptr;
-    const bool fold_user = m.world == 1 && !no_fold;
-    const bool fold = m.world == 1 && fold_item_env;
+    // (-0.5 ms, +0.7 ms).  Options fold_user / fold_item switch either (A/B measurements, tests).
+    const bool fold_user = m.world == 1 && m.opt.fold_user;
+    const bool fold = m.world == 1 && m.opt.fold_item;
     bool user_mapped = false;
     if (standalone) {
         launch_rebuild(m, st);                       // [T]:342-359
@@ -447,7 +585,7 @@ static SweepKey sweep_key(const Model& m)
 static int graph_sweep(Model& m, bool& done)
 {
     done = false;
-    static const bool disabled = getenv("SBMF_NO_GRAPH") != nullptr;
+    const bool disabled = !m.opt.graph;
     // the first two sweeps after init_factors / set_state run as direct launches: they build the lazily allocated inverse
     // maps (ensure_inverse), which must not happen inside a capture
     if (disabled || m.timing_enabled || m.sweeps_done < 2 || m.sweeps_since_init < 2 || m.need_rebuild) return SBMF_OK;
@@ -554,11 +692,28 @@ int sbmf_cuda_sweep(sbmf_handle* h, uint32_t n_sweeps)
         m.err = "sweep: call set_train and init_factors first";
         return SBMF_ERR_STATE;
     }
+    API_CK(cudaSetDevice(m.device));   // before anything allocates: the caller may have switched devices (several handles per thread)
     if (!m.have_test) {
         int rc = build_test(m, 0, nullptr, nullptr, nullptr);
         if (rc != SBMF_OK) return rc;
     }
-    API_CK(cudaSetDevice(m.device));
+    if ((uint64_t)m.sweeps_done + n_sweeps > m.hist_cap) {   // the RMSE history grows with the chain (it used to stop at 4096 sweeps)
+        uint64_t cap = m.hist_cap;
+        while (cap < (uint64_t)m.sweeps_done + n_sweeps) cap *= 2;
+        if (cap > 0xffffffffull) cap = 0xffffffffull;
+        double* nh = nullptr;
+        API_CK(cudaStreamSynchronize(m.s_main));
+        API_CK(cudaMalloc((void**)&nh, (size_t)cap * 16));
+        API_CK(cudaMemset(nh, 0, (size_t)cap * 16));
+        API_CK(cudaMemcpy(nh, m.rmse_hist, (size_t)m.hist_cap * 16, cudaMemcpyDeviceToDevice));
+        cudaFree(m.rmse_hist);
+        m.rmse_hist = nh;
+        m.hist_cap = (uint32_t)cap;
+        if (m.graph_exec) {   // the captured sweep holds the old pointer
+            cudaGraphExecDestroy(m.graph_exec);
+            m.graph_exec = nullptr;
+        }
+    }
     API_CK(cudaEventRecord(m.ev_call[0], m.s_main));
     for (uint32_t s = 0; s < n_sweeps; ++s) {
         int rc = one_sweep(m);
@@ -633,7 +788,7 @@ int sbmf_cuda_get_rmse_history(sbmf_handle* h, uint32_t first, uint32_t count, d
     if (!h) return SBMF_ERR_INVALID;
     Model& m = h->m;
     if ((uint64_t)first + count > m.sweeps_done || (uint64_t)first + count > m.hist_cap) {
-        m.err = "get_rmse_history: range exceeds the sweeps run (or the 4096-sweep history)";
+        m.err = "get_rmse_history: range exceeds the sweeps run";
         return SBMF_ERR_INVALID;
     }
     API_CK(cudaSetDevice(m.device));
@@ -686,7 +841,8 @@ int sbmf_cuda_get_state(sbmf_handle* h, sbmf_state* out)
     cudaStream_t st = m.s_main;
     API_CK(cudaStreamSynchronize(st));
     if (out->U || out->V) {
-        float* d_tmp = nullptr;
+        DeviceTmp tmp;
+        float*& d_tmp = tmp.p;
         const size_t nu = (size_t)m.I * m.K, nv = (size_t)m.K * m.J;
         API_CK(cudaMalloc((void**)&d_tmp, std::max(nu, nv) * 4));
         if (out->U) {
@@ -699,7 +855,6 @@ int sbmf_cuda_get_state(sbmf_handle* h, sbmf_state* out)
             API_CK(cudaMemcpyAsync(out->V, d_tmp, nv * 4, cudaMemcpyDeviceToHost, st));
             API_CK(cudaStreamSynchronize(st));
         }
-        cudaFree(d_tmp);
     }
     if (out->b_i) API_CK(cudaMemcpy(out->b_i, m.us.bias, (size_t)m.I * 4, cudaMemcpyDeviceToHost));
     if (out->b_j) API_CK(cudaMemcpy(out->b_j, m.it.bias, (size_t)m.J * 4, cudaMemcpyDeviceToHost));

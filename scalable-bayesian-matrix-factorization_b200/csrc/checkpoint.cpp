@@ -2,10 +2,12 @@
 // The reference has no checkpointing on this path; the file simply carries what sbmf_cuda_get_state and
 // sbmf_cuda_get_pred_sum return, so that sbmf_cuda_set_state / set_pred_sum can continue the chain in another process.
 //
-// Layout (little-endian): 96-byte header
-//   char magic[8] = "SBMFCKP1"; u32 num_users, num_items, K; i32 hyper_mode; u64 n_train, n_test; u32 sweeps_done, present;
-//   f64 b_0, alpha, mu_b_0, sigma_b_0, sum_e, sum_e2
-// then, for every bit set in `present`, in this order: U[I][K] f32, V[K][J] f32, b_i[I], b_j[J], mu_b_i[I], sigma_b_i[I],
+// Layout (little-endian): 128-byte header
+//   char magic[8] = "SBMFCKP2"; u32 num_users, num_items, K; i32 hyper_mode; u64 n_train, n_test; u32 sweeps_done, present;
+//   f64 b_0, alpha, mu_b_0, sigma_b_0, sum_e, sum_e2;
+//   u64 seed; i32 sample_mode; u32 burn_in, residual_mode, rebuild_every; u8 reserved[8]
+// (the chain a resumed handle continues is a function of the seed and the mode flags, so they travel with the state and the
+// caller -- the CLI's -load_state -- can refuse a resume under different flags).  Then, for every bit set in `present`, in this order: U[I][K] f32, V[K][J] f32, b_i[I], b_j[J], mu_b_i[I], sigma_b_i[I],
 // mu_b_j[J], sigma_b_j[J] f32, sigma_u[K], mu_u[K], sigma_v[K], mu_v[K] f64, E[n_train] f32, pred_sum[n_test] f64.
 #include <stdint.h>
 #include <stdio.h>
@@ -18,7 +20,7 @@
 namespace {
 
 thread_local std::string g_err;
-const char kMagic[8] = {'S', 'B', 'M', 'F', 'C', 'K', 'P', '1'};
+const char kMagic[8] = {'S', 'B', 'M', 'F', 'C', 'K', 'P', '2'};
 constexpr int kArrays = 14;   // 13 pointer members of sbmf_state + pred_sum
 
 struct Header {
@@ -28,8 +30,12 @@ struct Header {
     uint64_t n_train, n_test;
     uint32_t sweeps_done, present;
     double b_0, alpha, mu_b_0, sigma_b_0, sum_e, sum_e2;
+    uint64_t seed;
+    int32_t sample_mode;
+    uint32_t burn_in, residual_mode, rebuild_every;
+    uint8_t reserved[8];
 };
-static_assert(sizeof(Header) == 96, "checkpoint header is 96 bytes");
+static_assert(sizeof(Header) == 128, "checkpoint header is 128 bytes");
 
 // byte size of array i for the dimensions in the header
 uint64_t array_bytes(const Header& h, int i)
@@ -112,6 +118,11 @@ int sbmf_cuda_checkpoint_write(const char* path, const sbmf_checkpoint_dims* dim
     h.n_train = dims->n_train;
     h.n_test = dims->n_test;
     h.sweeps_done = st->sweeps_done;
+    h.seed = dims->seed;
+    h.sample_mode = dims->sample_mode;
+    h.burn_in = dims->burn_in;
+    h.residual_mode = dims->residual_mode;
+    h.rebuild_every = dims->rebuild_every;
     for (int i = 0; i < kArrays; ++i)
         if (member(st, pred_sum, i)) h.present |= 1u << i;
     h.b_0 = st->b_0;
@@ -165,13 +176,18 @@ int sbmf_cuda_checkpoint_read_dims(const char* path, sbmf_checkpoint_dims* dims)
     dims->n_test = h.n_test;
     dims->sweeps_done = h.sweeps_done;
     dims->present = h.present;
+    dims->seed = h.seed;
+    dims->sample_mode = h.sample_mode;
+    dims->burn_in = h.burn_in;
+    dims->residual_mode = h.residual_mode;
+    dims->rebuild_every = h.rebuild_every;
     return SBMF_OK;
 }
 
-int sbmf_cuda_checkpoint_read(const char* path, sbmf_state* st, double* pred_sum, int* pred_sum_present)
+int sbmf_cuda_checkpoint_read(const char* path, const sbmf_checkpoint_dims* expect, sbmf_state* st, double* pred_sum, int* pred_sum_present)
 {
-    if (!path || !st) {
-        g_err = "checkpoint_read: null argument";
+    if (!path || !st || !expect) {
+        g_err = "checkpoint_read: null argument (expect = the dimensions the buffers in st were allocated for)";
         return SBMF_ERR_INVALID;
     }
     FILE* f = fopen(path, "rb");
@@ -184,6 +200,16 @@ int sbmf_cuda_checkpoint_read(const char* path, sbmf_state* st, double* pred_sum
     if (rc != SBMF_OK) {
         fclose(f);
         return rc;
+    }
+    // the arrays are copied with the sizes of the FILE: refuse before touching the caller's buffers if they were sized otherwise
+    if (h.num_users != expect->num_users || h.num_items != expect->num_items || h.K != expect->K || h.n_train != expect->n_train ||
+        h.n_test != expect->n_test) {
+        fclose(f);
+        g_err = std::string(path) + ": checkpoint is for " + std::to_string(h.num_users) + " users x " + std::to_string(h.num_items) +
+                " items, K=" + std::to_string(h.K) + ", " + std::to_string(h.n_train) + " train / " + std::to_string(h.n_test) +
+                " test ratings; the caller's buffers are for " + std::to_string(expect->num_users) + " x " + std::to_string(expect->num_items) +
+                ", K=" + std::to_string(expect->K) + ", " + std::to_string(expect->n_train) + " / " + std::to_string(expect->n_test);
+        return SBMF_ERR_INVALID;
     }
     if (pred_sum_present) *pred_sum_present = 0;
     for (int i = 0; i < kArrays; ++i) {

@@ -65,6 +65,16 @@ bool load(std::string& err)
             return -1;                                                          \
         }                                                                       \
     } while (0)
+// inside an open ncclGroupStart: close the group before reporting, otherwise the next collective hangs instead of failing
+#define NCG(call)                                                               \
+    do {                                                                        \
+        ncclResult_t r_ = (call);                                               \
+        if (r_ != 0) {                                                          \
+            err = std::string(#call) + ": " + g_api.GetErrorString(r_);         \
+            g_api.GroupEnd();                                                   \
+            return -1;                                                          \
+        }                                                                       \
+    } while (0)
 }  // namespace
 
 int comm_unique_id(uint8_t out[128], std::string& err)
@@ -101,33 +111,20 @@ int comm_allreduce_sum_f64(Comm& c, double* buf, size_t count, cudaStream_t st, 
     return 0;
 }
 
-// In-place all-gather-v of nseg strided segments.  Default: point-to-point -- every rank sends its own part of every
-// segment straight to every peer (one grouped NCCL launch, all NVLink links busy at once); SBMF_AGV=bcast selects one
-// broadcast per (segment, root) instead.
+// In-place all-gather-v of nseg strided segments, point-to-point: every rank sends its own part of every segment straight
+// to every peer (one grouped NCCL launch, all NVLink links busy at once; measured faster than one broadcast per root).
 template <typename T>
 static int allgatherv(Comm& c, T* base, size_t stride, int nseg, const size_t* offsets, const size_t* counts, int dtype, cudaStream_t st,
                       std::string& err)
 {
-    static const bool use_bcast = getenv("SBMF_AGV") && !strcmp(getenv("SBMF_AGV"), "bcast");
-    if (!use_bcast) {
-        NC(g_api.GroupStart());
-        for (int q = 0; q < c.world; ++q) {
-            if (q == c.rank) continue;
-            for (int s = 0; s < nseg; ++s) {
-                if (counts[c.rank]) NC(g_api.Send(base + (size_t)s * stride + offsets[c.rank], counts[c.rank], dtype, q, (ncclComm_t)c.nccl, st));
-                if (counts[q]) NC(g_api.Recv(base + (size_t)s * stride + offsets[q], counts[q], dtype, q, (ncclComm_t)c.nccl, st));
-            }
-        }
-        NC(g_api.GroupEnd());
-        return 0;
-    }
     NC(g_api.GroupStart());
-    for (int s = 0; s < nseg; ++s)
-        for (int q = 0; q < c.world; ++q) {
-            if (!counts[q]) continue;
-            T* p = base + (size_t)s * stride + offsets[q];
-            NC(g_api.Broadcast(p, p, counts[q], dtype, q, (ncclComm_t)c.nccl, st));
+    for (int q = 0; q < c.world; ++q) {
+        if (q == c.rank) continue;
+        for (int s = 0; s < nseg; ++s) {
+            if (counts[c.rank]) NCG(g_api.Send(base + (size_t)s * stride + offsets[c.rank], counts[c.rank], dtype, q, (ncclComm_t)c.nccl, st));
+            if (counts[q]) NCG(g_api.Recv(base + (size_t)s * stride + offsets[q], counts[q], dtype, q, (ncclComm_t)c.nccl, st));
         }
+    }
     NC(g_api.GroupEnd());
     return 0;
 }
@@ -163,8 +160,8 @@ int comm_alltoallv_f32(Comm& c, const float* send, const size_t* send_off, const
 {
     NC(g_api.GroupStart());
     for (int q = 0; q < c.world; ++q) {
-        if (send_cnt[q]) NC(g_api.Send(send + send_off[q], send_cnt[q], ncclFloat32, q, (ncclComm_t)c.nccl, st));
-        if (recv_cnt[q]) NC(g_api.Recv(recv + recv_off[q], recv_cnt[q], ncclFloat32, q, (ncclComm_t)c.nccl, st));
+        if (send_cnt[q]) NCG(g_api.Send(send + send_off[q], send_cnt[q], ncclFloat32, q, (ncclComm_t)c.nccl, st));
+        if (recv_cnt[q]) NCG(g_api.Recv(recv + recv_off[q], recv_cnt[q], ncclFloat32, q, (ncclComm_t)c.nccl, st));
     }
     NC(g_api.GroupEnd());
     return 0;

@@ -74,24 +74,37 @@ __device__ __forceinline__ double draw_gauss_f64(int mode, uint64_t seed, uint32
     return mean + sd * normal_f64(philox_site(seed, site, row, c1, sweep));
 }
 
-// ran_gamma(shape, rate) of [R]:118-148 for shape >= 1 (true at every call site of [T]): Marsaglia-Tsang;
-// attempt a consumes counter (row, a, site, sweep): normal from words 0/1, uniform from word 2.
+// ran_gamma(shape, rate) of [R]:118-148.  shape >= 1 (true at every call site of [T] with its default priors): Marsaglia-Tsang;
+// attempt a consumes counter (row, a, site, sweep): normal from words 0/1, uniform from word 2.  shape < 1 ([R]:120-125):
+// Gamma(shape + 1) * u^(1/shape), u from word 3 of the counter (row, 0xffffffff, site, sweep).  The rejection loop is capped:
+// Marsaglia-Tsang accepts > 95 % of the attempts, so 64 rejections in a row mean NaN / non-positive arguments (priors are
+// validated at create, but a diverged chain can still produce them) -- the draw then degrades to the Gamma mean instead of
+// spinning forever in a single-thread kernel.
+constexpr uint32_t GAMMA_MAX_ATTEMPTS = 64;
 __device__ __forceinline__ double draw_gamma_f64(int mode, uint64_t seed, uint32_t site, uint32_t row, uint32_t sweep,
                                                   double shape, double rate)
 {
     if (mode == SAMPLE_ZERO) return shape / rate;
-    const double d = shape - 1.0 / 3.0;
+    double boost = 1.0, sh = shape;
+    if (shape < 1.0) {
+        const uint4 xb = philox_site(seed, site, row, 0xffffffffu, sweep);
+        const double u = ((double)xb.w + 0.5) * (1.0 / 4294967296.0);   // in (0, 1): [R] redraws u == 0
+        boost = pow(u, 1.0 / shape);
+        sh = shape + 1.0;
+    }
+    const double d = sh - 1.0 / 3.0;
     const double c = 1.0 / sqrt(9.0 * d);
-    for (uint32_t a = 0;; ++a) {
+    for (uint32_t a = 0; a < GAMMA_MAX_ATTEMPTS; ++a) {
         const uint4 x = philox_site(seed, site, row, a, sweep);
         const double z = normal_f64(x);
         double v = 1.0 + c * z;
-        if (v <= 0.0) continue;
+        if (!(v > 0.0)) continue;
         v = v * v * v;
         const double u = ((double)x.z + 0.5) * (1.0 / 4294967296.0);
-        if (u < 1.0 - 0.0331 * (z * z) * (z * z)) return d * v / rate;
-        if (log(u) < 0.5 * z * z + d * (1.0 - v + log(v))) return d * v / rate;
+        if (u < 1.0 - 0.0331 * (z * z) * (z * z)) return d * v * boost / rate;
+        if (log(u) < 0.5 * z * z + d * (1.0 - v + log(v))) return d * v * boost / rate;
     }
+    return shape / rate;
 }
 
 // ---------------------------------------------------------------------------------------------------

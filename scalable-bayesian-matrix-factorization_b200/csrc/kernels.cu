@@ -1222,8 +1222,7 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
     const uint32_t n = self.bin_count[BIN];
     if (!n) return;
     if constexpr (WARPS == 0) {   // short rows: G lanes per row (kBins[].cap = G * RPL)
-        static const bool no_group = getenv("SBMF_NO_GROUP") != nullptr;   // debugging knob: one warp per short row instead
-        if (no_group) {
+        if (!m.opt.group_rows) {   // option group_rows = 0: one warp per short row instead (debugging / A-B)
             constexpr int R1 = kBins[BIN].cap / 32;
             const dim3 grid1((n + 3) / 4);
             if (refresh) SBMF_LAUNCH((row_resident_kernel<R1, 1, true>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
@@ -1302,8 +1301,9 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     // strictly L2-resident) loses to 100-200 MB on both the Netflix-shaped matrix (item phase 10.94 -> 10.90 ms) and the
     // 10M x 1M one (user phase 378 -> 271 ms); beyond ~200 MB it is flat.
     const size_t block_bytes = (size_t)other.n * 32;
-    static const size_t l2_budget = (size_t)(getenv("SBMF_L2_BUDGET_MB") ? atol(getenv("SBMF_L2_BUDGET_MB")) : 192) << 20;   // tuning knob
+    const size_t l2_budget = (size_t)m.opt.l2_budget_mb << 20;   // option l2_budget_mb (tests shrink it to reach the multi-launch continuation)
     int nb = (int)(l2_budget / (block_bytes ? block_bytes : 1));
+    if (m.opt.max_blocks_per_launch > 0 && nb > (int)m.opt.max_blocks_per_launch) nb = (int)m.opt.max_blocks_per_launch;
     if (nb < 1) nb = 1;
     if (nb > KB) nb = KB;
     for (int b0 = 0; b0 < KB; b0 += nb) {
@@ -1422,18 +1422,28 @@ int launch_permute(Model& m, bool csr_to_csc, Side* gather_side, cudaStream_t st
     int rc = 0;
     if (csr_to_csc) {
         SBMF_LAUNCH((permute_gather_kernel), gs, 256, 0, st, m.us.e, m.send_idx, m.sendbuf, m.n_csr);
-        rc |= comm_group_begin(m.err);
-        rc |= comm_alltoallv_f32(m.comm, m.sendbuf, m.send_off.data(), m.send_cnt.data(), m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), st, m.err);
-        if (gather_side) rc |= launch_allgather_side(m, *gather_side, st);
-        rc |= comm_group_end(m.err);
+        if ((rc = comm_group_begin(m.err)) != 0) return rc;
+        rc = comm_alltoallv_f32(m.comm, m.sendbuf, m.send_off.data(), m.send_cnt.data(), m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), st, m.err);
+        if (!rc && gather_side) rc = launch_allgather_side(m, *gather_side, st);
+        if (rc) {   // a failed call: close the outer group (keeping the first error message) and stop issuing NCCL work
+            std::string ignored;
+            comm_group_end(ignored);
+            return rc;
+        }
+        if ((rc = comm_group_end(m.err)) != 0) return rc;
         SBMF_LAUNCH((permute_gather_kernel), gr, 256, 0, st, m.recvbuf, m.recv_pos, m.it.e, m.n_csc);
     } else {
         if (ensure_inverse(m, m.recv_pos, &m.recv_pos_inv, m.n_csc, st)) SBMF_LAUNCH((permute_gather_kernel), gr, 256, 0, st, m.it.e, m.recv_pos_inv, m.recvbuf, m.n_csc);
         else SBMF_LAUNCH((permute_scatter_kernel), gr, 256, 0, st, m.it.e, m.recv_pos, m.recvbuf, m.n_csc);
-        rc |= comm_group_begin(m.err);
-        rc |= comm_alltoallv_f32(m.comm, m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), m.sendbuf, m.send_off.data(), m.send_cnt.data(), st, m.err);
-        if (gather_side) rc |= launch_allgather_side(m, *gather_side, st);
-        rc |= comm_group_end(m.err);
+        if ((rc = comm_group_begin(m.err)) != 0) return rc;
+        rc = comm_alltoallv_f32(m.comm, m.recvbuf, m.recv_off.data(), m.recv_cnt.data(), m.sendbuf, m.send_off.data(), m.send_cnt.data(), st, m.err);
+        if (!rc && gather_side) rc = launch_allgather_side(m, *gather_side, st);
+        if (rc) {   // a failed call: close the outer group (keeping the first error message) and stop issuing NCCL work
+            std::string ignored;
+            comm_group_end(ignored);
+            return rc;
+        }
+        if ((rc = comm_group_end(m.err)) != 0) return rc;
         if (ensure_inverse(m, m.send_idx, &m.send_idx_inv, m.n_csr, st)) SBMF_LAUNCH((permute_gather_kernel), gs, 256, 0, st, m.sendbuf, m.send_idx_inv, m.us.e, m.n_csr);
         else SBMF_LAUNCH((permute_scatter_kernel), gs, 256, 0, st, m.sendbuf, m.send_idx, m.us.e, m.n_csr);
     }

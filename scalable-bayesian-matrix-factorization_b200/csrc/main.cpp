@@ -357,10 +357,19 @@ int main(int argc, char** argv)
             if (cd.num_users != num_users || cd.num_items != num_items || cd.K != K || cd.n_train != nN || cd.n_test != nT ||
                 cd.hyper_mode != cfg.hyper_mode)
                 throw path + ": checkpoint was written for another problem (users/items/K/ratings/-hyper differ)";
+            // the continued chain equals the interrupted one only under the same seed and mode flags
+            if (cd.seed != cfg.seed || cd.sample_mode != cfg.sample_mode || cd.burn_in != cfg.burn_in || cd.residual_mode != cfg.residual_mode ||
+                cd.rebuild_every != cfg.rebuild_every)
+                throw path + ": checkpoint was written by a chain with other flags (seed " + std::to_string(cd.seed) + ", sample mode " +
+                    std::to_string(cd.sample_mode) + ", burn-in " + std::to_string(cd.burn_in) + ", residual mode " + std::to_string(cd.residual_mode) +
+                    ", rebuild_every " + std::to_string(cd.rebuild_every) + "): pass the same flags to continue it";
+            sbmf_checkpoint_dims expect;
+            memset(&expect, 0, sizeof(expect));
+            expect.num_users = num_users; expect.num_items = num_items; expect.K = K; expect.n_train = nN; expect.n_test = nT;
             sbmf_state st;
             bind_state(st);
             int have_ps = 0;
-            if (sbmf_cuda_checkpoint_read(path.c_str(), &st, cps.data(), &have_ps) != SBMF_OK) throw std::string(sbmf_cuda_checkpoint_last_error());
+            if (sbmf_cuda_checkpoint_read(path.c_str(), &expect, &st, cps.data(), &have_ps) != SBMF_OK) throw std::string(sbmf_cuda_checkpoint_last_error());
             ck(sbmf_cuda_set_state(h, &st), h, "set_state");
             if (have_ps) ck(sbmf_cuda_set_pred_sum(h, cps.data()), h, "set_pred_sum");
             first_iter = st.sweeps_done;
@@ -423,6 +432,8 @@ int main(int argc, char** argv)
             memset(&cd, 0, sizeof(cd));
             cd.num_users = num_users; cd.num_items = num_items; cd.K = K; cd.hyper_mode = cfg.hyper_mode;
             cd.n_train = nN; cd.n_test = nT;
+            cd.seed = cfg.seed; cd.sample_mode = cfg.sample_mode; cd.burn_in = cfg.burn_in; cd.residual_mode = cfg.residual_mode;
+            cd.rebuild_every = cfg.rebuild_every;
             if (sbmf_cuda_checkpoint_write(cmd.get(p_save, "").c_str(), &cd, &st, cps.data()) != SBMF_OK)
                 throw std::string(sbmf_cuda_checkpoint_last_error());
         }

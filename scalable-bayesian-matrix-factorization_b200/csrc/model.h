@@ -77,8 +77,27 @@ struct Side {
     int prior_b = 0;                      // ... of the bias hyper-prior (4 = users, 5 = items)
 };
 
+// Tuning / developer options of a handle (sbmf_cuda_set_option; include/sbmf_cuda.h lists them).  They replace the
+// process-wide getenv knobs of round 1: every value lives in the handle, is set through the ABI and is covered by tests.
+struct Options {
+    int64_t l2_budget_mb = 192;   // resident bins: bytes of gathered factor blocks one launch keeps in flight (launch_phase)
+    int64_t max_blocks_per_launch = 0;   // resident bins: cap on the factor blocks one launch processes (0 = only the L2 budget)
+    int64_t resident_max = RESIDENT_MAX;   // rows longer than this stream through the sliced pipeline (<= RESIDENT_MAX)
+    int64_t slice_len = 0;        // heavy-row slice length; 0 = chosen from the shard size (build_worklists)
+    int64_t group_rows = 1;       // short rows: several rows per warp (row_group_kernel); 0 = one warp per row
+    int64_t fold_user = 1;        // one GPU: CSC->CSR residual hand-over folded into the user phase's first touch
+    int64_t fold_item = 0;        // one GPU: CSR->CSC hand-over folded into the item phase's first touch
+    int64_t graph = 1;            // replay the steady-state sweep from a CUDA graph when per-phase timing is off
+    int64_t device_plan = 1;      // multi-GPU: exchange plan computed on the device (0 = host planner, plan.cpp)
+    int64_t mgpu_pool = 1;        // multi-GPU: rating-sized arrays from the stream-ordered pool (0 = cudaMalloc)
+    int64_t peer = 1;             // multi-GPU: peer-mapped replicas / direct NVLink pushes (0 = NCCL exchanges)
+    int64_t trace = 0;            // 1: wall-clock of the set_train stages on stderr; 2: without device synchronisation
+    int64_t sharded_build = 1;    // multi-GPU: every rank uploads and sorts only its slice of the COO (0 = global build per rank)
+};
+
 struct Model {
     sbmf_config cfg{};
+    Options opt;
     int device = 0;
     int sm_count = 148;
     uint32_t K = 0, KB = 0, KP = 0;

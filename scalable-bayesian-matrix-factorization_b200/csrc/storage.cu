@@ -53,18 +53,12 @@ static cudaError_t dmalloc(T** p, size_t n)
 // sbmf_cuda_create): a second set_train in the same process then reuses the memory of the first instead of paying
 // cudaMalloc / cudaFree of several GB again (measured 25-110 ms and varying for the layout alone).  Multi-GPU models keep
 // cudaMalloc throughout: their buffers are exported through CUDA IPC, which pool memory does not support.
-// SBMF_MGPU_POOL=1 (opt-in until measured on a multi-GPU box): the pool also serves the multi-GPU layout -- only the six
-// buffers setup_peer_access exports (factors, biases, exchange buffers; plain dmalloc below) have to be cudaMalloc memory.
-static bool mgpu_pool()
-{
-    static const bool on = getenv("SBMF_MGPU_POOL") != nullptr;
-    return on;
-}
-
+// Option mgpu_pool (default on): the pool also serves the multi-GPU layout -- only the six buffers setup_peer_access exports
+// (factors, biases, exchange buffers; plain dmalloc below) have to be cudaMalloc memory.
 template <class T>
 static cudaError_t palloc(const Model& m, T** p, size_t n, cudaStream_t st)
 {
-    if (m.world > 1 && !mgpu_pool()) return dmalloc(p, n);
+    if (m.world > 1 && !m.opt.mgpu_pool) return dmalloc(p, n);
     return cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), st);
 }
 
@@ -145,7 +139,7 @@ int setup_peer_access(Model& m)
 {
     m.peer_ok = false;
     const int G = m.world;
-    if (G > MAX_PEERS || getenv("SBMF_NO_PEER")) return SBMF_OK;
+    if (G > MAX_PEERS || !m.opt.peer) return SBMF_OK;
     void* mine[6] = {m.us.F, m.it.F, m.us.bias, m.it.bias, m.recvbuf, m.sendbuf};
     constexpr int HW = 6 * 64 / 4;   // floats per rank
     std::vector<float> host((size_t)G * HW, 0.f);
@@ -297,7 +291,7 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
     hsp.push_back(0);
     // slice length: at most SLICE_LEN, but short enough that one streaming launch is >= ~8 waves of CTAs on this GPU
     // (a multi-GPU shard or a thin heavy tail would otherwise run 2-3 ragged waves per launch)
-    static const int64_t resident_max = getenv("SBMF_RESIDENT_MAX") ? atol(getenv("SBMF_RESIDENT_MAX")) : RESIDENT_MAX;   // tuning knob (<= 2048)
+    const int64_t resident_max = m.opt.resident_max;   // option (<= RESIDENT_MAX)
     uint64_t nnz_heavy_total = 0;
     for (uint32_t r = row0; r < row1; ++r) {
         const int64_t c = ptr[r + 1] - ptr[r];
@@ -307,7 +301,7 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
     {
         const int64_t want = (int64_t)(nnz_heavy_total / ((uint64_t)m.sm_count * 80u));
         slice_len = std::min<int64_t>(SLICE_LEN, std::max<int64_t>(1024, (want + 255) / 256 * 256));
-        if (const char* ev = getenv("SBMF_SLICE_LEN")) slice_len = atol(ev);   // tuning knob
+        if (m.opt.slice_len > 0) slice_len = m.opt.slice_len;   // option
     }
     for (uint32_t r = row0; r < row1; ++r) {
         const int64_t c = ptr[r + 1] - ptr[r];
@@ -354,10 +348,10 @@ __global__ void rebase_kernel(int64_t* ptr, uint32_t n, int64_t base)
 }
 
 template <typename T>
-static cudaError_t slice_inplace(T*& arr, uint64_t off, uint64_t cnt, cudaStream_t st)
+static cudaError_t slice_inplace(const Model& m, T*& arr, uint64_t off, uint64_t cnt, cudaStream_t st)
 {
     T* loc = nullptr;
-    if (mgpu_pool()) {   // everything stream-ordered: no cudaMalloc / cudaFree of rating-sized arrays
+    if (m.opt.mgpu_pool) {   // everything stream-ordered: no cudaMalloc / cudaFree of rating-sized arrays
         cudaError_t e = cudaMallocAsync((void**)&loc, (cnt ? cnt : 1) * sizeof(T), st);
         if (e != cudaSuccess) return e;
         if (cnt) e = cudaMemcpyAsync(loc, arr + off, cnt * sizeof(T), cudaMemcpyDeviceToDevice, st);
@@ -567,9 +561,9 @@ static int shard_storage(Model& m)
     m.n_csr = c1 - c0;
     m.n_csc = t1 - t0;
     {
-        // SBMF_DEVICE_PLAN=1: plan on the device (plan_exchange_device above) instead of downloading perm and walking it on the
-        // host.  Opt-in until it has run on a multi-GPU box; the host path is the one the CPU tests cover.
-        static const bool device_plan = getenv("SBMF_DEVICE_PLAN") != nullptr;
+        // option device_plan (default on): plan on the device (plan_exchange_device above) instead of downloading perm and
+        // walking it on the host (plan.cpp, which the CPU tests cover and the GPU tests compare with)
+        const bool device_plan = m.opt.device_plan != 0;
         std::vector<int64_t> sc(G), rc(G), pc((size_t)G * G);
         CK(dmalloc(&m.send_idx, m.n_csr)); CK(dmalloc(&m.recv_pos, m.n_csc));
         CK(dmalloc(&m.sendbuf, m.n_csr)); CK(dmalloc(&m.recvbuf, m.n_csc));
@@ -611,13 +605,13 @@ static int shard_storage(Model& m)
             m.recv_off[q] = ro; m.recv_cnt[q] = (size_t)rc[q]; ro += (size_t)rc[q];
         }
     }
-    if (mgpu_pool()) cudaFreeAsync(m.perm, m.s_main);
+    if (m.opt.mgpu_pool) cudaFreeAsync(m.perm, m.s_main);
     else cudaFree(m.perm);
     m.perm = nullptr;
     cudaStream_t st = m.s_main;
-    CK(slice_inplace(m.us.idx, c0, m.n_csr, st)); CK(slice_inplace(m.us.e, c0, m.n_csr, st)); CK(slice_inplace(m.csr_urow, c0, m.n_csr, st));
-    CK(slice_inplace(m.csr_r, c0, m.n_csr, st)); CK(slice_inplace(m.csr_id, c0, m.n_csr, st));
-    CK(slice_inplace(m.it.idx, t0, m.n_csc, st)); CK(slice_inplace(m.it.e, t0, m.n_csc, st)); CK(slice_inplace(m.csc_id, t0, m.n_csc, st));
+    CK(slice_inplace(m, m.us.idx, c0, m.n_csr, st)); CK(slice_inplace(m, m.us.e, c0, m.n_csr, st)); CK(slice_inplace(m, m.csr_urow, c0, m.n_csr, st));
+    CK(slice_inplace(m, m.csr_r, c0, m.n_csr, st)); CK(slice_inplace(m, m.csr_id, c0, m.n_csr, st));
+    CK(slice_inplace(m, m.it.idx, t0, m.n_csc, st)); CK(slice_inplace(m, m.it.e, t0, m.n_csc, st)); CK(slice_inplace(m, m.csc_id, t0, m.n_csc, st));
     SBMF_LAUNCH((rebase_kernel), (m.I + 256) / 256, 256, 0, m.s_main, m.us.ptr, m.I, (int64_t)c0);
     SBMF_LAUNCH((rebase_kernel), (m.J + 256) / 256, 256, 0, m.s_main, m.it.ptr, m.J, (int64_t)t0);
     CK(cudaGetLastError());
@@ -636,9 +630,9 @@ static int alloc_side_state(Model& m, Side& s)
     return SBMF_OK;
 }
 
-struct Trace {   // SBMF_TRACE=1: wall-clock of the set_train stages on stderr (=2: host time only, no device synchronisation)
-    bool on = getenv("SBMF_TRACE") != nullptr;
-    bool sync = !(getenv("SBMF_TRACE") && getenv("SBMF_TRACE")[0] == '2');
+struct Trace {   // option trace = 1: wall-clock of the set_train stages on stderr (= 2: host time only, no device synchronisation)
+    bool on, sync;
+    explicit Trace(const Model& m) : on(m.opt.trace != 0), sync(m.opt.trace != 2) {}
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     void lap(const char* what)
     {
@@ -653,7 +647,7 @@ struct Trace {   // SBMF_TRACE=1: wall-clock of the set_train stages on stderr (
 int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* item, const float* rating, uint32_t num_users,
                   uint32_t num_items)
 {
-    Trace tr;
+    Trace tr(m);
     free_storage(m);
     tr.lap("free previous");
     if (n >= (1ull << 31)) {

@@ -42,7 +42,9 @@ class State(C.Structure):
 
 class CheckpointDims(C.Structure):
     _fields_ = [("num_users", C.c_uint32), ("num_items", C.c_uint32), ("K", C.c_uint32), ("hyper_mode", C.c_int32),
-                ("n_train", C.c_uint64), ("n_test", C.c_uint64), ("sweeps_done", C.c_uint32), ("present", C.c_uint32)]
+                ("n_train", C.c_uint64), ("n_test", C.c_uint64), ("sweeps_done", C.c_uint32), ("present", C.c_uint32),
+                ("seed", C.c_uint64), ("sample_mode", C.c_int32), ("burn_in", C.c_uint32), ("residual_mode", C.c_uint32),
+                ("rebuild_every", C.c_uint32)]
 
 
 STATE_ARRAYS = ("U", "V", "b_i", "b_j", "mu_b_i", "sigma_b_i", "mu_b_j", "sigma_b_j", "sigma_u", "mu_u", "sigma_v", "mu_v", "E")
@@ -62,6 +64,14 @@ class SynthSpec(C.Structure):
                 ("s_item", C.c_double), ("test_frac", C.c_double), ("seed", C.c_uint64), ("device", C.c_int32),
                 ("reserved0", C.c_int32)]
 
+
+class ProbeResult(C.Structure):
+    _fields_ = [("hbm_copy_gbs", C.c_double), ("hbm_read_gbs", C.c_double), ("gather_sectors_per_s", C.c_double * 8),
+                ("sm_clock_mhz_max", C.c_double), ("table_bytes", C.c_uint64), ("n_gathers", C.c_uint64), ("sm_count", C.c_int32),
+                ("reserved0", C.c_int32)]
+
+
+PROBE_FORMS = ("g32_lane", "g64_lane", "g64_coop2", "g128_lane", "g128_coop4")
 
 FM_SAMPLE_LIVE, FM_SAMPLE_ZERO = 0, 1
 
@@ -154,7 +164,9 @@ def load_library(path=None):
     lib.sbmf_cuda_set_pred_sum.argtypes = [C.c_void_p, C.c_void_p]
     lib.sbmf_cuda_checkpoint_write.argtypes = [C.c_char_p, P(CheckpointDims), P(State), C.c_void_p]
     lib.sbmf_cuda_checkpoint_read_dims.argtypes = [C.c_char_p, P(CheckpointDims)]
-    lib.sbmf_cuda_checkpoint_read.argtypes = [C.c_char_p, P(State), C.c_void_p, P(C.c_int)]
+    lib.sbmf_cuda_checkpoint_read.argtypes = [C.c_char_p, P(CheckpointDims), P(State), C.c_void_p, P(C.c_int)]
+    lib.sbmf_cuda_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    lib.sbmf_cuda_get_option.argtypes = [C.c_void_p, C.c_char_p, P(C.c_int64)]
     lib.sbmf_cuda_checkpoint_last_error.restype = C.c_char_p
     lib.sbmf_cuda_sweep.argtypes = [C.c_void_p, C.c_uint32]
     lib.sbmf_cuda_eval.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double)]
@@ -210,7 +222,7 @@ def _f32(a):
 class SbmfModel:
     """One handle of the C ABI.  Method names follow the sbmf_cuda_* entry points."""
 
-    def __init__(self, cfg=None, **kw):
+    def __init__(self, cfg=None, options=None, **kw):
         self.lib = load_library()
         self.cfg = cfg if cfg is not None else default_config(**kw)
         self.h = C.c_void_p()
@@ -219,6 +231,8 @@ class SbmfModel:
             raise SbmfError(rc, self.lib.sbmf_cuda_last_error(None).decode())
         self.K = self.cfg.K
         self.N = self.Nt = self.I = self.J = 0
+        for name, value in (options or {}).items():
+            self.set_option(name, value)
 
     def _ck(self, rc):
         if rc != 0:
@@ -319,6 +333,15 @@ class SbmfModel:
 
     def reset_timing(self):
         self._ck(self.lib.sbmf_cuda_reset_timing(self.h))
+
+    def set_option(self, name, value):
+        """sbmf_cuda_set_option: tuning / developer options by name (include/sbmf_cuda.h lists them)"""
+        self._ck(self.lib.sbmf_cuda_set_option(self.h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int64()
+        self._ck(self.lib.sbmf_cuda_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
 
     def set_timing_enabled(self, on):
         """0 = off (sweeps only enqueue work), 1 = per-phase events, 2 = also per-launch events of the dominant kernel"""
@@ -458,13 +481,15 @@ def _state_struct(arr, I, J, K, N):
     return st, keep
 
 
-def checkpoint_write(path, arr, num_users, num_items, K, n_train, n_test, hyper_mode=0, pred_sum=None):
-    """sbmf_cuda_checkpoint_write: a get_state()-shaped dict (+ the running prediction sums) to a file; host only"""
+def checkpoint_write(path, arr, num_users, num_items, K, n_train, n_test, hyper_mode=0, pred_sum=None, seed=1, sample_mode=0, burn_in=0,
+                     residual_mode=0, rebuild_every=1):
+    """sbmf_cuda_checkpoint_write: a get_state()-shaped dict (+ the running prediction sums) to a file; host only.  seed and the mode
+    flags are those of the chain that produced the state (a resume continues it only under the same values)."""
     lib = load_library()
     st, keep = _state_struct(arr, num_users, num_items, K, n_train)
     ps = None if pred_sum is None else np.ascontiguousarray(pred_sum, np.float64)
     assert ps is None or ps.shape == (n_test,)
-    dims = CheckpointDims(num_users, num_items, K, hyper_mode, n_train, n_test, 0, 0)
+    dims = CheckpointDims(num_users, num_items, K, hyper_mode, n_train, n_test, 0, 0, seed, sample_mode, burn_in, residual_mode, rebuild_every)
     rc = lib.sbmf_cuda_checkpoint_write(os.fsencode(path), C.byref(dims), C.byref(st), _ptr(ps))
     if rc != 0:
         raise SbmfError(rc, lib.sbmf_cuda_checkpoint_last_error().decode())
@@ -484,13 +509,27 @@ def checkpoint_read(path):
         setattr(st, k, v.ctypes.data)
     ps = np.empty(Nt, np.float64) if (dims.present >> 13) & 1 else None
     have = C.c_int(0)
-    rc = lib.sbmf_cuda_checkpoint_read(os.fsencode(path), C.byref(st), _ptr(ps), C.byref(have))
+    rc = lib.sbmf_cuda_checkpoint_read(os.fsencode(path), C.byref(dims), C.byref(st), _ptr(ps), C.byref(have))
     if rc != 0:
         raise SbmfError(rc, lib.sbmf_cuda_checkpoint_last_error().decode())
     for k in STATE_SCALARS:
         arr[k] = getattr(st, k)
     d = {k: getattr(dims, k) for k, _ in CheckpointDims._fields_}
     return d, arr, (ps if have.value else None)
+
+
+def probe(device=0, table_bytes=0, n_gathers=0):
+    """sbmf_cuda_probe: HBM streaming bandwidth and the L2 -> SM gather rates of this device, measured now (csrc/probe.cu)."""
+    lib = load_library()
+    lib.sbmf_cuda_probe.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.POINTER(ProbeResult)]
+    lib.sbmf_cuda_probe_last_error.restype = C.c_char_p
+    r = ProbeResult()
+    rc = lib.sbmf_cuda_probe(int(device), int(table_bytes), int(n_gathers), C.byref(r))
+    if rc != 0:
+        raise SbmfError(rc, lib.sbmf_cuda_probe_last_error().decode())
+    return {"hbm_copy_gbs": r.hbm_copy_gbs, "hbm_read_gbs": r.hbm_read_gbs, "sm_count": r.sm_count, "sm_clock_mhz_max": r.sm_clock_mhz_max,
+            "table_bytes": r.table_bytes, "n_gathers": r.n_gathers,
+            "gather_sectors_per_s": {name: r.gather_sectors_per_s[i] for i, name in enumerate(PROBE_FORMS)}}
 
 
 def nccl_unique_id():

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(built):
     lib = ctypes.CDLL(built)
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
-    assert lib.sbmf_cuda_abi_version() == 1
+    assert lib.sbmf_cuda_abi_version() == 2
 
 
 def test_header_compiles_as_c(tmp_path):

@@ -510,3 +510,191 @@ def test_ng_mode_live_same_streams(ml100k):
     gs, os_ = m.get_state(), o.state()
     assert abs(gs["alpha"] - os_["alpha"]) / os_["alpha"] <= 1e-3
     m.close()
+
+
+# ------------------------------------------------------------------------------------------ options: every launch shape, same chain
+OPTION_SETS = [
+    {"max_blocks_per_launch": 1},                       # every block a launch of its own: b_begin > 0 continuation, pacc round trips
+    {"max_blocks_per_launch": 2, "group_rows": 0},      # ... and short rows on the one-warp-per-row kernel
+    {"fold_user": 0}, {"fold_item": 1},                 # residual hand-over between the slot orders: stand-alone pass <-> folded
+    {"resident_max": 64, "slice_len": 256},             # most rows through the sliced streaming pipeline, many slices per row
+    {"resident_max": 300, "slice_len": 1024, "max_blocks_per_launch": 1, "fold_item": 1},
+    {"graph": 0},
+]
+
+
+@pytest.mark.parametrize("residual_mode", [0, 1])
+@pytest.mark.parametrize("opts", OPTION_SETS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
+def test_options_keep_the_chain(opts, residual_mode):
+    """sbmf_cuda_set_option only changes launch shapes and which kernel path serves a row; every setting must reproduce the
+    oracle (zero noise, 1e-4) on a matrix that has rows in every resident bin and streamed rows on both sides."""
+    d = skewed_case(seed=9, I=60)
+    d2 = dict(d, train_user=d["train_item"], train_item=d["train_user"], test_user=d["test_item"], test_item=d["test_user"],
+              num_users=d["num_items"], num_items=d["num_users"])
+    for dd in (d, d2):
+        K = 20
+        import sbmf
+        m = sbmf.SbmfModel(K=K, sample_mode=2, residual_mode=residual_mode, options=opts)
+        for k, v in opts.items():
+            assert m.get_option(k) == v
+        m.set_train(dd["train_user"], dd["train_item"], dd["train_rating"], dd["num_users"], dd["num_items"])
+        m.set_test(dd["test_user"], dd["test_item"], dd["test_rating"])
+        o = orc.Oracle(dd["train_user"], dd["train_item"], dd["train_rating"], dd["test_user"], dd["test_item"], dd["test_rating"],
+                       dd["num_users"], dd["num_items"], K, noise=orc.NOISE_ZERO)
+        init_both(m, o, dd, K)
+        m.set_timing_enabled(0)      # graph replay from sweep 2 on (unless graph = 0)
+        m.sweep(6)
+        r_o, _ = o.sweep(6)
+        gs, os_ = m.get_state(), o.state()
+        check_state(gs, os_, 1e-4)
+        assert rel_err(gs["E"], os_["E"]) <= 1e-4
+        assert np.max(np.abs(m.rmse_history(0, 6)[0] - r_o)) <= 1e-5
+        m.close()
+
+
+def test_option_errors(ml100k):
+    import sbmf
+    m = sbmf.SbmfModel(K=8)
+    with pytest.raises(sbmf.SbmfError) as e:
+        m.set_option("no_such_option", 1)
+    assert e.value.code == -1 and "unknown option" in str(e.value)
+    with pytest.raises(sbmf.SbmfError) as e:
+        m.set_option("resident_max", 4096)                 # above RESIDENT_MAX
+    assert e.value.code == -1
+    d = ml100k
+    m.set_train(d["train_user"], d["train_item"], d["train_rating"], d["num_users"], d["num_items"])
+    with pytest.raises(sbmf.SbmfError) as e:
+        m.set_option("resident_max", 100)                  # shapes the work lists: only before set_train
+    assert e.value.code == -4
+    m.set_option("l2_budget_mb", 64)                       # launch-shape options stay adjustable
+    m.close()
+
+
+def test_invalid_priors_are_rejected():
+    """Round-1 advisor finding: non-positive Gamma shape / rate priors made the single-thread hyper kernel spin forever."""
+    import sbmf
+    for field, idx, val in (("alpha", 0, 0.0), ("beta", 4, -1.0), ("sigma", 2, 0.0), ("alpha_dash", None, -0.5), ("ng_a_0", None, 0.0),
+                            ("mu", 1, float("nan")), ("beta_dash", None, float("inf"))):
+        cfg = sbmf.default_config(K=4)
+        if idx is None:
+            setattr(cfg.priors, field, val)
+        else:
+            getattr(cfg.priors, field)[idx] = val
+        with pytest.raises(sbmf.SbmfError) as e:
+            sbmf.SbmfModel(cfg=cfg)
+        assert e.value.code == -1 and "priors" in str(e.value), (field, idx, val)
+
+
+def test_small_gamma_shapes_terminate():
+    """Shapes below 1 (ran_gamma's boost branch, random.h:120-125) and an empty training set: draws finish and stay finite."""
+    import sbmf
+    cfg = sbmf.default_config(K=4, sample_mode=0, seed=3)
+    cfg.priors.alpha_dash = 0.2          # alpha ~ Gamma(0.2 + 0, ...) on the empty training set
+    for i in range(6):
+        cfg.priors.alpha[i] = 0.05
+    m = sbmf.SbmfModel(cfg=cfg)
+    e = np.empty(0, np.uint32)
+    m.set_train(e, e, np.empty(0, np.float32), 4, 3)
+    m.set_test(np.array([0], np.uint32), np.array([1], np.uint32), np.array([3.0], np.float32))
+    m.init_factors()
+    m.sweep(20)
+    s = m.get_state()
+    assert np.isfinite(s["alpha"]) and s["alpha"] > 0 and np.all(np.isfinite(s["U"])) and np.all(np.isfinite(s["sigma_u"])) and np.all(s["sigma_u"] > 0)
+    m.close()
+
+
+# ------------------------------------------------------------------------------------------ BASELINE.json sizes against the oracle
+def synth(I, J, N, seed):
+    import sbmf
+    s = sbmf.synth_generate(I, J, N, seed=seed)
+    s["num_users"], s["num_items"] = I, J
+    return s
+
+
+@pytest.fixture(scope="module")
+def ml1m_shaped():
+    return synth(6040, 3706, 1000209, 20151001)      # BASELINE.json configs[0]'s shape (SURVEY.md 8d: seed 20151001 + config#)
+
+
+def test_ml1m_shaped_layout_and_zero_noise(ml1m_shaped):
+    """configs[0] (ML-1M shape, 6,040 x 3,706, 1.0M ratings, K = 50): device layout bit-exact, then 10 zero-noise sweeps within
+    1e-4 of the oracle on factors, biases, every hyper-parameter, the residual, the RMSE trajectory and the predictions."""
+    d, K = ml1m_shaped, 50
+    m, o = make_pair(d, K, 2)
+    got, want = m.get_layout(), o.layout()
+    for k in ("row_ptr", "col", "csr_id", "col_ptr", "row", "csc_id", "perm"):
+        assert np.array_equal(got[k], want[k]), k
+    init_both(m, o, d, K)
+    t = m.timing()
+    assert t["nnz_heavy_item"] > 0 and t["nnz_light_item"] > 0 and t["nnz_light_user"] > 0
+    m.sweep(10)
+    r_o, rs_o = o.sweep(10)
+    gs, os_ = m.get_state(), o.state()
+    check_state(gs, os_, 1e-4)
+    assert rel_err(gs["E"], os_["E"]) <= 1e-4
+    r_g, rs_g = m.rmse_history(0, 10)
+    assert np.max(np.abs(r_g - r_o)) <= 1e-5 and np.max(np.abs(rs_g - rs_o)) <= 1e-5
+    assert np.max(np.abs(m.get_pred() - o.pred_mean())) <= 1e-4
+    m.close()
+
+
+def test_ml1m_shaped_live_trajectory(ml1m_shaped):
+    """north_star: "with live sampling, the per-sweep test-RMSE trajectory on ML-1M matches within 0.003".  Same U0 / V0 on both
+    sides; the reference side is the oracle in its bit-exact glibc rand() mode (pinned to the unmodified binary by
+    tests/test_oracle.py) over 5 rand() seeds, the device side 5 Philox seeds; per-sweep means compared at every sweep
+    (at this size the seed-to-seed spread is ~1e-3 from sweep 0 on)."""
+    import sbmf
+    d, K, T, S = ml1m_shaped, 50, 12, 5
+    rs = np.random.RandomState(11)
+    U0 = (0.1 * rs.standard_normal((d["num_users"], K))).astype(np.float32)
+    V0 = (0.1 * rs.standard_normal((K, d["num_items"]))).astype(np.float32)
+    dev, ref = [], []
+    for s in range(S):
+        m = sbmf.SbmfModel(K=K, sample_mode=0, seed=104729 * (s + 1))
+        m.set_train(d["train_user"], d["train_item"], d["train_rating"], d["num_users"], d["num_items"])
+        m.set_test(d["test_user"], d["test_item"], d["test_rating"])
+        m.init_factors(U0, V0)
+        m.sweep(T)
+        dev.append(m.rmse_history(0, T)[0].copy())
+        m.close()
+        o = orc.Oracle(d["train_user"], d["train_item"], d["train_rating"], d["test_user"], d["test_item"], d["test_rating"],
+                       d["num_users"], d["num_items"], K, noise=orc.NOISE_RAND)
+        o.srand(s + 1)
+        o.init_factors(U0.astype(np.float64), V0.astype(np.float64))
+        ref.append(o.sweep(T)[0])
+        o.close()
+    dev, ref = np.array(dev), np.array(ref)
+    diff = np.abs(dev.mean(0) - ref.mean(0))
+    assert np.all(diff <= 0.003), (diff, dev.mean(0), ref.mean(0))
+    assert np.all(np.abs(dev - ref.mean(0)) <= 0.006)          # and no single chain strays
+    assert ref.mean(0)[-1] < ref.mean(0)[0]
+
+
+def test_ml10m_shaped_zero_noise_vs_oracle():
+    """configs[1] (ML-10M shape, 71,567 x 10,681, 10M ratings, K = 100), the oracle itself (~10 s per sweep on one core): layout
+    bit-exact and 3 zero-noise sweeps within 1e-4.  At this size every resident bin (1, 4 and 8 warps per row, both row-group
+    widths) holds thousands of rows and the streamed items have up to several hundred thousand ratings, so all kernel paths are
+    compared with the reference's arithmetic, not with themselves."""
+    I, J, N, K = 71567, 10681, 10000000, 100
+    d = synth(I, J, N, 20151002)
+    m, o = make_pair(d, K, 2)
+    got, want = m.get_layout(), o.layout()
+    for k in ("row_ptr", "col", "csr_id", "col_ptr", "row", "csc_id", "perm"):
+        assert np.array_equal(got[k], want[k]), k
+    del got, want
+    init_both(m, o, d, K)
+    t = m.timing()
+    assert min(t["nnz_light_user"], t["nnz_heavy_user"], t["nnz_light_item"], t["nnz_heavy_item"]) > 0
+    deg = np.bincount(d["train_user"], minlength=I)
+    caps = [32, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048]
+    lo = 0
+    for c in caps:                                              # every resident bin is populated
+        assert np.count_nonzero((deg > lo) & (deg <= c)) > 0, c
+        lo = c
+    m.sweep(3)
+    r_o, _ = o.sweep(3)
+    gs, os_ = m.get_state(), o.state()
+    check_state(gs, os_, 1e-4)
+    assert rel_err(gs["E"], os_["E"]) <= 1e-4
+    assert np.max(np.abs(m.rmse_history(0, 3)[0] - r_o)) <= 1e-5
+    m.close()

@@ -37,10 +37,13 @@ def test_checkpoint_file_round_trip(sbmf_mod, tmp_path, with_E, with_ps):
     arr = fake_state(sbmf, I, J, K, N, rs, with_E)
     ps = rs.standard_normal(Nt) if with_ps else None
     path = str(tmp_path / "c.ckpt")
-    sbmf.checkpoint_write(path, arr, I, J, K, N, Nt, hyper_mode=2, pred_sum=ps)
+    sbmf.checkpoint_write(path, arr, I, J, K, N, Nt, hyper_mode=2, pred_sum=ps, seed=2 ** 40 + 5, sample_mode=1, burn_in=3, residual_mode=1,
+                          rebuild_every=4)
     assert not os.path.exists(path + ".tmp")
     dims, got, ps2 = sbmf.checkpoint_read(path)
     assert (dims["num_users"], dims["num_items"], dims["K"], dims["n_train"], dims["n_test"], dims["hyper_mode"]) == (I, J, K, N, Nt, 2)
+    # the flags of the chain that wrote the state travel with it (a resume under other flags is a different chain)
+    assert (dims["seed"], dims["sample_mode"], dims["burn_in"], dims["residual_mode"], dims["rebuild_every"]) == (2 ** 40 + 5, 1, 3, 1, 4)
     assert dims["sweeps_done"] == 7
     assert ((dims["present"] >> 12) & 1) == int(with_E) and ((dims["present"] >> 13) & 1) == int(with_ps)
     for k in sbmf.STATE_ARRAYS:
@@ -53,8 +56,8 @@ def test_checkpoint_file_round_trip(sbmf_mod, tmp_path, with_E, with_ps):
     assert (ps2 is None) == (ps is None)
     if ps is not None:
         assert np.array_equal(ps2, ps)
-    # header 96 bytes + exactly the present arrays
-    want = 96 + 4 * (I * K + K * J + 3 * I + 3 * J) + 8 * 4 * K + (4 * N if with_E else 0) + (8 * Nt if with_ps else 0)
+    # header 128 bytes + exactly the present arrays
+    want = 128 + 4 * (I * K + K * J + 3 * I + 3 * J) + 8 * 4 * K + (4 * N if with_E else 0) + (8 * Nt if with_ps else 0)
     assert os.path.getsize(path) == want
 
 
@@ -77,6 +80,35 @@ def test_checkpoint_rejects_garbage_and_truncation(sbmf_mod, tmp_path):
     assert "truncated" in str(e.value)
     with pytest.raises(sbmf.SbmfError):   # unwritable target
         sbmf.checkpoint_write(str(tmp_path / "no_such_dir" / "x.ckpt"), arr, I, J, K, N, Nt)
+
+
+def test_checkpoint_read_refuses_buffers_of_other_dimensions(sbmf_mod, tmp_path):
+    """sbmf_cuda_checkpoint_read copies with the sizes in the FILE: a caller whose buffers were sized for another problem must be
+    refused before anything is written (round-1 advisor finding: heap overflow when read_dims was skipped)."""
+    import ctypes as C
+    sbmf = sbmf_mod
+    I, J, K, N, Nt = 9, 6, 4, 30, 5
+    arr = fake_state(sbmf, I, J, K, N, np.random.RandomState(1))
+    path = str(tmp_path / "big.ckpt")
+    sbmf.checkpoint_write(path, arr, I, J, K, N, Nt, pred_sum=np.ones(Nt))
+    lib = sbmf.load_library()
+    for wrong in ({"num_users": 3}, {"num_items": 2}, {"K": 2}, {"n_train": 7}, {"n_test": 1}):
+        want = dict(num_users=I, num_items=J, K=K, n_train=N, n_test=Nt)
+        want.update(wrong)
+        # buffers of the (smaller) size the caller believes in, with a canary after each
+        small = {k: np.full(int(np.prod(shape)) + 8, 7.0, dt) for k, (shape, dt) in
+                 sbmf._state_shapes(want["num_users"], want["num_items"], want["K"], want["n_train"]).items()}
+        st = sbmf.State()
+        for k, v in small.items():
+            setattr(st, k, v.ctypes.data)
+        ps = np.full(want["n_test"] + 8, 7.0)
+        dims = sbmf.CheckpointDims(want["num_users"], want["num_items"], want["K"], 0, want["n_train"], want["n_test"], 0, 0, 0, 0, 0, 0, 0)
+        have = C.c_int(0)
+        rc = lib.sbmf_cuda_checkpoint_read(os.fsencode(path), C.byref(dims), C.byref(st), ps.ctypes.data, C.byref(have))
+        assert rc == -1, wrong
+        assert b"caller's buffers" in lib.sbmf_cuda_checkpoint_last_error()
+        assert all(np.all(v == 7.0) for v in small.values()) and np.all(ps == 7.0)     # nothing was touched
+    assert lib.sbmf_cuda_checkpoint_read(os.fsencode(path), None, None, None, None) == -1
 
 
 # ------------------------------------------------------------------------------------------------------------ GPU
@@ -211,3 +243,26 @@ def test_cli_save_and_load_state(sbmf_mod, ml100k, tmp_path):
     assert np.max(np.abs(p4 - p22)) <= 1e-4
     r = subprocess.run(base + ["-iter", "1", "-dim", "1,1,13", "-load_state", "s.ckpt"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 1 and "another problem" in r.stderr
+    # same problem, other seed: the chain would not be the one that was interrupted
+    r = subprocess.run([cli, "-train", str(tr), "-test", str(te), "-seed", "10"] + dim + ["-iter", "1", "-load_state", "s.ckpt"],
+                       capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "other flags" in r.stderr
+
+
+@pytest.mark.gpu
+def test_rmse_history_grows_past_its_first_allocation(sbmf_mod, tiny):
+    """The history starts with room for 4096 sweeps and grows with the chain (it used to return an error beyond that); the graph
+    replay survives the reallocation."""
+    sbmf = sbmf_mod
+    m = _model(sbmf, tiny, 3, sample_mode=0, seed=2)
+    m.init_factors()
+    m.set_timing_enabled(0)
+    m.sweep(4090)
+    m.sweep(20)
+    r, rs = m.rmse_history(0, 4110)
+    assert np.all(np.isfinite(r)) and np.all(r > 0) and np.all(rs > 0)
+    m2 = _model(sbmf, tiny, 3, sample_mode=0, seed=2)
+    m2.init_factors()
+    m2.sweep(5)
+    assert np.array_equal(m2.rmse_history(0, 5)[0], r[:5])
+    m.close(); m2.close()

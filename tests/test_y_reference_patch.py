@@ -67,7 +67,6 @@ def test_patched_libfm_reaches_the_library(patched, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="general FM Gibbs path: first run on a B200 pending (written without GPU access)", strict=False)
 def test_patched_libfm_prints_the_binding_trajectory(patched):
     """tests/fm_gpu_cases.py::case_libfm_learner in a process of its own (the CPU suite runs the same case on the CPU execution of the
     kernels, tests/test_fm_simt_emulation.py)"""

@@ -4,9 +4,8 @@ zero-noise state within 1e-4 after 10 iterations (MF and general design matrices
 columns of every kernel tier), live chains as distributions, error behaviour.  Cases live in tests/fm_gpu_cases.py and run in a
 process of their own each.
 
-Status: this path was written after the round's GPU budget was spent, so these cases have NOT run on a B200 yet (the formulas and
-the run schedule are checked on the CPU by tests/test_fm_emulation.py).  Until their first hardware run they are non-strict
-xfail: a failure is reported as xfailed, a pass as xpassed, and neither hides behind the rest of the suite."""
+Status: all cases passed on a B200 at the end of round 1 (GPUTEST_r01.json: 12 xpassed); they are now ordinary gating tests --
+a regression in csrc/fm.cu turns the suite red."""
 import os
 import subprocess
 import sys
@@ -16,7 +15,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = ["columns", "zero_mf", "zero_general", "zero_general_k20", "zero_als", "zero_variants", "long_columns", "live", "live_small", "errors", "cli"]
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first run on a B200 pending (written without GPU access)", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("case", CASES)

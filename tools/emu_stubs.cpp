@@ -31,6 +31,9 @@ extern "C" int sbmf_cuda_synth_generate(const sbmf_synth_spec*, uint64_t*, uint6
     return SBMF_ERR_UNSUPPORTED;
 }
 extern "C" const char* sbmf_cuda_synth_last_error(void) { return "no device generator in the host build"; }
+// hardware probes (csrc/probe.cu) measure a GPU: nothing to emulate
+extern "C" int sbmf_cuda_probe(int, uint64_t, uint64_t, sbmf_probe_result*) { return SBMF_ERR_UNSUPPORTED; }
+extern "C" const char* sbmf_cuda_probe_last_error(void) { return "no hardware probes in the host build"; }
 
 // marker: bindings refuse a library that exports this unless the test harness asked for the emulation (sbmf.py load_library, bench.py)
 extern "C" int sbmf_simt_host_emulation(void) { return 1; }

@@ -2,7 +2,9 @@
 """tools/mgpu_check.py -- multi-GPU parity check, run under torchrun (one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py
 Every rank: G-GPU zero-noise sweeps vs the CPU oracle (<= 1e-4), G-GPU vs 1-GPU live chain on the same seed (same Philox
-draws by construction), with rebuild_every 1 and 3 (the latter exercises the reverse CSC->CSR all-to-all)."""
+draws by construction), with rebuild_every 1 and 3 (the latter exercises the reverse CSC->CSR all-to-all).
+Optional argument: "name=value,name=value" options for the multi-GPU handles (sbmf_cuda_set_option), e.g. "device_plan=0,peer=0".
+tests/test_zz_multi_gpu.py runs it under pytest on boxes with >= 2 GPUs."""
 import os
 import sys
 
@@ -23,6 +25,9 @@ def rel(a, b):
 
 
 def main():
+    opts = {}
+    if len(sys.argv) > 1 and sys.argv[1]:
+        opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in sys.argv[1].split(",")}
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo")
     idt = torch.zeros(128, dtype=torch.uint8)
@@ -50,7 +55,7 @@ def main():
             if rank == 0:
                 idt = torch.frombuffer(bytearray(sbmf.nccl_unique_id()), dtype=torch.uint8).clone()
             dist.broadcast(idt, 0)
-            m = sbmf.SbmfModel(K=K, sample_mode=2, device=local, rank=rank, world_size=world, nccl_id=idt.numpy().tobytes(), rebuild_every=every)
+            m = sbmf.SbmfModel(K=K, sample_mode=2, device=local, rank=rank, world_size=world, nccl_id=idt.numpy().tobytes(), rebuild_every=every, options=opts)
             m.set_train(d["train_user"], d["train_item"], d["train_rating"], d["num_users"], d["num_items"])
             m.set_test(d["test_user"], d["test_item"], d["test_rating"])
             m.init_factors(U0, V0)
@@ -78,7 +83,7 @@ def main():
         if rank == 0:
             idt = torch.frombuffer(bytearray(sbmf.nccl_unique_id()), dtype=torch.uint8).clone()
         dist.broadcast(idt, 0)
-        mg = sbmf.SbmfModel(K=K, sample_mode=0, seed=11, device=local, rank=rank, world_size=world, nccl_id=idt.numpy().tobytes())
+        mg = sbmf.SbmfModel(K=K, sample_mode=0, seed=11, device=local, rank=rank, world_size=world, nccl_id=idt.numpy().tobytes(), options=opts)
         m1 = sbmf.SbmfModel(K=K, sample_mode=0, seed=11, device=local)
         mg.set_timing_enabled(0)     # multi-GPU chain replays the captured CUDA graph (with the NCCL calls inside) from sweep 2 on
         for m in (mg, m1):
@@ -97,7 +102,7 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
     if rank == 0:
-        print("MGPU_CHECK_OK worst", worst, flush=True)
+        print("MGPU_CHECK_OK worst", worst, "options", opts, flush=True)
     dist.destroy_process_group()
 
 
