@@ -392,6 +392,43 @@ def full_config_point(sbmf, dev):
             "n_train": n, "what": "the complete ML-10M-shaped K=100 configuration on one B200, everything resident, CUDA events"}
 
 
+def e2e_cli(workload, steps, ref_load_s=None, ref_load_n=None):
+    """The drop-in job FROM FILES: bin/sbmf -train F -test F -dim 1,1,K -iter steps -out P on the workload written as triple text
+    and as libFM binary (.x/.y) by bin/sbmf_synth; stage seconds from the CLI's own -timing file (parse = the reader of
+    csrc/rating_reader.h replacing the three getline + sscanf passes of gibbs_sbpmf2.cpp:32-221; build = set_train + set_test)."""
+    I, J, NTRAIN, K = WORKLOADS[workload]
+    n = int(round(NTRAIN / (1 - TEST_FRAC)))
+    exe, synth = os.path.join(PKG, "bin", "sbmf"), os.path.join(PKG, "bin", "sbmf_synth")
+    out = {"workload": workload, "what": "bin/sbmf from files: parse + device build + sweeps (each followed by the RMSE read-back and its `rmse is` line) + -out predictions; wall clock of the whole process and the CLI's own stage timers"}
+    with tempfile.TemporaryDirectory(prefix="sbmf_cli_") as tmp:
+        for fmt in ("triples", "libfm_binary"):
+            tr, te = os.path.join(tmp, f"{fmt}.train"), os.path.join(tmp, f"{fmt}.test")
+            t0 = time.perf_counter()
+            g = subprocess.run([synth, "-users", str(I), "-items", str(J), "-ratings", str(n), "-seed", str(SEED), "-test_frac", str(TEST_FRAC),
+                                "-binary", "1" if fmt == "libfm_binary" else "0", "-train", tr, "-test", te], capture_output=True, text=True, check=True)
+            info = json.loads(g.stdout.strip().splitlines()[-1])
+            write_s = time.perf_counter() - t0
+            tj = os.path.join(tmp, f"{fmt}.timing.json")
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "-train", tr, "-test", te, "-dim", f"1,1,{K}", "-iter", str(steps), "-seed", "1", "-out", os.path.join(tmp, f"{fmt}.pred"),
+                                "-timing", tj], capture_output=True, text=True, cwd=tmp)
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                out[fmt] = {"error": (r.stderr or r.stdout)[-300:]}
+                continue
+            st = json.load(open(tj))
+            rm = [float(l.split()[-1]) for l in r.stdout.splitlines() if l.startswith("rmse is")]
+            files = [tr, te] if fmt == "triples" else [tr + ".x", tr + ".y", te + ".x", te + ".y"]
+            out[fmt] = {"value": info["n_train"] * K * steps / wall, "unit": UNIT, "wall_s": wall, "stages": st, "final_rmse": rm[-1] if rm else None,
+                        "input_bytes": int(sum(os.path.getsize(f) for f in files)), "n_train": info["n_train"], "files_written_in_s": round(write_s, 2)}
+            for f in files:
+                os.remove(f)
+    if ref_load_s is not None:
+        out["reference_load"] = {"seconds": ref_load_s, "n_train": ref_load_n, "ratings_per_s": ref_load_n / ref_load_s if ref_load_s > 0 else None,
+                                 "what": "the reference's own three getline + sscanf passes + jagged-array build (gibbs_sbpmf2.cpp:32-221) on the cpu_baseline sample: wall(T=1) minus one sweep"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -404,6 +441,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-point", action="store_true", help="skip the ML-10M-shaped full-configuration point")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the G-GPU vs 1-GPU chain check")
+    ap.add_argument("--no-cli", action="store_true", help="skip e2e_cli (the job from files through bin/sbmf)")
     ap.add_argument("--options", default="", help="name=value,... passed to sbmf_cuda_set_option on every handle (A/B measurements)")
     a = ap.parse_args()
     rank, local_rank, world = dist_env()
@@ -560,14 +598,20 @@ def main():
     if not a.no_cpu_baseline and world == 1:
         cb = cpu_reference(take_sample(d, a.cpu_sample), K)
     if not a.no_full_point and world == 1 and a.workload != FULL_POINT:
-        del d
         fp = full_config_point(sbmf, dev)
+    cli = None
+    if not a.no_cli and world == 1:
+        del d
+        try:
+            cli = e2e_cli(a.workload, a.steps, cb.get("load_s") if cb else None, cb.get("n_train") if cb else None)
+        except Exception as e:   # noqa: BLE001 - an additional measurement: report, do not lose the line
+            cli = {"error": f"{type(e).__name__}: {e}"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "run": run,
             "sweeps_per_s": 1e3 / ms_per_step, "wall_ms_per_step": wall_ms / a.steps, "rmse_after_timed": rmse, "clocks": clocks,
             "gpu_launches": int(launches), "phases_ms": phases, "roofline": roof, "roofline_sweep": sweep_roof, "probes": probes, "e2e": e2e,
-            "cpu_baseline": cb, "parity": parity, "full_config_point": fp, "paper_i5_openmp_fu_per_s": 25.4e6}
+            "cpu_baseline": cb, "parity": parity, "full_config_point": fp, "e2e_cli": cli, "paper_i5_openmp_fu_per_s": 25.4e6}
     emit(line)
 
 

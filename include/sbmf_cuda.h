@@ -143,8 +143,10 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
                           into several launches that continue from the stored residual / partial predictions
      max_blocks_per_launch (0)  additional cap on the factor blocks per launch of the resident rows (0: none)
      resident_max  (2048) rows with more ratings stream through the sliced pipeline          [before set_train]
+     resident_max_user / resident_max_item  the same threshold per side (resident_max sets both)  [before set_train]
      slice_len     (0)    ratings per slice of a streamed row; 0 = chosen from the shard size  [before set_train]
      group_rows    (1)    short rows share a warp (0: one warp per row)
+     pair_gather   (1)    streamed rows gather (previous, current) factor block as one 64-byte row by lane pairs (0: two gathers)
      fold_user / fold_item (1 / 0)  one GPU: residual hand-over between the slot orders folded into the phase's first touch
      graph         (1)    steady-state sweep replayed from a CUDA graph when per-phase timing is off
      device_plan   (1)    multi-GPU: exchange plan computed on the device (0: host planner)  [before set_train]

@@ -51,8 +51,11 @@ static const OptionDesc kOptions[] = {
     {"l2_budget_mb", &Options::l2_budget_mb, 1, 1 << 20, false},
     {"max_blocks_per_launch", &Options::max_blocks_per_launch, 0, 1 << 20, false},
     {"resident_max", &Options::resident_max, 1, RESIDENT_MAX, true},
+    {"resident_max_user", &Options::resident_max_user, 1, RESIDENT_MAX, true},
+    {"resident_max_item", &Options::resident_max_item, 1, RESIDENT_MAX, true},
     {"slice_len", &Options::slice_len, 0, 1 << 24, true},
     {"group_rows", &Options::group_rows, 0, 1, false},
+    {"pair_gather", &Options::pair_gather, 0, 1, false},
     {"fold_user", &Options::fold_user, 0, 1, false},
     {"fold_item", &Options::fold_item, 0, 1, false},
     {"graph", &Options::graph, 0, 1, false},
@@ -93,6 +96,7 @@ int sbmf_cuda_set_option(sbmf_handle* h, const char* name, int64_t value)
         return SBMF_ERR_STATE;
     }
     m.opt.*(d->field) = value;
+    if (d->field == &Options::resident_max) m.opt.resident_max_user = m.opt.resident_max_item = value;
     if (m.graph_exec) {   // the captured sweep may embed the old choice
         cudaSetDevice(m.device);
         cudaStreamSynchronize(m.s_main);

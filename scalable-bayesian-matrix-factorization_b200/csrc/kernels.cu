@@ -37,6 +37,11 @@ struct PhaseArgs {
     float* brep[MAX_PEERS];
     int nrep;
     const float* Fother;
+    // F2other[pb][row][16] = (block pb, block pb + 1) of every row of the other side side by side (pair_pack_kernel): the
+    // streaming pipeline's pass b gathers the two blocks it needs (b - 1 to apply, b to accumulate) as ONE 64-byte row that two
+    // adjacent lanes fetch together -- half the L1TEX wavefronts of two separate sector gathers (sbmf_cuda_probe: 1.50 vs 0.88
+    // sectors per clock per SM)
+    const float* F2other;
     uint32_t ns_self, ns_other;   // rows per factor block INCLUDING the all-zero pad row at index n (gather target of empty slots)
     float* bias;
     const float* mu_b;
@@ -579,12 +584,96 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
 // to e (PREV: 0 = only the global shift, 1 = bias delta, 2 = delta of block pb, re-gathering f) and accumulates
 // the partial sums of the current step (CUR: 0 = nothing, 1 = bias: sum e, 2 = block b: g, G) per slice;
 // heavy_solve<CUR> combines a row's slices in slice order and performs the update(s).
-template <int PREV, int CUR, int UNR, int THREADS, bool REFRESH>
-__global__ void __launch_bounds__(THREADS)
-heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const float* __restrict__ hdelta, const float* __restrict__ hbias_delta,
-                        float* __restrict__ hpart, int pb, int b)
+// The update(s) of one streamed row, executed by the LAST slice CTA of the row to finish a pass (heavy_accumulate_kernel):
+// warp w sums the partials of slices s0 + w, s0 + w + NW, ... (independent coalesced 192-byte reads, through L2: the lines were
+// written by other SMs during this launch), the sums are combined in warp order -- a fixed tree whatever CTA happens to be last,
+// so results are reproducible -- and warp 0 performs the update(s).  CUR == 1: bias half-step; CUR == 2: factor block b.
+template <int CUR, int NW>
+__device__ __forceinline__ void heavy_row_solve(const PhaseArgs& a, uint32_t hrow, uint32_t s0, uint32_t s1, const float* __restrict__ hpart,
+                                                float* __restrict__ hdelta, float* __restrict__ hbias_delta, int b, float (*s_part)[NACC], float* s_tot)
 {
-    __shared__ float s_part[THREADS / 32][NACC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t row = a.rows_of_hrow[hrow];
+    if (CUR == 1) {
+        float t = 0.f;
+        for (uint32_t s = s0 + threadIdx.x; s < s1; s += NW * 32) t += __ldcg(hpart + (size_t)s * NACC);
+        t = warp_sum(t);
+        if (lane == 0) s_part[warp][0] = t;
+        __syncthreads();
+        if (warp != 0) return;
+        t = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += s_part[w][0];
+        const float alpha = a.sc->alpha_f;
+        const uint32_t sweep = a.sc->sweep;
+        const float c = (float)(a.ptr[row + 1] - a.ptr[row]);
+        const float bo = a.bias[row], sb = a.sigma_b[row], mb = a.mu_b[row];
+        const float s = 1.0f / (sb + alpha * c);
+        const float mean = s * (sb * mb + alpha * (t + c * bo));
+        float z = 0.f;
+        if (a.mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        const float bn = draw_f32(a.mode, mean, s, z);
+        __syncwarp();   // every lane has read the old bias (all lanes compute the same value, lane 0 stores it)
+        if (lane == 0) {
+            for (int q = 0; q < a.nrep; ++q) a.brep[q][row] = bn;
+            hbias_delta[hrow] = bo - bn;
+        }
+    } else {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+        for (uint32_t s = s0 + warp; s < s1; s += NW) {
+            a0 += __ldcg(hpart + (size_t)s * NACC + lane);
+            if (lane < NACC - 32) a1 += __ldcg(hpart + (size_t)s * NACC + 32 + lane);
+        }
+        s_part[warp][lane] = a0;
+        if (lane < NACC - 32) s_part[warp][32 + lane] = a1;
+        __syncthreads();
+        if (warp != 0) return;
+        const float alpha = a.sc->alpha_f;
+        const uint32_t sweep = a.sc->sweep;
+        float zl = 0.f;
+        if (a.mode != SAMPLE_ZERO && lane < 8) zl = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)(b * 8 + lane), sweep));
+        a0 = 0.f;
+        a1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            a0 += s_part[w][lane];
+            if (lane < NACC - 32) a1 += s_part[w][32 + lane];
+        }
+        s_tot[lane] = a0;
+        if (lane < NACC - 32) s_tot[32 + lane] = a1;
+        __syncwarp();
+        float z[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) z[k] = __shfl_sync(0xffffffffu, zl, k);
+        const size_t foff = ((size_t)b * a.ns_self + row) * 8;
+        const f8 uo = ld256(a.Fself + foff);
+        f8 un;
+        float d[8];
+        solve_block(s_tot, uo, z, a.sigma_kf + b * 8, a.mu_kf + b * 8, alpha, a.mode, (int)a.K - b * 8, un, d);
+        __syncwarp();   // every lane has read the old factors
+        if (lane == 0) {
+            for (int q = 0; q < a.nrep; ++q) st256(a.Frep[q] + foff, un);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hdelta[(size_t)hrow * 8 + k] = d[k];
+        }
+    }
+}
+
+// PAIR (PREV == 2 and CUR == 2 only): the factor rows come from the pair array F2other.  Lanes (2k, 2k+1) fetch the 64-byte row
+// of the even lane's rating with one 256-bit load each (lower half = block pb to the even lane, upper half = block b to the odd
+// lane), then the row of the odd lane's rating with the halves swapped.  Every lane thus holds the previous block of its OWN
+// rating (delta apply, residual store) and the current block of its PARTNER's rating, whose updated residual arrives by one
+// shuffle for the accumulation.  Which load delivered which is a matter of lane parity: 16 selects per rating, paid from the
+// issue slots this gather-bound kernel leaves idle.
+template <int PREV, int CUR, int UNR, int THREADS, bool REFRESH, bool PAIR = false>
+__global__ void __launch_bounds__(THREADS)
+heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, float* __restrict__ hdelta, float* __restrict__ hbias_delta,
+                        float* __restrict__ hpart, const uint32_t* __restrict__ slice_ptr, uint32_t* __restrict__ hcount, int pb, int b)
+{
+    __shared__ __align__(16) float s_part[THREADS / 32][NACC];
+    __shared__ __align__(16) float s_tot[NACC];
+    __shared__ uint32_t s_last;
     const Slice sl = slices[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float dprev[8];
@@ -620,6 +709,58 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
     ga.clear();
     const uint32_t* idx = a.idx + sl.start;
     float* ep = a.e + sl.start;
+    if constexpr (PAIR) {
+        static_assert(!PAIR || (PREV == 2 && CUR == 2), "the pair form serves the block-to-block step");
+        const float* F2 = a.F2other + (size_t)pb * a.ns_other * 16;
+        const int odd = lane & 1;
+        for (uint32_t base0 = 0; base0 < sl.len; base0 += THREADS * UNR) {   // warp-uniform trip count: the shuffles need every lane
+            uint32_t id[UNR];
+            float e[UNR];
+            float pr[REFRESH ? UNR : 1];
+            bool ok[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const uint32_t i = base0 + u * THREADS + threadIdx.x;
+                ok[u] = i < sl.len;
+                id[u] = ok[u] ? idx[i] : pad_row;
+                e[u] = ok[u] ? ep[i] : 0.f;
+                if (REFRESH) pr[u] = (ok[u] && pb > 0) ? pp[i] : 0.f;
+            }
+            f8 r1[UNR], r2[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const uint32_t idp = __shfl_xor_sync(0xffffffffu, id[u], 1);
+                const uint32_t id_even = odd ? idp : id[u], id_odd = odd ? id[u] : idp;
+                r1[u] = ld256_nc(F2 + (size_t)id_even * 16 + odd * 8);         // even lane: own previous block; odd lane: partner's current block
+                r2[u] = ld256_nc(F2 + (size_t)id_odd * 16 + (odd ^ 1) * 8);   // even lane: partner's current block; odd lane: own previous block
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const uint32_t i = base0 + u * THREADS + threadIdx.x;
+                f8 fprev, fcur;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    fprev.v[k] = odd ? r2[u].v[k] : r1[u].v[k];
+                    fcur.v[k] = odd ? r1[u].v[k] : r2[u].v[k];
+                }
+                if (kPairedDots && REFRESH) {
+                    const float2 s2 = dot8_pair(fprev, dun);
+                    e[u] += s2.x;
+                    pr[u] += s2.y;
+                } else {
+                    e[u] += dot8(fprev, dprev);
+                    if (REFRESH) pr[u] += dot8(fprev, unprev);
+                }
+                if (ok[u]) {
+                    ep[i] = e[u];
+                    if (REFRESH) pp[i] = pr[u];
+                }
+                // the partner's rating is the one whose current block this lane holds (an invalid slot carries e = 0 and the zero pad row)
+                const float e_partner = __shfl_xor_sync(0xffffffffu, e[u], 1);
+                ga.add(fcur, e_partner);
+            }
+        }
+    } else
     // batches of UNR ratings per thread: all index/residual loads, then all gathers, then the math, so that
     // 2*UNR sector gathers per thread are in flight (the kernel is bound by the L2->SM gather path, not by arithmetic)
     for (uint32_t base = threadIdx.x; base < sl.len; base += THREADS * UNR) {
@@ -692,86 +833,22 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, const flo
             hpart[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
         }
     }
-}
-
-// One CTA of HS_WARPS warps per heavy row.  A row has up to several hundred slices (more on a multi-GPU shard, where slices
-// are shorter): warp w sums the partials of slices s0 + w, s0 + w + HS_WARPS, ... (independent coalesced 192-byte reads), the
-// sums are combined in warp order -- a fixed tree, so results are reproducible -- and warp 0 performs the update(s).
-// HS_WARPS = 8 where rows average many slices, 2 otherwise (thousands of rows with a handful of slices: fewer idle warps);
-// the choice (launch_phase) depends only on the work lists, so it is the same every sweep.
-template <int CUR, int HS_WARPS>
-__global__ void __launch_bounds__(HS_WARPS * 32)
-heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ heavy_rows, const uint32_t* __restrict__ slice_ptr, uint32_t n_heavy,
-                   const float* __restrict__ hpart, float* __restrict__ hdelta, float* __restrict__ hbias_delta, int b)
-{
-    __shared__ __align__(16) float s_part[HS_WARPS][NACC];
-    __shared__ __align__(16) float s_tot[NACC];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t hrow = blockIdx.x;
-    const uint32_t row = heavy_rows[hrow];
-    const uint32_t s0 = slice_ptr[hrow], s1 = slice_ptr[hrow + 1];
-    if (CUR == 1) {
-        float t = 0.f;
-        for (uint32_t s = s0 + threadIdx.x; s < s1; s += HS_WARPS * 32) t += hpart[(size_t)s * NACC];
-        t = warp_sum(t);
-        if (lane == 0) s_part[warp][0] = t;
+    if (CUR != 0) {
+        // The row's update runs in the tail of this launch: every slice CTA publishes its partial, takes a ticket, and the CTA
+        // that draws the last ticket of its row combines the partials (in slice order) and solves.  All CTAs of the row have
+        // read the pending delta / bias delta of the previous step before they take a ticket, so the solve may overwrite them.
+        __threadfence();
         __syncthreads();
-        if (warp != 0) return;
-        t = 0.f;
-#pragma unroll
-        for (int w = 0; w < HS_WARPS; ++w) t += s_part[w][0];
-        const float alpha = a.sc->alpha_f;
-        const uint32_t sweep = a.sc->sweep;
-        const float c = (float)(a.ptr[row + 1] - a.ptr[row]);
-        const float bo = a.bias[row], sb = a.sigma_b[row], mb = a.mu_b[row];
-        const float s = 1.0f / (sb + alpha * c);
-        const float mean = s * (sb * mb + alpha * (t + c * bo));
-        float z = 0.f;
-        if (a.mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
-        const float bn = draw_f32(a.mode, mean, s, z);
-        __syncwarp();   // every lane has read the old bias (all lanes compute the same value, lane 0 stores it)
-        if (lane == 0) {
-            for (int q = 0; q < a.nrep; ++q) a.brep[q][row] = bn;
-            hbias_delta[hrow] = bo - bn;
+        if (threadIdx.x == 0) {
+            const uint32_t n_row = slice_ptr[sl.hrow + 1] - slice_ptr[sl.hrow];
+            const uint32_t ticket = atomicAdd(&hcount[sl.hrow], 1u);
+            s_last = (ticket == n_row - 1) ? 1u : 0u;
+            if (s_last) hcount[sl.hrow] = 0u;   // re-armed for the next pass (nobody else touches it before the next launch)
         }
-    } else {
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-        for (uint32_t s = s0 + warp; s < s1; s += HS_WARPS) {
-            a0 += hpart[(size_t)s * NACC + lane];
-            if (lane < NACC - 32) a1 += hpart[(size_t)s * NACC + 32 + lane];
-        }
-        s_part[warp][lane] = a0;
-        if (lane < NACC - 32) s_part[warp][32 + lane] = a1;
         __syncthreads();
-        if (warp != 0) return;
-        const float alpha = a.sc->alpha_f;
-        const uint32_t sweep = a.sc->sweep;
-        float zl = 0.f;
-        if (a.mode != SAMPLE_ZERO && lane < 8) zl = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)(b * 8 + lane), sweep));
-        a0 = 0.f;
-        a1 = 0.f;
-#pragma unroll
-        for (int w = 0; w < HS_WARPS; ++w) {
-            a0 += s_part[w][lane];
-            if (lane < NACC - 32) a1 += s_part[w][32 + lane];
-        }
-        s_tot[lane] = a0;
-        if (lane < NACC - 32) s_tot[32 + lane] = a1;
-        __syncwarp();
-        float z[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) z[k] = __shfl_sync(0xffffffffu, zl, k);
-        const size_t foff = ((size_t)b * a.ns_self + row) * 8;
-        const f8 uo = ld256(a.Fself + foff);
-        f8 un;
-        float d[8];
-        solve_block(s_tot, uo, z, a.sigma_kf + b * 8, a.mu_kf + b * 8, alpha, a.mode, (int)a.K - b * 8, un, d);
-        __syncwarp();   // every lane has read the old factors
-        if (lane == 0) {
-            for (int q = 0; q < a.nrep; ++q) st256(a.Frep[q] + foff, un);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) hdelta[(size_t)hrow * 8 + k] = d[k];
+        if (s_last) {
+            __threadfence();
+            heavy_row_solve<CUR, THREADS / 32>(a, sl.hrow, slice_ptr[sl.hrow], slice_ptr[sl.hrow + 1], hpart, hdelta, hbias_delta, b, s_part, s_tot);
         }
     }
 }
@@ -1123,6 +1200,21 @@ export_factors_kernel(const float* __restrict__ F, float* __restrict__ dst, uint
     }
 }
 
+// Pair array of one side (PhaseArgs::F2other): F2[pb][row][0..7] = F[pb][row], F2[pb][row][8..15] = F[pb + 1][row].  Rebuilt from
+// the K8 blocks at the start of every phase whose streaming pipeline gathers this side (the rows were all rewritten by the
+// previous phase): one streaming pass, ~0.1 ms for the Netflix-shaped user side, saved many times over by the pipeline.
+__global__ void __launch_bounds__(256)
+pair_pack_kernel(const float* __restrict__ F, float* __restrict__ F2, uint32_t ns, uint32_t npairs)
+{
+    const uint64_t total = (uint64_t)npairs * ns;
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
+        const f8 lo = ld256(F + t * 8);                        // (pb, row) -> F[pb][row]
+        const f8 hi = ld256(F + (t + ns) * 8);                 //           -> F[pb + 1][row]
+        st256(F2 + t * 16, lo);
+        st256(F2 + t * 16 + 8, hi);
+    }
+}
+
 // ========================================================================================================
 // launch wrappers
 void init_constant_tables()
@@ -1270,6 +1362,7 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         }
     }
     a.Fother = other.F;
+    a.F2other = other.F2;
     a.ns_self = self.n + 1;
     a.ns_other = other.n + 1;
     a.bias = self.bias;
@@ -1293,7 +1386,14 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     cudaStream_t sr = m.s_main, sh = m.s_aux;
     cudaStream_t sb[3] = {m.s_main, m.s_res[0], m.s_res[1]};
     cudaEventRecord(m.ev_fork, sr);
-    if (heavy) cudaStreamWaitEvent(sh, m.ev_fork, 0);
+    if (heavy) {
+        cudaStreamWaitEvent(sh, m.ev_fork, 0);
+        if (other.F2 && m.opt.pair_gather && KB > 1) {   // the other side's rows are final for this phase: lay its block pairs side by side
+            const uint64_t total = (uint64_t)(KB - 1) * (other.n + 1);
+            SBMF_LAUNCH((pair_pack_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, sh, other.F, other.F2, other.n + 1, (uint32_t)(KB - 1));
+            m.launches++;
+        }
+    }
     cudaStreamWaitEvent(sb[1], m.ev_fork, 0);
     cudaStreamWaitEvent(sb[2], m.ev_fork, 0);
     // resident rows: several blocks per launch (e, idx and the row set-up are then touched once per launch, not once per
@@ -1330,28 +1430,20 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     cudaStreamWaitEvent(sr, m.ev_join_res[1], 0);
     if (heavy) {
         const uint32_t ns = self.n_slices, nh = self.n_heavy;
-        const uint32_t gs = nh;   // one CTA per heavy row
         float* hbias = self.hdelta + (size_t)nh * 8;
-    // 2 ratings per thread x 64 threads per slice CTA measured best on B200 (profiles/): small CTAs, ~20 warps per SM
+    // 2 ratings per thread x 64 threads per slice CTA measured best on B200 (profiles/): small CTAs, ~20 warps per SM.
+    // The row updates (heavy_row_solve) run in the tail of each pass, by the last slice CTA of the row: one launch per step.
 #define HEAVY_ACC(PREV, CUR, PB, B)                                                                                                              \
     do {                                                                                                                                         \
-        if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, PB, B);  \
-        else SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, false>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, PB, B);         \
-    } while (0)
-        const bool wide_solve = ns >= 8u * nh;   // >= 8 slices per heavy row on average
-#define HEAVY_SOLVE(CUR, B)                                                                                                                       \
-    do {                                                                                                                                         \
-        if (wide_solve) SBMF_LAUNCH((heavy_solve_kernel<CUR, 8>), gs, 256, 0, sh, a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, B); \
-        else SBMF_LAUNCH((heavy_solve_kernel<CUR, 2>), gs, 64, 0, sh, a, self.heavy_rows, self.heavy_slice_ptr, nh, self.hpart, self.hdelta, hbias, B);   \
+        if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, self.hcount, PB, B);  \
+        else SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, false>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, self.hcount, PB, B);         \
     } while (0)
         if (with_bias) {
             HEAVY_ACC(0, 1, 0, 0);
-            HEAVY_SOLVE(1, 0);
             HEAVY_ACC(1, 2, 0, 0);
         } else {
             HEAVY_ACC(0, 2, 0, 0);
         }
-        HEAVY_SOLVE(2, 0);
         const bool detail = m.timing_detail && !apply_shift;   // item phase only
         if (detail && m.ev_top.size() < (size_t)2 * KB) {
             while (m.ev_top.size() < (size_t)2 * KB) {
@@ -1361,16 +1453,17 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
             }
         }
         if (detail) m.ev_top_used = 0;
+        const bool pair = other.F2 != nullptr && m.opt.pair_gather;
         for (int b = 1; b < KB; ++b) {
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
-            HEAVY_ACC(2, 2, b - 1, b);
+            if (!pair) HEAVY_ACC(2, 2, b - 1, b);
+            else if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<2, 2, 2, 64, true, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, self.hcount, b - 1, b);
+            else SBMF_LAUNCH((heavy_accumulate_kernel<2, 2, 2, 64, false, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, self.hcount, b - 1, b);
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
-            HEAVY_SOLVE(2, b);
         }
         HEAVY_ACC(2, 0, KB - 1, 0);
 #undef HEAVY_ACC
-#undef HEAVY_SOLVE
-        m.launches += 2 * KB + 3;
+        m.launches += KB + 1 + (with_bias ? 1 : 0);
         cudaEventRecord(m.ev_join, sh);
         cudaStreamWaitEvent(sr, m.ev_join, 0);
     }

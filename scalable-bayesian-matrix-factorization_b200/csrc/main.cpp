@@ -23,6 +23,7 @@
 //       -burn_in n, -rebuild_every n, -device n, -item_offset n|auto (libFM text/binary: item feature id - offset = item id),
 //       -dump_triples F (write the parsed train triples), -dry_run 1 (parse, print the header lines, stop before touching a GPU),
 //       -save_state F / -load_state F (checkpoint after the last sweep / continue a chain: sbmf_cuda_set_state, csrc/checkpoint.cpp),
+//       -timing F (stage seconds of the job as JSON: parse / create / build / init / sweeps / out),
 //       -dump_xt F (the transposed design matrix of the training data in libFM's binary format, as tools/transpose writes it)
 #include <math.h>
 #include <stdint.h>
@@ -241,6 +242,7 @@ int main(int argc, char** argv)
         const std::string p_load = cmd.reg("load_state", "continue the chain from this checkpoint instead of initialising; -iter = number of further sweeps");
         const std::string p_xt = cmd.reg("dump_xt", "write the transposed design matrix of the training data (libFM binary .xt, as tools/transpose writes it) from the device-built layout");
         const std::string p_dry = cmd.reg("dry_run", "1 = parse the inputs, print the header lines and stop (no GPU needed)");
+        const std::string p_timing = cmd.reg("timing", "write the wall-clock seconds of the job's stages (parse, create, build, init, sweeps, out) to this file as one JSON object");
         // general FM Gibbs (-method fm_mcmc | fm_als, csrc/fm_main.h): libFM's own flags for -method mcmc / als
         cmd.reg("meta", "fm_mcmc / fm_als: filename with the group id of every attribute, one per line");
         cmd.reg("regular", "fm_mcmc / fm_als: 'r' or 'r0,r1,r2' = prior precision of w0, start value of the w / v group precisions");
@@ -267,6 +269,9 @@ int main(int argc, char** argv)
         const std::string train_file = cmd.get(p_train, "../../data/ra.train_sbpmf");
         const std::string test_file = cmd.get(p_test, "../../data/ra.test_sbpmf");
 
+        const auto t_job = std::chrono::steady_clock::now();
+        auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
+        double s_parse = 0.0, s_create = 0.0, s_build = 0.0, s_init = 0.0, s_sweeps = 0.0, s_out = 0.0;
         Ratings tr, te;
         bool libfm_tr = false, libfm_te = false;
         long off = 0;
@@ -289,6 +294,7 @@ int main(int argc, char** argv)
                 if (!te.item.empty()) te.item_max -= (uint32_t)off;
             }
         }
+        s_parse = since(t_job);
         const uint32_t user_max = tr.user_max > te.user_max ? tr.user_max : te.user_max;   // [T]:45-52, 112-119
         const uint32_t item_max = tr.item_max > te.item_max ? tr.item_max : te.item_max;
         const uint32_t num_users = user_max + 1, num_items = item_max + 1;                  // [T]:151-153
@@ -319,9 +325,13 @@ int main(int argc, char** argv)
         cfg.sample_mode = cmd.geti(p_samp, 1) == 0 ? SBMF_SAMPLE_ZERO_NOISE : (sdm == "sqrt" ? SBMF_SAMPLE_SQRT : SBMF_SAMPLE_REF_VAR_AS_STDEV);
 
         sbmf_handle* h = NULL;
+        auto t_stage = std::chrono::steady_clock::now();
         if (sbmf_cuda_create(&cfg, &h) != SBMF_OK) throw std::string("sbmf_cuda_create: ") + sbmf_cuda_last_error(NULL);
+        s_create = since(t_stage);
+        t_stage = std::chrono::steady_clock::now();
         ck(sbmf_cuda_set_train(h, tr.user.size(), tr.user.data(), tr.item.data(), tr.rating.data(), num_users, num_items), h, "set_train");
         ck(sbmf_cuda_set_test(h, te.user.size(), te.user.data(), te.item.data(), te.rating.data()), h, "set_test");
+        s_build = since(t_stage);
         if (cmd.has(p_xt)) {
             // the device storage build IS the transpose: CSR rows = user features, CSC rows = item features (csrc/xt_writer.cpp).
             // Item features are numbered after the users: at the offset of the libFM input, else at num_users like
@@ -350,6 +360,7 @@ int main(int argc, char** argv)
             st.mu_u = cmu.data(); st.sigma_v = csv.data(); st.mu_v = cmv.data(); st.E = cE.data();
         };
         uint32_t first_iter = 0;
+        t_stage = std::chrono::steady_clock::now();
         if (cmd.has(p_load)) {
             const std::string path = cmd.get(p_load, "");
             sbmf_checkpoint_dims cd;
@@ -377,6 +388,7 @@ int main(int argc, char** argv)
             ck(sbmf_cuda_init_factors(h, NULL, NULL), h, "init_factors");
         }
         ck(sbmf_cuda_set_timing_enabled(h, 0), h, "set_timing_enabled");
+        s_init = since(t_stage);
 
         std::ofstream rlog;
         if (cmd.has(p_rlog) && !cmd.get(p_rlog, "").empty()) {
@@ -392,6 +404,7 @@ int main(int argc, char** argv)
             if (!file_rmse.is_open()) throw std::string("unable to open test_rmse_*_mcmc in the current directory");
         }
         const int verbosity = (int)cmd.geti(p_verb, 0);
+        t_stage = std::chrono::steady_clock::now();
         for (uint32_t iter = first_iter; iter < first_iter + T; ++iter) {
             const auto t0 = std::chrono::steady_clock::now();
             double rmse = 0.0, rmse_sweep = 0.0;
@@ -416,12 +429,22 @@ int main(int argc, char** argv)
                 if (verbosity > 0) std::cout << "alpha=" << st.alpha << "\tb_0=" << st.b_0 << "\ttime=" << dt << std::endl;
             }
         }
+        s_sweeps = since(t_stage);
+        t_stage = std::chrono::steady_clock::now();
         if (cmd.has(p_out)) {
             std::vector<float> pred(te.user.size());
             if (first_iter + T > cfg.burn_in) ck(sbmf_cuda_get_pred(h, pred.data()), h, "get_pred");
             std::ofstream o(cmd.get(p_out, "").c_str());
             if (!o.is_open()) throw "unable to open " + cmd.get(p_out, "");
             for (float v : pred) o << (double)v << "\n";   // the bytes of DVector::save (matrix.h:268-277), without its flush per line
+        }
+        s_out = since(t_stage);
+        if (cmd.has(p_timing)) {
+            std::ofstream o(cmd.get(p_timing, "").c_str());
+            if (!o.is_open()) throw "unable to open " + cmd.get(p_timing, "");
+            o << "{\"parse_s\": " << s_parse << ", \"create_s\": " << s_create << ", \"build_s\": " << s_build << ", \"init_s\": " << s_init
+              << ", \"sweeps_s\": " << s_sweeps << ", \"out_s\": " << s_out << ", \"total_s\": " << since(t_job) << ", \"sweeps\": " << T
+              << ", \"n_train\": " << tr.user.size() << ", \"n_test\": " << te.user.size() << ", \"K\": " << K << "}\n";
         }
         if (cmd.has(p_save)) {
             sbmf_state st;

@@ -55,6 +55,7 @@ struct Side {
     uint32_t* idx = nullptr;          // [N] opposite-side id of each slot
     float* e = nullptr;               // [N] residual e_ij in this side's slot order
     float* F = nullptr;               // [KB][n][8]  K8-blocked factors (own rows; gather target of the other side)
+    float* F2 = nullptr;              // [KB-1][n+1][16] block pairs (pb, pb+1) side by side, rebuilt per phase; only if the OTHER side streams rows
     float *bias = nullptr, *mu_b = nullptr, *sigma_b = nullptr;   // [n]
     double *sigma_k = nullptr, *mu_k = nullptr;                   // [KP] hyper-parameters (fp64 masters)
     double* post_var = nullptr;                                   // [KP] posterior variance of mu_k (Normal-Gamma modes, [S]:391/411)
@@ -69,6 +70,7 @@ struct Side {
     uint32_t* heavy_slice_ptr = nullptr;  // [n_heavy+1] slice range of each heavy row
     Slice* slices = nullptr;              // [n_slices]
     float* hpart = nullptr;               // [n_slices][NACC]
+    uint32_t* hcount = nullptr;           // [n_heavy] tickets of the slice CTAs of a row in the current pass (0 between launches)
     float* hdelta = nullptr;              // [n_heavy][8] pending factor deltas of the block just solved, then [n_heavy] bias deltas
     uint64_t nnz_resident = 0, nnz_heavy = 0;
     uint32_t site_f = 0, site_b = 0;      // Philox streams of the factor / bias draws
@@ -82,9 +84,11 @@ struct Side {
 struct Options {
     int64_t l2_budget_mb = 192;   // resident bins: bytes of gathered factor blocks one launch keeps in flight (launch_phase)
     int64_t max_blocks_per_launch = 0;   // resident bins: cap on the factor blocks one launch processes (0 = only the L2 budget)
-    int64_t resident_max = RESIDENT_MAX;   // rows longer than this stream through the sliced pipeline (<= RESIDENT_MAX)
+    int64_t resident_max = RESIDENT_MAX;   // rows longer than this stream through the sliced pipeline (<= RESIDENT_MAX); sets both sides
+    int64_t resident_max_user = RESIDENT_MAX, resident_max_item = RESIDENT_MAX;   // ... per side
     int64_t slice_len = 0;        // heavy-row slice length; 0 = chosen from the shard size (build_worklists)
     int64_t group_rows = 1;       // short rows: several rows per warp (row_group_kernel); 0 = one warp per row
+    int64_t pair_gather = 1;      // streaming pipeline: gather (previous, current) block as one 64-byte row by lane pairs (0: two sector gathers)
     int64_t fold_user = 1;        // one GPU: CSC->CSR residual hand-over folded into the user phase's first touch
     int64_t fold_item = 0;        // one GPU: CSR->CSC hand-over folded into the item phase's first touch
     int64_t graph = 1;            // replay the steady-state sweep from a CUDA graph when per-phase timing is off

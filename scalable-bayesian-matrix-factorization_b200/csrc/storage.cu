@@ -120,11 +120,11 @@ static int bits_for(uint32_t n)
 
 static void free_side(Side& s)
 {
-    cudaFree(s.ptr); cudaFree(s.idx); cudaFree(s.e); cudaFree(s.F);
+    cudaFree(s.ptr); cudaFree(s.idx); cudaFree(s.e); cudaFree(s.F); cudaFree(s.F2);
     cudaFree(s.bias); cudaFree(s.mu_b); cudaFree(s.sigma_b);
     cudaFree(s.sigma_k); cudaFree(s.mu_k); cudaFree(s.post_var); cudaFree(s.sigma_kf); cudaFree(s.mu_kf); cudaFree(s.hyp_part);
     for (int b = 0; b < NBINS; ++b) cudaFree(s.bin_rows[b]);
-    cudaFree(s.heavy_rows); cudaFree(s.heavy_slice_ptr); cudaFree(s.slices); cudaFree(s.hpart); cudaFree(s.hdelta);
+    cudaFree(s.heavy_rows); cudaFree(s.heavy_slice_ptr); cudaFree(s.slices); cudaFree(s.hpart); cudaFree(s.hdelta); cudaFree(s.hcount);
     const uint32_t sf = s.site_f, sb = s.site_b, a = s.site_sigma_k, b_ = s.site_mu_k, c = s.site_sigma_b, d = s.site_mu_b;
     const int pr = s.prior, prb = s.prior_b;
     s = Side();
@@ -291,7 +291,7 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
     hsp.push_back(0);
     // slice length: at most SLICE_LEN, but short enough that one streaming launch is >= ~8 waves of CTAs on this GPU
     // (a multi-GPU shard or a thin heavy tail would otherwise run 2-3 ragged waves per launch)
-    const int64_t resident_max = m.opt.resident_max;   // option (<= RESIDENT_MAX)
+    const int64_t resident_max = (&s == &m.us) ? m.opt.resident_max_user : m.opt.resident_max_item;   // options (<= RESIDENT_MAX)
     uint64_t nnz_heavy_total = 0;
     for (uint32_t r = row0; r < row1; ++r) {
         const int64_t c = ptr[r + 1] - ptr[r];
@@ -333,6 +333,8 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
     CK(dmalloc(&s.slices, slices.size()));
     CK(dmalloc(&s.hpart, slices.size() * NACC));
     CK(dmalloc(&s.hdelta, heavy.size() * 9));   // [n_heavy][8] block deltas + [n_heavy] bias deltas
+    CK(dmalloc(&s.hcount, heavy.size()));
+    CK(cudaMemset(s.hcount, 0, (heavy.size() ? heavy.size() : 1) * 4));
     if (!heavy.empty()) {
         CK(cudaMemcpy(s.heavy_rows, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(s.slices, slices.data(), slices.size() * sizeof(Slice), cudaMemcpyHostToDevice));
@@ -619,9 +621,11 @@ static int shard_storage(Model& m)
     return SBMF_OK;
 }
 
-static int alloc_side_state(Model& m, Side& s)
+static int alloc_side_state(Model& m, Side& s, const Side& other)
 {
     CK(dmalloc(&s.F, (size_t)m.KB * (s.n + 1) * 8));   // + the all-zero pad row
+    // block pairs for the other side's streaming pipeline (kernels.cu: pair_pack_kernel); only where that pipeline has rows
+    if (other.n_heavy > 0 && m.KB > 1) CK(dmalloc(&s.F2, (size_t)(m.KB - 1) * (s.n + 1) * 16));
     CK(dmalloc(&s.bias, s.n)); CK(dmalloc(&s.mu_b, s.n)); CK(dmalloc(&s.sigma_b, s.n));
     CK(dmalloc(&s.sigma_k, m.KP)); CK(dmalloc(&s.mu_k, m.KP)); CK(dmalloc(&s.post_var, m.KP)); CK(dmalloc(&s.sigma_kf, m.KP)); CK(dmalloc(&s.mu_kf, m.KP));
     s.hyp_chunks = (s.n + 16383) / 16384;
@@ -735,8 +739,8 @@ int build_storage(Model& m, uint64_t n, const uint32_t* user, const uint32_t* it
     if ((rc = build_worklists(m, m.us, m.ub[m.rank], m.ub[m.rank + 1])) != SBMF_OK) return rc;
     if ((rc = build_worklists(m, m.it, m.ib[m.rank], m.ib[m.rank + 1])) != SBMF_OK) return rc;
     tr.lap("shard + work lists");
-    if ((rc = alloc_side_state(m, m.us)) != SBMF_OK) return rc;
-    if ((rc = alloc_side_state(m, m.it)) != SBMF_OK) return rc;
+    if ((rc = alloc_side_state(m, m.us, m.it)) != SBMF_OK) return rc;
+    if ((rc = alloc_side_state(m, m.it, m.us)) != SBMF_OK) return rc;
     m.red_blocks = (uint32_t)m.sm_count * 8;
     CK(dmalloc(&m.red_part, (size_t)m.red_blocks * 2));
     CK(dmalloc(&m.red2, 2));

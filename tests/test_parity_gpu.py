@@ -520,6 +520,7 @@ OPTION_SETS = [
     {"resident_max": 64, "slice_len": 256},             # most rows through the sliced streaming pipeline, many slices per row
     {"resident_max": 300, "slice_len": 1024, "max_blocks_per_launch": 1, "fold_item": 1},
     {"graph": 0},
+    {"pair_gather": 0, "resident_max": 128},            # streamed rows gather previous / current block as two sectors instead of one 64-byte row
 ]
 
 

@@ -290,6 +290,8 @@ inline T __shfl_sync(unsigned, T v, int src_lane, int width = 32)
 }
 template <class T>
 inline T __ldg(const T* p) { return *p; }
+template <class T>
+inline T __ldcg(const T* p) { return *(const volatile T*)p; }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline uint32_t atomicMin(uint32_t* a, uint32_t v)

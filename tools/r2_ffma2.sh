@@ -24,10 +24,11 @@ m = sbmf.SbmfModel(K=100, seed=5)
 m.set_train(d["train_user"], d["train_item"], d["train_rating"], 71567, 10681); m.set_test(d["test_user"], d["test_item"], d["test_rating"])
 m.init_factors(); m.sweep(4)
 st = m.get_state(with_E=False); r, _ = m.rmse_history(0, 4)
-np.savez(f"gpurun_out/ffma2_chain_{lvl}.npz", U=st["U"], V=st["V"], b_i=st["b_i"], b_j=st["b_j"], r=r)
+import hashlib
+np.savez(f"gpurun_out/ffma2_chain_{lvl}.npz", r=r, **{k: np.frombuffer(hashlib.sha256(np.ascontiguousarray(st[k]).tobytes()).digest(), np.uint8) for k in ("U", "V", "b_i", "b_j")})
 print("FFMA2 =", lvl, "rmse", r)
 PY
-  python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/ffma2_bench_$lvl.json 2> $O/ffma2_bench_$lvl.err
+  python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-full-point --no-cli > $O/ffma2_bench_$lvl.json 2> $O/ffma2_bench_$lvl.err
 done
 python - <<'PY'
 import json, numpy as np
