@@ -429,13 +429,110 @@ def e2e_cli(workload, steps, ref_load_s=None, ref_load_n=None):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# general FM Gibbs (csrc/fm.cu behind include/sbmf_fm_cuda.h): libFM's -method mcmc on a design matrix
+FM_WORKLOADS = {
+    # name: (users, items, train ratings, K, dense real-valued context attributes per case)
+    "fm_mf_ml10m": (71567, 10681, 10000000, 8, 0),      # matrix factorisation as an FM: one-hot user + one-hot item
+    "fm_wide_ml1m": (6040, 3706, 1000209, 8, 4),        # ... plus 4 dense attributes (every column of them has one entry per case)
+}
+
+
+def fm_bench(a):
+    """python bench.py --workload fm_mf_ml10m | fm_wide_ml1m [--impl reference]: iterations/s of libFM's MCMC learner
+    (fm_learn_mcmc.h:411-623, 780-835).  Ours: sbmf_fm_learn on one B200.  Reference: the unmodified libFM built from
+    /root/reference (oracle/_ref/libFM -method mcmc) on the same files, one thread; per-iteration time = (wall(iter=3) - wall(iter=1)) / 2."""
+    I, J, NTRAIN, K, W = FM_WORKLOADS[a.workload]
+    n = int(round(NTRAIN / (1 - TEST_FRAC)))
+    cfg = {"workload": f"{a.workload}: synthetic MovieLens-shaped ratings {I}x{J}, ~{NTRAIN} train cases, cast as a factorization machine "
+                       f"(one-hot user + one-hot item{' + %d dense real-valued attributes' % W if W else ''}), K={K}, libFM -method mcmc -task r",
+           "users": I, "items": J, "K": K, "dense_attributes": W, "parallelism": "1 GPU"}
+    metric, unit = "fm_gibbs_iterations_per_s", "iterations/s"
+    with tempfile.TemporaryDirectory(prefix="sbmf_fm_") as tmp:
+        tr, te = os.path.join(tmp, "fm.train"), os.path.join(tmp, "fm.test")
+        subprocess.run([os.path.join(PKG, "bin", "sbmf_synth"), "-users", str(I), "-items", str(J), "-ratings", str(n), "-seed", str(SEED), "-test_frac", str(TEST_FRAC),
+                        "-libfm_text", "1", "-train", tr, "-test", te], capture_output=True, text=True, check=True)
+
+        def dense(nrows, seed):
+            rs = np.random.RandomState(seed)
+            return (np.round(rs.standard_normal((nrows, W)) * 8) / 8).astype(np.float32)
+
+        if W:   # append the dense attributes to every line (ids after users and items); 1M-line files: plain Python is fine
+            for path, seed in ((tr, 1), (te, 2)):
+                lines = open(path).read().splitlines()
+                x = dense(len(lines), seed)
+                with open(path, "w") as f:
+                    for ln, row in zip(lines, x):
+                        f.write(ln + "".join(f" {I + J + k}:{row[k]:g}" for k in range(W)) + "\n")
+        if a.impl == "reference":
+            exe = os.path.join(ROOT, "oracle", "_ref", "libFM")
+            if not os.path.exists(exe):
+                emit({"impl": "reference", "unavailable": "oracle/_ref/libFM not built (needs /root/reference at build time)"})
+                return
+            walls = {}
+            for it in (1, 3):
+                t0 = time.perf_counter()
+                r = subprocess.run([exe, "-task", "r", "-train", tr, "-test", te, "-dim", f"1,1,{K}", "-iter", str(it), "-method", "mcmc", "-init_stdev", "0.1"],
+                                   capture_output=True, text=True, cwd=tmp, env=dict(os.environ, OMP_NUM_THREADS="1"))
+                walls[it] = time.perf_counter() - t0
+                if r.returncode != 0:
+                    emit({"impl": "reference", "unavailable": "libFM failed: " + (r.stderr or r.stdout)[-200:]})
+                    return
+            per = (walls[3] - walls[1]) / 2
+            rm = [float(x.split("Test=")[1]) for x in r.stdout.splitlines() if x.startswith("#Iter")]
+            cb = {"value": 1 / per, "unit": unit, "cores": 1, "kind": "reference", "sample": "the whole workload; unmodified libFM 1.4.2 of the reference (src/libfm/libfm.cpp, g++ -O3), -method mcmc",
+                  "s_per_iteration": per, "load_s": walls[1] - per, "test_rmse": rm}
+            emit({"impl": "reference", "metric": metric, "value": 1 / per, "unit": unit, "n_gpus": 1, "steps": 2, "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True,
+                  "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
+                  "e2e": {"value": 1 / per, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+            return
+        import sbmf
+        d = sbmf.synth_generate_host(I, J, n, test_frac=TEST_FRAC, seed=SEED)   # the matrix bin/sbmf_synth wrote (same generator, same seed)
+
+        def fm(u, i, r, seed):
+            nr = u.size
+            cols = [u.astype(np.uint32), (I + i).astype(np.uint32)] + [np.full(nr, I + J + k, dtype=np.uint32) for k in range(W)]
+            x = dense(nr, seed) if W else None
+            vals = [np.ones(nr, np.float32), np.ones(nr, np.float32)] + [x[:, k] for k in range(W)]
+            return {"row_ptr": ((2 + W) * np.arange(nr + 1)).astype(np.int64), "attr": np.stack(cols, axis=1).reshape(-1), "x": np.stack(vals, axis=1).reshape(-1),
+                    "y": r.astype(np.float32)}
+        mtr, mte = fm(d["train_user"], d["train_item"], d["train_rating"], 1), fm(d["test_user"], d["test_item"], d["test_rating"], 2)
+        p = I + J + W + 1     # libFM counts one attribute beyond the largest id it reads (libfm.cpp:326)
+        group = np.zeros(p, np.uint32)
+        m = sbmf.FmModel(p, K, attr_group=group, seed=1)
+        t0 = time.perf_counter()
+        m.set_train(mtr); m.set_test(mte); m.init()
+        setup_s = time.perf_counter() - t0
+        Wm = max(a.warmup, 3)
+        m.learn(Wm); m.rmse_history(0, Wm)
+        with ClockSampler(0) as cs:
+            t0 = time.perf_counter()
+            m.learn(a.steps)
+            r = m.rmse_history(Wm, a.steps)          # synchronises
+            dt = (time.perf_counter() - t0) / a.steps
+        nnz = int(mtr["row_ptr"][-1])
+        alg = nnz * (16.0 + K * 24.0 + K * 4.0 + 8.0 + 4.0 * K)   # DESIGN.md 11: w draw, v draws, q rebuild, re-prediction per entry and iteration
+        peak, peak_src = peaks()
+        roof = {"kernel": "fm_col_* / fm_predict_* (column passes of one iteration)", "bound": "hbm", "achieved": alg / dt / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg / dt / 1e9 / peak, "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_iteration": alg,
+                "note": "whole-iteration figure (wall clock around sbmf_fm_learn + history read-back): 16 B per entry for the w draw, 24 B per entry and factor for "
+                        "the v draws, 4 B per entry and factor for the q rebuild, 8 + 4K B per entry for libFM's full re-prediction"}
+        emit({"metric": metric, "value": 1 / dt, "unit": unit, "n_gpus": 1, "steps": a.steps, "warmup": Wm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "f32 (column sums f64)", "data": "synthetic", "config": cfg, "clocks": cs.summary(), "roofline": roof,
+              "run": {"cases": int(mtr["y"].size), "nnz": nnz, "attributes": p, "runs": int(m.get_runs().size - 1), "setup_s": round(setup_s, 3)},
+              "test_rmse": [round(float(x), 5) for x in r[1]], "gpu_launches": None,
+              "e2e": {"value": a.steps / (a.steps * dt + setup_s), "unit": unit, "h2d_bytes_per_step": (12.0 * nnz + 4.0 * mtr["y"].size) / a.steps, "d2h_bytes_per_step": 16.0,
+                      "what": "set_train + set_test + init (H2D of the design matrix, device transpose) + the timed iterations"}})
+        m.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="netflix_k100", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="netflix_k100", choices=sorted(WORKLOADS) + sorted(FM_WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=2000000, help="train ratings in the CPU baseline's sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -447,6 +544,10 @@ def main():
     rank, local_rank, world = dist_env()
     if world != a.gpus and world != 1:
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    if a.workload in FM_WORKLOADS:     # the general FM Gibbs path: one GPU (cases shard naturally; replicas only)
+        if rank == 0:
+            fm_bench(a)
+        return
     I, J, NTRAIN, K = WORKLOADS[a.workload]
     W = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

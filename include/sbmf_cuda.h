@@ -146,7 +146,9 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
      resident_max_user / resident_max_item  the same threshold per side (resident_max sets both)  [before set_train]
      slice_len     (0)    ratings per slice of a streamed row; 0 = chosen from the shard size  [before set_train]
      group_rows    (1)    short rows share a warp (0: one warp per row)
-     pair_gather   (1)    streamed rows gather (previous, current) factor block as one 64-byte row by lane pairs (0: two gathers)
+     pair_gather   (0)    streamed rows gather (previous, current) factor block as one 64-byte row by lane pairs from a per-phase
+                          pair array instead of two sector gathers (measured slower on sorted rating rows)   [before set_train]
+     fuse_solve    (1)    streamed rows: the row updates run in the tail of each pass (0: a launch of their own)
      fold_user / fold_item (1 / 0)  one GPU: residual hand-over between the slot orders folded into the phase's first touch
      graph         (1)    steady-state sweep replayed from a CUDA graph when per-phase timing is off
      device_plan   (1)    multi-GPU: exchange plan computed on the device (0: host planner)  [before set_train]

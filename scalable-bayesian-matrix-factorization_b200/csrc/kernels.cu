@@ -660,6 +660,30 @@ __device__ __forceinline__ void heavy_row_solve(const PhaseArgs& a, uint32_t hro
     }
 }
 
+// one ticket per slice CTA: fetch-and-add with release semantics at GPU scope (MEMBAR.ALL.GPU + ATOMG by the calling thread only)
+__device__ __forceinline__ uint32_t ticket_release(uint32_t* counter)
+{
+#ifdef SBMF_SIMT_EMU
+    __threadfence();
+    return atomicAdd(counter, 1u);
+#else
+    uint32_t t;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
+    return t;
+#endif
+}
+
+// The row updates as a launch of their own, one CTA per streamed row (option fuse_solve = 0: A/B against the fused tail).
+template <int CUR, int NW>
+__global__ void __launch_bounds__(NW * 32)
+heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ slice_ptr, const float* __restrict__ hpart, float* __restrict__ hdelta,
+                   float* __restrict__ hbias_delta, int b)
+{
+    __shared__ __align__(16) float s_part[NW][NACC];
+    __shared__ __align__(16) float s_tot[NACC];
+    heavy_row_solve<CUR, NW>(a, blockIdx.x, slice_ptr[blockIdx.x], slice_ptr[blockIdx.x + 1], hpart, hdelta, hbias_delta, b, s_part, s_tot);
+}
+
 // PAIR (PREV == 2 and CUR == 2 only): the factor rows come from the pair array F2other.  Lanes (2k, 2k+1) fetch the 64-byte row
 // of the even lane's rating with one 256-bit load each (lower half = block pb to the even lane, upper half = block b to the odd
 // lane), then the row of the odd lane's rating with the halves swapped.  Every lane thus holds the previous block of its OWN
@@ -833,21 +857,23 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, float* __
             hpart[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
         }
     }
-    if (CUR != 0) {
+    if (CUR != 0 && hcount != nullptr) {   // hcount == nullptr: the updates run as a launch of their own (heavy_solve_kernel)
         // The row's update runs in the tail of this launch: every slice CTA publishes its partial, takes a ticket, and the CTA
         // that draws the last ticket of its row combines the partials (in slice order) and solves.  All CTAs of the row have
         // read the pending delta / bias delta of the previous step before they take a ticket, so the solve may overwrite them.
-        __threadfence();
+        // The ticket is a RELEASE atomic of thread 0 after the barrier (cumulative: it orders the partial stores of the whole CTA).
+        // Not __threadfence() by every thread: on sm_100 that is MEMBAR.SC + CCTL.IVALL, i.e. every finishing CTA would also
+        // invalidate its SM's L1 under the gathers of the CTAs still running (measured: 806 -> 902 us per pass).
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint32_t n_row = slice_ptr[sl.hrow + 1] - slice_ptr[sl.hrow];
-            const uint32_t ticket = atomicAdd(&hcount[sl.hrow], 1u);
+            const uint32_t ticket = ticket_release(&hcount[sl.hrow]);
             s_last = (ticket == n_row - 1) ? 1u : 0u;
             if (s_last) hcount[sl.hrow] = 0u;   // re-armed for the next pass (nobody else touches it before the next launch)
         }
         __syncthreads();
         if (s_last) {
-            __threadfence();
+            __threadfence();   // acquire side, once per row and pass; the partials are then read through L2 (__ldcg)
             heavy_row_solve<CUR, THREADS / 32>(a, sl.hrow, slice_ptr[sl.hrow], slice_ptr[sl.hrow + 1], hpart, hdelta, hbias_delta, b, s_part, s_tot);
         }
     }
@@ -1433,17 +1459,29 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         float* hbias = self.hdelta + (size_t)nh * 8;
     // 2 ratings per thread x 64 threads per slice CTA measured best on B200 (profiles/): small CTAs, ~20 warps per SM.
     // The row updates (heavy_row_solve) run in the tail of each pass, by the last slice CTA of the row: one launch per step.
+        const bool fuse = m.opt.fuse_solve != 0;
+        uint32_t* hc = fuse ? self.hcount : nullptr;
+        const bool wide_solve = ns >= 8u * nh;   // >= 8 slices per streamed row on average
 #define HEAVY_ACC(PREV, CUR, PB, B)                                                                                                              \
     do {                                                                                                                                         \
-        if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, self.hcount, PB, B);  \
-        else SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, false>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, self.hcount, PB, B);         \
+        if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, PB, B);  \
+        else SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, false>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, PB, B);         \
+    } while (0)
+#define HEAVY_SOLVE(CUR, B)                                                                                                                      \
+    do {                                                                                                                                         \
+        if (fuse) break;                                                                                                                         \
+        if (wide_solve) SBMF_LAUNCH((heavy_solve_kernel<CUR, 8>), nh, 256, 0, sh, a, self.heavy_slice_ptr, self.hpart, self.hdelta, hbias, B);   \
+        else SBMF_LAUNCH((heavy_solve_kernel<CUR, 2>), nh, 64, 0, sh, a, self.heavy_slice_ptr, self.hpart, self.hdelta, hbias, B);               \
+        m.launches++;                                                                                                                            \
     } while (0)
         if (with_bias) {
             HEAVY_ACC(0, 1, 0, 0);
+            HEAVY_SOLVE(1, 0);
             HEAVY_ACC(1, 2, 0, 0);
         } else {
             HEAVY_ACC(0, 2, 0, 0);
         }
+        HEAVY_SOLVE(2, 0);
         const bool detail = m.timing_detail && !apply_shift;   // item phase only
         if (detail && m.ev_top.size() < (size_t)2 * KB) {
             while (m.ev_top.size() < (size_t)2 * KB) {
@@ -1457,12 +1495,14 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         for (int b = 1; b < KB; ++b) {
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
             if (!pair) HEAVY_ACC(2, 2, b - 1, b);
-            else if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<2, 2, 2, 64, true, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, self.hcount, b - 1, b);
-            else SBMF_LAUNCH((heavy_accumulate_kernel<2, 2, 2, 64, false, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, self.hcount, b - 1, b);
+            else if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<2, 2, 2, 64, true, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, b - 1, b);
+            else SBMF_LAUNCH((heavy_accumulate_kernel<2, 2, 2, 64, false, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, b - 1, b);
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
+            HEAVY_SOLVE(2, b);
         }
         HEAVY_ACC(2, 0, KB - 1, 0);
 #undef HEAVY_ACC
+#undef HEAVY_SOLVE
         m.launches += KB + 1 + (with_bias ? 1 : 0);
         cudaEventRecord(m.ev_join, sh);
         cudaStreamWaitEvent(sr, m.ev_join, 0);

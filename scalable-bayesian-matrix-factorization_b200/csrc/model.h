@@ -88,7 +88,8 @@ struct Options {
     int64_t resident_max_user = RESIDENT_MAX, resident_max_item = RESIDENT_MAX;   // ... per side
     int64_t slice_len = 0;        // heavy-row slice length; 0 = chosen from the shard size (build_worklists)
     int64_t group_rows = 1;       // short rows: several rows per warp (row_group_kernel); 0 = one warp per row
-    int64_t pair_gather = 1;      // streaming pipeline: gather (previous, current) block as one 64-byte row by lane pairs (0: two sector gathers)
+    int64_t pair_gather = 0;      // streaming pipeline: gather (previous, current) block as one 64-byte row by lane pairs (0: two sector gathers)
+    int64_t fuse_solve = 1;       // streaming pipeline: row updates in the tail of each pass (0: a launch of their own)
     int64_t fold_user = 1;        // one GPU: CSC->CSR residual hand-over folded into the user phase's first touch
     int64_t fold_item = 0;        // one GPU: CSR->CSC hand-over folded into the item phase's first touch
     int64_t graph = 1;            // replay the steady-state sweep from a CUDA graph when per-phase timing is off

@@ -625,7 +625,7 @@ static int alloc_side_state(Model& m, Side& s, const Side& other)
 {
     CK(dmalloc(&s.F, (size_t)m.KB * (s.n + 1) * 8));   // + the all-zero pad row
     // block pairs for the other side's streaming pipeline (kernels.cu: pair_pack_kernel); only where that pipeline has rows
-    if (other.n_heavy > 0 && m.KB > 1) CK(dmalloc(&s.F2, (size_t)(m.KB - 1) * (s.n + 1) * 16));
+    if (other.n_heavy > 0 && m.KB > 1 && m.opt.pair_gather) CK(dmalloc(&s.F2, (size_t)(m.KB - 1) * (s.n + 1) * 16));
     CK(dmalloc(&s.bias, s.n)); CK(dmalloc(&s.mu_b, s.n)); CK(dmalloc(&s.sigma_b, s.n));
     CK(dmalloc(&s.sigma_k, m.KP)); CK(dmalloc(&s.mu_k, m.KP)); CK(dmalloc(&s.post_var, m.KP)); CK(dmalloc(&s.sigma_kf, m.KP)); CK(dmalloc(&s.mu_kf, m.KP));
     s.hyp_chunks = (s.n + 16383) / 16384;

@@ -5,6 +5,7 @@
 //
 //   sbmf_synth -users I -items J -ratings N [-test_frac 0.1] [-seed S] [-s_user 0.8] [-s_item 1.0] [-threads T]
 //              [-binary 1]      write libFM's binary format (FILE.x + FILE.y, rows `rating user:1 (I+item):1`) instead of triples
+//              [-libfm_text 1]  write libFM's text format `rating user:1 (I+item):1` instead of triples
 //              [-max_train M]   keep only the first whole users holding about M train ratings (a bounded sample; 0 = all)
 //              -train FILE -test FILE
 // The last test line pins the id space (num_users = 1 + max user, num_items = J) as the reference sizes its arrays by the
@@ -22,6 +23,7 @@
 #include "../../include/sbmf_cuda.h"
 
 // `%u\t%u\t%g\n` per rating, formatted by hand (ratings are half stars: "3" or "3.5") on all host threads, written in order
+static uint32_t g_libfm_item_offset = 0;   // > 0: write libFM text `rating user:1 (offset + item):1` instead of triples
 static inline char* put_uint(char* p, uint32_t v)
 {
     char tmp[10];
@@ -52,17 +54,29 @@ static void write_triples(const char* path, const uint32_t* u, const uint32_t* i
                 o.resize((e - b) * 40);
                 char* p = &o[0];
                 for (uint64_t k = b; k < e; ++k) {
-                    p = put_uint(p, u[k]);
-                    *p++ = '\t';
-                    p = put_uint(p, i[k]);
-                    *p++ = '\t';
-                    const float x2 = r[k] * 2.0f;
-                    const int h = (int)x2;
-                    if (r[k] >= 0.f && (float)h == x2 && h < 2000000000) {
-                        p = put_uint(p, (uint32_t)(h >> 1));
-                        if (h & 1) { *p++ = '.'; *p++ = '5'; }
+                    auto put_rating = [&]() {
+                        const float x2 = r[k] * 2.0f;
+                        const int h = (int)x2;
+                        if (r[k] >= 0.f && (float)h == x2 && h < 2000000000) {
+                            p = put_uint(p, (uint32_t)(h >> 1));
+                            if (h & 1) { *p++ = '.'; *p++ = '5'; }
+                        } else {
+                            p += snprintf(p, 32, "%g", (double)r[k]);
+                        }
+                    };
+                    if (g_libfm_item_offset) {
+                        put_rating();
+                        *p++ = ' ';
+                        p = put_uint(p, u[k]);
+                        *p++ = ':'; *p++ = '1'; *p++ = ' ';
+                        p = put_uint(p, g_libfm_item_offset + i[k]);
+                        *p++ = ':'; *p++ = '1';
                     } else {
-                        p += snprintf(p, 32, "%g", (double)r[k]);
+                        p = put_uint(p, u[k]);
+                        *p++ = '\t';
+                        p = put_uint(p, i[k]);
+                        *p++ = '\t';
+                        put_rating();
                     }
                     *p++ = '\n';
                 }
@@ -73,7 +87,8 @@ static void write_triples(const char* path, const uint32_t* u, const uint32_t* i
         for (uint64_t t = 0; t < T; ++t)
             if (!out[t].empty()) fwrite(out[t].data(), 1, out[t].size(), f);
     }
-    if (pin) fprintf(f, "%u\t%u\t3\n", pin_u, pin_i);
+    if (pin && g_libfm_item_offset) fprintf(f, "3 %u:1 %u:1\n", pin_u, g_libfm_item_offset + pin_i);
+    else if (pin) fprintf(f, "%u\t%u\t3\n", pin_u, pin_i);
     fclose(f);
 }
 
@@ -112,7 +127,7 @@ int main(int argc, char** argv)
     spec.test_frac = 0.1;
     spec.seed = 20151001;
     uint64_t max_train = 0;
-    int threads = 0, binary = 0;
+    int threads = 0, binary = 0, libfm_text = 0;
     std::string train, test;
     for (int a = 1; a + 1 < argc; a += 2) {
         const std::string k = argv[a];
@@ -127,6 +142,7 @@ int main(int argc, char** argv)
         else if (k == "-threads") threads = atoi(v);
         else if (k == "-max_train") max_train = strtoull(v, nullptr, 10);
         else if (k == "-binary") binary = atoi(v);
+        else if (k == "-libfm_text") libfm_text = atoi(v);
         else if (k == "-train") train = v;
         else if (k == "-test") test = v;
         else {
@@ -156,6 +172,7 @@ int main(int argc, char** argv)
     const uint32_t umax = n ? tu[n - 1] : 0;
     nt = 0;
     while (nt < nte && su[nt] <= umax) ++nt;
+    if (libfm_text) g_libfm_item_offset = spec.num_users;   // items numbered after ALL users, like scripts/triple_format_to_libfm.pl
     if (binary) {   // FILE.x + FILE.y (the id space is explicit in the header's num_cols; no pin row needed, but kept for equal counts)
         write_binary(train, tu, ti, tr, n, umax + 1, spec.num_items);
         std::vector<uint32_t> u2(su, su + nt), i2(si, si + nt);

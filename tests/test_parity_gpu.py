@@ -520,7 +520,9 @@ OPTION_SETS = [
     {"resident_max": 64, "slice_len": 256},             # most rows through the sliced streaming pipeline, many slices per row
     {"resident_max": 300, "slice_len": 1024, "max_blocks_per_launch": 1, "fold_item": 1},
     {"graph": 0},
-    {"pair_gather": 0, "resident_max": 128},            # streamed rows gather previous / current block as two sectors instead of one 64-byte row
+    {"pair_gather": 1, "resident_max": 128},            # streamed rows gather (previous, current) block as one 64-byte row by lane pairs
+    {"fuse_solve": 0, "resident_max": 128},             # streamed rows: updates as a launch of their own instead of the tail of the pass
+    {"resident_max_user": 64, "resident_max_item": 1024},
 ]
 
 
