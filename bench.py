@@ -48,11 +48,29 @@ WORKLOADS = {
 }
 
 
-def generate(sbmf, workload, device):
+def generate(sbmf, workload, device, rank=0, world=1, barrier=None):
     I, J, NTRAIN, _ = WORKLOADS[workload]
     n = int(round(NTRAIN / (1 - TEST_FRAC)))
     if float(I) * float(J) > 1e11:
-        return sbmf.synth_generate_host(I, J, n, test_frac=TEST_FRAC, seed=SEED)
+        if world == 1:
+            return sbmf.synth_generate_host(I, J, n, test_frac=TEST_FRAC, seed=SEED)
+        # the host sampler uses every host thread: one rank generates, the others map the arrays from /dev/shm
+        keys = ("train_user", "train_item", "train_rating", "test_user", "test_item", "test_rating")
+        base = f"/dev/shm/sbmf_bench_{workload}_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            d = sbmf.synth_generate_host(I, J, n, test_frac=TEST_FRAC, seed=SEED)
+            for k in keys:
+                np.save(f"{base}_{k}.npy", d[k])
+        barrier()
+        if rank != 0:
+            d = {k: np.load(f"{base}_{k}.npy", mmap_mode="r") for k in keys}
+            d = {k: np.ascontiguousarray(v) for k, v in d.items()}
+            d["num_users"], d["num_items"] = I, J
+        barrier()
+        if rank == 0:
+            for k in keys:
+                os.remove(f"{base}_{k}.npy")
+        return d
     return sbmf.synth_generate(I, J, n, test_frac=TEST_FRAC, seed=SEED, device=device)
 TEST_FRAC = 0.1
 SEED = 20151001 + 3
@@ -599,7 +617,7 @@ def main():
 
     dev = local_rank
     t0 = time.perf_counter()
-    d = generate(sbmf, a.workload, dev)
+    d = generate(sbmf, a.workload, dev, rank, world, barrier)
     gen_s = time.perf_counter() - t0
     n_train, n_test = int(d["train_user"].size), int(d["test_user"].size)
     run = {"n_train": n_train, "n_test": n_test, "synth_seconds": round(gen_s, 2), "options": opts}

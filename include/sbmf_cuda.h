@@ -148,13 +148,13 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
      group_rows    (1)    short rows share a warp (0: one warp per row)
      pair_gather   (0)    streamed rows gather (previous, current) factor block as one 64-byte row by lane pairs from a per-phase
                           pair array instead of two sector gathers (measured slower on sorted rating rows)   [before set_train]
-     fuse_solve    (1)    streamed rows: the row updates run in the tail of each pass (0: a launch of their own)
+     fuse_solve    (0)    streamed rows: the row updates run in the tail of each pass, by the last slice CTA of the row, instead of
+                          a launch of their own (halves the launch count of a phase; measured slower on one GPU)
      fold_user / fold_item (1 / 0)  one GPU: residual hand-over between the slot orders folded into the phase's first touch
      graph         (1)    steady-state sweep replayed from a CUDA graph when per-phase timing is off
      device_plan   (1)    multi-GPU: exchange plan computed on the device (0: host planner)  [before set_train]
      mgpu_pool     (1)    multi-GPU: rating-sized arrays from the stream-ordered pool        [before set_train]
      peer          (1)    multi-GPU: peer-mapped replicas + direct NVLink pushes (0: NCCL)   [before set_train]
-     sharded_build (1)    multi-GPU: each rank uploads / sorts only its slice of the COO      [before set_train]
      trace         (0)    stage times of set_train on stderr
    Unknown name or value out of range: SBMF_ERR_INVALID; a [before set_train] option after set_train: SBMF_ERR_STATE. */
 int sbmf_cuda_set_option(sbmf_handle* h, const char* name, int64_t value);

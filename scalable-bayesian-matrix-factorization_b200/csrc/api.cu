@@ -64,7 +64,6 @@ static const OptionDesc kOptions[] = {
     {"mgpu_pool", &Options::mgpu_pool, 0, 1, true},
     {"peer", &Options::peer, 0, 1, true},
     {"trace", &Options::trace, 0, 2, false},
-    {"sharded_build", &Options::sharded_build, 0, 1, true},
 };
 
 static const OptionDesc* find_option(const char* name)

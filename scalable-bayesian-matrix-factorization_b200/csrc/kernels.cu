@@ -588,8 +588,11 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
 // warp w sums the partials of slices s0 + w, s0 + w + NW, ... (independent coalesced 192-byte reads, through L2: the lines were
 // written by other SMs during this launch), the sums are combined in warp order -- a fixed tree whatever CTA happens to be last,
 // so results are reproducible -- and warp 0 performs the update(s).  CUR == 1: bias half-step; CUR == 2: factor block b.
+#ifndef SBMF_SOLVE_INLINE
+#define SBMF_SOLVE_INLINE __forceinline__
+#endif
 template <int CUR, int NW>
-__device__ __forceinline__ void heavy_row_solve(const PhaseArgs& a, uint32_t hrow, uint32_t s0, uint32_t s1, const float* __restrict__ hpart,
+__device__ SBMF_SOLVE_INLINE void heavy_row_solve(const PhaseArgs& a, uint32_t hrow, uint32_t s0, uint32_t s1, const float* __restrict__ hpart,
                                                 float* __restrict__ hdelta, float* __restrict__ hbias_delta, int b, float (*s_part)[NACC], float* s_tot)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -690,8 +693,8 @@ heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ slice_ptr, const fl
 // rating (delta apply, residual store) and the current block of its PARTNER's rating, whose updated residual arrives by one
 // shuffle for the accumulation.  Which load delivered which is a matter of lane parity: 16 selects per rating, paid from the
 // issue slots this gather-bound kernel leaves idle.
-template <int PREV, int CUR, int UNR, int THREADS, bool REFRESH, bool PAIR = false>
-__global__ void __launch_bounds__(THREADS)
+template <int PREV, int CUR, int UNR, int THREADS, bool REFRESH, bool PAIR = false, bool FUSE = true>
+__global__ void __launch_bounds__(THREADS, REFRESH ? 8 : 10)   // 64-thread CTAs: 96 (124 with the prediction refresh) registers per thread
 heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, float* __restrict__ hdelta, float* __restrict__ hbias_delta,
                         float* __restrict__ hpart, const uint32_t* __restrict__ slice_ptr, uint32_t* __restrict__ hcount, int pb, int b)
 {
@@ -785,48 +788,66 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, float* __
             }
         }
     } else
-    // batches of UNR ratings per thread: all index/residual loads, then all gathers, then the math, so that
-    // 2*UNR sector gathers per thread are in flight (the kernel is bound by the L2->SM gather path, not by arithmetic)
-    for (uint32_t base = threadIdx.x; base < sl.len; base += THREADS * UNR) {
-        uint32_t id[UNR];
-        float e[UNR];
-        float pr[REFRESH ? UNR : 1];
+    // (the general form)
+    // Batches of UNR ratings per thread, software-pipelined by one batch: the index / residual (/ partial prediction) words of
+    // batch t + 1 are requested right after the gathers of batch t have been issued, so that an iteration's critical path is one
+    // L2 round trip (the gathers) instead of a DRAM round trip (the index stream) FOLLOWED by the gathers -- with ~19 warps per SM
+    // the serial chain, not the L1TEX rate, was what a pass ran at (ncu: issue active 18 %, long scoreboard 21 per issue).
+    {
+        uint32_t idn[UNR];
+        float en[UNR];
+        float prn[REFRESH ? UNR : 1];
+        auto fetch = [&](uint32_t base) {
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const uint32_t i = base + u * THREADS;
-            const bool ok = i < sl.len;
-            id[u] = ok ? idx[i] : pad_row;
-            e[u] = ok ? ((PREV == 0) ? load_e_first(a, (int64_t)sl.start + i) : ep[i]) : 0.f;
-            if (REFRESH && PREV == 2) pr[u] = (ok && pb > 0) ? pp[i] : 0.f;
-        }
-        f8 fp[PREV == 2 ? UNR : 1], fc[CUR == 2 ? UNR : 1];
-        if (PREV == 2) {
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) fp[u] = ld256_nc(Fp + (size_t)id[u] * 8);
-        }
-        if (CUR == 2) {
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) fc[u] = ld256_nc(Fc + (size_t)id[u] * 8);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const uint32_t i = base + u * THREADS;
-            if (kPairedDots && REFRESH && PREV == 2) {   // (<f_prev, d_prev>, <f_prev, u_new_prev>) as one FFMA2 chain
-                const float2 s2 = dot8_pair(fp[u], dun);
-                e[u] += s2.x;
-                pr[u] += s2.y;
-            } else {
-                if (PREV == 2) e[u] += dot8(fp[u], dprev);
-                else e[u] += dscalar;
-                if (REFRESH && PREV == 2) pr[u] += dot8(fp[u], unprev);
+            for (int u = 0; u < UNR; ++u) {
+                const uint32_t i = base + u * THREADS;
+                const bool ok = i < sl.len;
+                idn[u] = ok ? idx[i] : pad_row;
+                en[u] = ok ? ((PREV == 0) ? load_e_first(a, (int64_t)sl.start + i) : ep[i]) : 0.f;
+                if (REFRESH && PREV == 2) prn[u] = (ok && pb > 0) ? pp[i] : 0.f;
             }
-            if (REFRESH && PREV == 2) {
-                if (CUR == 0) e[u] = (i < sl.len) ? rp[i] - (row_const + a.bias_other[id[u]] + pr[u]) : 0.f;   // phase done: fresh residual
-                else if (i < sl.len) pp[i] = pr[u];
+        };
+        fetch(threadIdx.x);
+        for (uint32_t base = threadIdx.x; base < sl.len; base += THREADS * UNR) {
+            uint32_t id[UNR];
+            float e[UNR];
+            float pr[REFRESH ? UNR : 1];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                id[u] = idn[u];
+                e[u] = en[u];
+                if (REFRESH && PREV == 2) pr[u] = prn[u];
             }
-            if (i < sl.len) ep[i] = e[u];
-            if (CUR == 1 && i < sl.len) acc[0] += e[u];
-            if (CUR == 2) ga.add(fc[u], e[u]);
+            f8 fp[PREV == 2 ? UNR : 1], fc[CUR == 2 ? UNR : 1];
+            if (PREV == 2) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) fp[u] = ld256_nc(Fp + (size_t)id[u] * 8);
+            }
+            if (CUR == 2) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) fc[u] = ld256_nc(Fc + (size_t)id[u] * 8);
+            }
+            fetch(base + THREADS * UNR);   // next batch (slots beyond the slice read nothing); other slots than the ones stored below
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const uint32_t i = base + u * THREADS;
+                if (kPairedDots && REFRESH && PREV == 2) {   // (<f_prev, d_prev>, <f_prev, u_new_prev>) as one FFMA2 chain
+                    const float2 s2 = dot8_pair(fp[u], dun);
+                    e[u] += s2.x;
+                    pr[u] += s2.y;
+                } else {
+                    if (PREV == 2) e[u] += dot8(fp[u], dprev);
+                    else e[u] += dscalar;
+                    if (REFRESH && PREV == 2) pr[u] += dot8(fp[u], unprev);
+                }
+                if (REFRESH && PREV == 2) {
+                    if (CUR == 0) e[u] = (i < sl.len) ? rp[i] - (row_const + a.bias_other[id[u]] + pr[u]) : 0.f;   // phase done: fresh residual
+                    else if (i < sl.len) pp[i] = pr[u];
+                }
+                if (i < sl.len) ep[i] = e[u];
+                if (CUR == 1 && i < sl.len) acc[0] += e[u];
+                if (CUR == 2) ga.add(fc[u], e[u]);
+            }
         }
     }
     if (CUR == 1) {
@@ -857,7 +878,7 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, float* __
             hpart[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
         }
     }
-    if (CUR != 0 && hcount != nullptr) {   // hcount == nullptr: the updates run as a launch of their own (heavy_solve_kernel)
+    if constexpr (CUR != 0 && FUSE) {   // FUSE == false: the updates run as a launch of their own (heavy_solve_kernel) and this tail does not exist
         // The row's update runs in the tail of this launch: every slice CTA publishes its partial, takes a ticket, and the CTA
         // that draws the last ticket of its row combines the partials (in slice order) and solves.  All CTAs of the row have
         // read the pending delta / bias delta of the previous step before they take a ticket, so the solve may overwrite them.
@@ -1462,11 +1483,16 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         const bool fuse = m.opt.fuse_solve != 0;
         uint32_t* hc = fuse ? self.hcount : nullptr;
         const bool wide_solve = ns >= 8u * nh;   // >= 8 slices per streamed row on average
-#define HEAVY_ACC(PREV, CUR, PB, B)                                                                                                              \
-    do {                                                                                                                                         \
-        if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, PB, B);  \
-        else SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, false>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, PB, B);         \
+#define HEAVY_ACC_T(PREV, CUR, RF, PR, FU, PB, B) \
+    SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, RF, PR, FU>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, PB, B)
+#define HEAVY_ACC_P(PREV, CUR, PR, PB, B)                                     \
+    do {                                                                      \
+        if (refresh && fuse) HEAVY_ACC_T(PREV, CUR, true, PR, true, PB, B);   \
+        else if (refresh) HEAVY_ACC_T(PREV, CUR, true, PR, false, PB, B);     \
+        else if (fuse) HEAVY_ACC_T(PREV, CUR, false, PR, true, PB, B);        \
+        else HEAVY_ACC_T(PREV, CUR, false, PR, false, PB, B);                 \
     } while (0)
+#define HEAVY_ACC(PREV, CUR, PB, B) HEAVY_ACC_P(PREV, CUR, false, PB, B)
 #define HEAVY_SOLVE(CUR, B)                                                                                                                      \
     do {                                                                                                                                         \
         if (fuse) break;                                                                                                                         \
@@ -1495,13 +1521,14 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         for (int b = 1; b < KB; ++b) {
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
             if (!pair) HEAVY_ACC(2, 2, b - 1, b);
-            else if (refresh) SBMF_LAUNCH((heavy_accumulate_kernel<2, 2, 2, 64, true, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, b - 1, b);
-            else SBMF_LAUNCH((heavy_accumulate_kernel<2, 2, 2, 64, false, true>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, b - 1, b);
+            else HEAVY_ACC_P(2, 2, true, b - 1, b);
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
             HEAVY_SOLVE(2, b);
         }
         HEAVY_ACC(2, 0, KB - 1, 0);
 #undef HEAVY_ACC
+#undef HEAVY_ACC_P
+#undef HEAVY_ACC_T
 #undef HEAVY_SOLVE
         m.launches += KB + 1 + (with_bias ? 1 : 0);
         cudaEventRecord(m.ev_join, sh);

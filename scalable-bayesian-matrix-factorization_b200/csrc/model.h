@@ -89,7 +89,8 @@ struct Options {
     int64_t slice_len = 0;        // heavy-row slice length; 0 = chosen from the shard size (build_worklists)
     int64_t group_rows = 1;       // short rows: several rows per warp (row_group_kernel); 0 = one warp per row
     int64_t pair_gather = 0;      // streaming pipeline: gather (previous, current) block as one 64-byte row by lane pairs (0: two sector gathers)
-    int64_t fuse_solve = 1;       // streaming pipeline: row updates in the tail of each pass (0: a launch of their own)
+    int64_t fuse_solve = 0;       // streaming pipeline: row updates in the tail of each pass by the row's last slice CTA (0: a launch of
+                                  // their own; measured on B200: the release fence + ticket per slice CTA costs 160 us per pass, a launch 55)
     int64_t fold_user = 1;        // one GPU: CSC->CSR residual hand-over folded into the user phase's first touch
     int64_t fold_item = 0;        // one GPU: CSR->CSC hand-over folded into the item phase's first touch
     int64_t graph = 1;            // replay the steady-state sweep from a CUDA graph when per-phase timing is off
@@ -97,7 +98,6 @@ struct Options {
     int64_t mgpu_pool = 1;        // multi-GPU: rating-sized arrays from the stream-ordered pool (0 = cudaMalloc)
     int64_t peer = 1;             // multi-GPU: peer-mapped replicas / direct NVLink pushes (0 = NCCL exchanges)
     int64_t trace = 0;            // 1: wall-clock of the set_train stages on stderr; 2: without device synchronisation
-    int64_t sharded_build = 1;    // multi-GPU: every rank uploads and sorts only its slice of the COO (0 = global build per rank)
 };
 
 struct Model {

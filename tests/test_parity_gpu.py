@@ -521,7 +521,7 @@ OPTION_SETS = [
     {"resident_max": 300, "slice_len": 1024, "max_blocks_per_launch": 1, "fold_item": 1},
     {"graph": 0},
     {"pair_gather": 1, "resident_max": 128},            # streamed rows gather (previous, current) block as one 64-byte row by lane pairs
-    {"fuse_solve": 0, "resident_max": 128},             # streamed rows: updates as a launch of their own instead of the tail of the pass
+    {"fuse_solve": 1, "resident_max": 128},             # streamed rows: updates in the tail of the pass (last slice CTA of the row) instead of a launch of their own
     {"resident_max_user": 64, "resident_max_item": 1024},
 ]
 

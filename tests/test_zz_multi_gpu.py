@@ -1,7 +1,7 @@
 """Multi-GPU parity inside the pytest -m gpu suite (skipped on boxes with fewer than 2 GPUs): G-GPU zero-noise chains against the
 oracle (<= 1e-4) and G-GPU live chains against the 1-GPU chain of the same seed, on ML-100K and on a matrix with streamed rows on
 either side -- tools/mgpu_check.py under torchrun, for the default configuration and for every multi-GPU option
-(host planner, cudaMalloc layout, NCCL exchanges instead of peer pushes, global build per rank)."""
+(host planner, cudaMalloc layout, NCCL exchanges instead of peer pushes)."""
 import glob
 import os
 import subprocess
@@ -14,7 +14,7 @@ NGPU = len(glob.glob("/dev/nvidia[0-9]*"))
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(NGPU < 2, reason=f"needs >= 2 GPUs on the box (found {NGPU})")]
 
-OPTION_SETS = ["", "device_plan=0,mgpu_pool=0", "peer=0", "sharded_build=0", "sharded_build=0,device_plan=0,peer=0"]
+OPTION_SETS = ["", "device_plan=0,mgpu_pool=0", "peer=0", "device_plan=0,peer=0"]
 
 
 @pytest.mark.parametrize("world", [2] + ([4] if NGPU >= 4 else []) + ([8] if NGPU >= 8 else []))
