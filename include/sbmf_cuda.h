@@ -146,6 +146,8 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
      resident_max_user / resident_max_item  the same threshold per side (resident_max sets both)  [before set_train]
      slice_len     (0)    ratings per slice of a streamed row; 0 = chosen from the shard size  [before set_train]
      group_rows    (1)    short rows share a warp (0: one warp per row)
+     row_kernels   (1)    resident rows: 2 = shared-memory reduction of the Gram sums and one block barrier per factor block
+                          (csrc/rows2.cuh; first measurement: slower); 1 = transposed shuffle reduction (csrc/kernels.cu)
      pair_gather   (0)    streamed rows gather (previous, current) factor block as one 64-byte row by lane pairs from a per-phase
                           pair array instead of two sector gathers (measured slower on sorted rating rows)   [before set_train]
      fuse_solve    (0)    streamed rows: the row updates run in the tail of each pass, by the last slice CTA of the row, instead of

@@ -98,10 +98,86 @@ __host__ __device__ __forceinline__ float2 dot8_pair(const f8& f, const float2 (
     return s;
 }
 
+// 64-bit register pair (lo, hi) as ONE operand: a pair prepared once per row and block stays in an aligned register pair instead of
+// being re-assembled by two moves in front of every FFMA2 that reads it (what ptxas did to dot8_pair under register pressure)
+#ifndef SBMF_SIMT_EMU
+typedef unsigned long long pair64;
+__device__ __forceinline__ pair64 pack_pair(float lo, float hi)
+{
+    pair64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_pair(pair64 p)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+// d = (s, s) * b + c
+__device__ __forceinline__ pair64 fma2_bcast_p(float s, pair64 b, pair64 c)
+{
+    pair64 d;
+    asm("{ .reg .b64 ra;\n\t"
+        "mov.b64 ra, {%1, %1};\n\t"
+        "fma.rn.f32x2 %0, ra, %2, %3; }"
+        : "=l"(d)
+        : "f"(s), "l"(b), "l"(c));
+    return d;
+}
+#else   // test-only host build of the kernels (launch.h)
+struct pair64 { float lo, hi; };
+inline pair64 pack_pair(float lo, float hi) { return pair64{lo, hi}; }
+inline float2 unpack_pair(pair64 p) { return float2{p.lo, p.hi}; }
+inline pair64 fma2_bcast_p(float s, pair64 b, pair64 c) { return pair64{fmaf(s, b.lo, c.lo), fmaf(s, b.hi, c.hi)}; }
+#endif
+// (<f, x>, <f, y>) for the 8 prepared pairs xy[k] = (x[k], y[k]): the same two 8-term chains as dot8_pair, k = 0..7
+__device__ __forceinline__ float2 dot8_pairs64(const f8& f, const pair64 (&xy)[8])
+{
+    pair64 s = pack_pair(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = fma2_bcast_p(f.v[k], xy[k], s);
+    return unpack_pair(s);
+}
+
+// "Native" order of the 48 accumulators = the order the build's GramAcc holds them in registers (scalar: gi(); packed: the pair
+// layout).  The shared-memory reduction of the row kernels moves them as 12 float4 quads without re-packing, and
+// native_entry() tells where each one belongs: kind 0 = g[k], 1 = G[k][l] (k <= l), 2 = padding / redundant copy.
+__host__ __device__ constexpr int native_entry(int n, int& k, int& l)
+{
+    k = 0;
+    l = 0;
+    if (n < 8) {
+        k = n;
+        return 0;
+    }
+#if SBMF_FFMA2
+    const int P = n / 2, half = n & 1;
+    for (int kk = 0; kk < 8; ++kk)
+        for (int p = kk / 2; p < 4; ++p)
+            if (pi(kk, p) == P) {
+                k = kk;
+                l = 2 * p + half;
+                return l >= kk ? 1 : 2;
+            }
+    return 2;
+#else
+    for (int kk = 0; kk < 8; ++kk)
+        for (int ll = kk; ll < 8; ++ll)
+            if (gi(kk, ll) == n) {
+                k = kk;
+                l = ll;
+                return 1;
+            }
+    return 2;
+#endif
+}
+
 // The accumulator of one (row | slice, block) step in whichever form the build selects.
 struct GramAcc {
 #if SBMF_FFMA2
     float2 a2[NPAIR];
+    __host__ __device__ __forceinline__ float4 quad(int j) const { return make_float4(a2[2 * j].x, a2[2 * j].y, a2[2 * j + 1].x, a2[2 * j + 1].y); }
     __host__ __device__ __forceinline__ void clear()
     {
 #pragma unroll
@@ -111,6 +187,7 @@ struct GramAcc {
     __host__ __device__ __forceinline__ void finish(float (&acc)[NACC]) const { unpack_pairs(a2, acc); }
 #else
     float a[NACC];
+    __host__ __device__ __forceinline__ float4 quad(int j) const { return make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]); }
     __host__ __device__ __forceinline__ void clear()
     {
 #pragma unroll

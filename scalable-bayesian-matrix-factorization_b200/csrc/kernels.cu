@@ -579,6 +579,10 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
     }
 }
 
+}  // namespace sbmf
+#include "rows2.cuh"   // second-generation resident-row kernels (option row_kernels = 2)
+namespace sbmf {
+
 // --------------------------------------------------------------------------------------------------------
 // Heavy rows: sliced streaming pipeline.  accumulate<PREV,CUR> applies the pending delta of the previous step
 // to e (PREV: 0 = only the global shift, 1 = bias delta, 2 = delta of block pb, re-gathering f) and accumulates
@@ -1276,6 +1280,19 @@ void init_constant_tables()
         }
     cudaMemcpyToSymbol(c_pk_a, pa, NACC);
     cudaMemcpyToSymbol(c_pk_b, pb, NACC);
+    // the same two offsets for the accumulators in the order the build's GramAcc holds them (rows2.cuh)
+    uint8_t na[NACC], nb[NACC];
+    for (int n = 0; n < NACC; ++n) {
+        int k = 0, l = 0;
+        const int kind = native_entry(n, k, l);
+        if (kind == 0) na[n] = nb[n] = (uint8_t)k;
+        else if (kind == 1) {
+            na[n] = (uint8_t)(8 + G_STRIDE * k + l);
+            nb[n] = (uint8_t)(8 + G_STRIDE * l + k);
+        } else na[n] = nb[n] = (uint8_t)(8 + 8 * G_STRIDE + (n & 3));
+    }
+    cudaMemcpyToSymbol(c_nat_a, na, NACC);
+    cudaMemcpyToSymbol(c_nat_b, nb, NACC);
 }
 
 static inline uint32_t grid_for(uint64_t n, int threads, int cap)
@@ -1360,11 +1377,14 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
     constexpr int RPL = kBins[BIN].rpl, WARPS = kBins[BIN].warps;
     const uint32_t n = self.bin_count[BIN];
     if (!n) return;
+    const bool v2 = m.opt.row_kernels == 2;   // rows2.cuh: shared-memory reduction, one barrier per block; 1 = the round-1 kernels (A/B)
     if constexpr (WARPS == 0) {   // short rows: G lanes per row (kBins[].cap = G * RPL)
         if (!m.opt.group_rows) {   // option group_rows = 0: one warp per short row instead (debugging / A-B)
             constexpr int R1 = kBins[BIN].cap / 32;
             const dim3 grid1((n + 3) / 4);
-            if (refresh) SBMF_LAUNCH((row_resident_kernel<R1, 1, true>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            if (v2 && refresh) SBMF_LAUNCH((row_resident2_kernel<R1, 1, true, 1>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            else if (v2) SBMF_LAUNCH((row_resident2_kernel<R1, 1, false, 1>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            else if (refresh) SBMF_LAUNCH((row_resident_kernel<R1, 1, true>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
             else SBMF_LAUNCH((row_resident_kernel<R1, 1, false>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
             m.launches++;
             return;
@@ -1372,14 +1392,19 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
         constexpr int G = kBins[BIN].cap / (RPL > 0 ? RPL : 1) >= 16 ? 16 : 8;
         const uint32_t rows_per_cta = 4 * (32 / G);
         const dim3 grid((n + rows_per_cta - 1) / rows_per_cta);
-        if (refresh) SBMF_LAUNCH((row_group_kernel<RPL, G, true>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        if (v2 && refresh) SBMF_LAUNCH((row_group2_kernel<RPL, G, true>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (v2) SBMF_LAUNCH((row_group2_kernel<RPL, G, false>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (refresh) SBMF_LAUNCH((row_group_kernel<RPL, G, true>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         else SBMF_LAUNCH((row_group_kernel<RPL, G, false>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         m.launches++;
         return;
     }
     if constexpr (WARPS > 0) {
+        constexpr int NR = (WARPS == 8) ? 2 : 1;   // rounds of the shared-memory reduction: the 8-warp exchange buffers must fit 48 KB
         const dim3 grid(WARPS == 1 ? (n + 3) / 4 : n), block(WARPS == 1 ? 128 : WARPS * 32);
-        if (refresh) SBMF_LAUNCH((row_resident_kernel<RPL, WARPS, true>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        if (v2 && refresh) SBMF_LAUNCH((row_resident2_kernel<RPL, WARPS, true, NR>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (v2) SBMF_LAUNCH((row_resident2_kernel<RPL, WARPS, false, NR>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (refresh) SBMF_LAUNCH((row_resident_kernel<RPL, WARPS, true>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         else SBMF_LAUNCH((row_resident_kernel<RPL, WARPS, false>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         m.launches++;
     }
