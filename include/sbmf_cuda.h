@@ -146,8 +146,11 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
      resident_max_user / resident_max_item  the same threshold per side (resident_max sets both)  [before set_train]
      slice_len     (0)    ratings per slice of a streamed row; 0 = chosen from the shard size  [before set_train]
      group_rows    (1)    short rows share a warp (0: one warp per row)
-     row_kernels   (1)    resident rows: 2 = shared-memory reduction of the Gram sums and one block barrier per factor block
-                          (csrc/rows2.cuh; first measurement: slower); 1 = transposed shuffle reduction (csrc/kernels.cu)
+     row_kernels   (1)    resident rows: 1 = csrc/kernels.cu (transposed shuffle reduction); 2 = csrc/rows2.cuh with the Gram sums reduced
+                          through shared memory (fewer instructions, more L1TEX wavefronts: measured slower); 3 = rows2.cuh with the
+                          shuffle reduction (one block barrier per factor block, 64-bit pair operands: measured equal to 1)
+     alt_bins      (1)    resident rows of 193..512 ratings are owned by 2 warps with 6 | 8 ratings per lane (one-barrier kernels of
+                          csrc/rows2.cuh) instead of 4 warps with 3 | 4: half the per-block reduction / solve work per rating
      pair_gather   (0)    streamed rows gather (previous, current) factor block as one 64-byte row by lane pairs from a per-phase
                           pair array instead of two sector gathers (measured slower on sorted rating rows)   [before set_train]
      fuse_solve    (0)    streamed rows: the row updates run in the tail of each pass, by the last slice CTA of the row, instead of

@@ -55,7 +55,8 @@ static const OptionDesc kOptions[] = {
     {"resident_max_item", &Options::resident_max_item, 1, RESIDENT_MAX, true},
     {"slice_len", &Options::slice_len, 0, 1 << 24, true},
     {"group_rows", &Options::group_rows, 0, 1, false},
-    {"row_kernels", &Options::row_kernels, 1, 2, false},
+    {"row_kernels", &Options::row_kernels, 1, 3, false},
+    {"alt_bins", &Options::alt_bins, 0, 1, false},
     {"pair_gather", &Options::pair_gather, 0, 1, true},
     {"fuse_solve", &Options::fuse_solve, 0, 1, false},
     {"fold_user", &Options::fold_user, 0, 1, false},

@@ -1377,13 +1377,26 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
     constexpr int RPL = kBins[BIN].rpl, WARPS = kBins[BIN].warps;
     const uint32_t n = self.bin_count[BIN];
     if (!n) return;
-    const bool v2 = m.opt.row_kernels == 2;   // rows2.cuh: shared-memory reduction, one barrier per block; 1 = the round-1 kernels (A/B)
+    // option alt_bins: rows of 193..512 ratings by 2 warps x (6 | 8) ratings per lane instead of 4 warps x (3 | 4) -- same capacity,
+    // half the per-block fixed work (reduction, solve) per rating
+    if constexpr (WARPS == 4 && RPL <= 4) {
+        if (m.opt.alt_bins) {
+            const dim3 grid(n), block(64);
+            if (refresh) SBMF_LAUNCH((row_resident2_kernel<2 * RPL, 2, true, 1, false>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            else SBMF_LAUNCH((row_resident2_kernel<2 * RPL, 2, false, 1, false>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            m.launches++;
+            return;
+        }
+    }
+    const int rk = (int)m.opt.row_kernels;   // 1: kernels.cu; 2: rows2.cuh with the shared-memory reduction; 3: rows2.cuh with the shuffle tree
     if constexpr (WARPS == 0) {   // short rows: G lanes per row (kBins[].cap = G * RPL)
         if (!m.opt.group_rows) {   // option group_rows = 0: one warp per short row instead (debugging / A-B)
             constexpr int R1 = kBins[BIN].cap / 32;
             const dim3 grid1((n + 3) / 4);
-            if (v2 && refresh) SBMF_LAUNCH((row_resident2_kernel<R1, 1, true, 1>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
-            else if (v2) SBMF_LAUNCH((row_resident2_kernel<R1, 1, false, 1>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            if (rk == 2 && refresh) SBMF_LAUNCH((row_resident2_kernel<R1, 1, true, 1, true>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            else if (rk == 2) SBMF_LAUNCH((row_resident2_kernel<R1, 1, false, 1, true>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            else if (rk == 3 && refresh) SBMF_LAUNCH((row_resident2_kernel<R1, 1, true, 1, false>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+            else if (rk == 3) SBMF_LAUNCH((row_resident2_kernel<R1, 1, false, 1, false>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
             else if (refresh) SBMF_LAUNCH((row_resident_kernel<R1, 1, true>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
             else SBMF_LAUNCH((row_resident_kernel<R1, 1, false>), grid1, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
             m.launches++;
@@ -1392,8 +1405,10 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
         constexpr int G = kBins[BIN].cap / (RPL > 0 ? RPL : 1) >= 16 ? 16 : 8;
         const uint32_t rows_per_cta = 4 * (32 / G);
         const dim3 grid((n + rows_per_cta - 1) / rows_per_cta);
-        if (v2 && refresh) SBMF_LAUNCH((row_group2_kernel<RPL, G, true>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
-        else if (v2) SBMF_LAUNCH((row_group2_kernel<RPL, G, false>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        if (rk == 2 && refresh) SBMF_LAUNCH((row_group2_kernel<RPL, G, true, true>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (rk == 2) SBMF_LAUNCH((row_group2_kernel<RPL, G, false, true>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (rk == 3 && refresh) SBMF_LAUNCH((row_group2_kernel<RPL, G, true, false>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (rk == 3) SBMF_LAUNCH((row_group2_kernel<RPL, G, false, false>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         else if (refresh) SBMF_LAUNCH((row_group_kernel<RPL, G, true>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         else SBMF_LAUNCH((row_group_kernel<RPL, G, false>), grid, 128, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         m.launches++;
@@ -1402,8 +1417,10 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
     if constexpr (WARPS > 0) {
         constexpr int NR = (WARPS == 8) ? 2 : 1;   // rounds of the shared-memory reduction: the 8-warp exchange buffers must fit 48 KB
         const dim3 grid(WARPS == 1 ? (n + 3) / 4 : n), block(WARPS == 1 ? 128 : WARPS * 32);
-        if (v2 && refresh) SBMF_LAUNCH((row_resident2_kernel<RPL, WARPS, true, NR>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
-        else if (v2) SBMF_LAUNCH((row_resident2_kernel<RPL, WARPS, false, NR>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        if (rk == 2 && refresh) SBMF_LAUNCH((row_resident2_kernel<RPL, WARPS, true, NR, true>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (rk == 2) SBMF_LAUNCH((row_resident2_kernel<RPL, WARPS, false, NR, true>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (rk == 3 && refresh) SBMF_LAUNCH((row_resident2_kernel<RPL, WARPS, true, 1, false>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
+        else if (rk == 3) SBMF_LAUNCH((row_resident2_kernel<RPL, WARPS, false, 1, false>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         else if (refresh) SBMF_LAUNCH((row_resident_kernel<RPL, WARPS, true>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         else SBMF_LAUNCH((row_resident_kernel<RPL, WARPS, false>), grid, block, 0, st, a, self.bin_rows[BIN], n, b0, b1, do_bias);
         m.launches++;

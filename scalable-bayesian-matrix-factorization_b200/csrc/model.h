@@ -89,6 +89,7 @@ struct Options {
     int64_t slice_len = 0;        // heavy-row slice length; 0 = chosen from the shard size (build_worklists)
     int64_t group_rows = 1;       // short rows: several rows per warp (row_group_kernel); 0 = one warp per row
     int64_t row_kernels = 1;      // resident rows: 1 = shuffle reduction (kernels.cu), 2 = rows2.cuh (shared-memory reduction, one barrier per block; measured slower, A/B)
+    int64_t alt_bins = 1;         // resident rows of 193..512 ratings: 2 warps x (6 | 8) per lane (rows2.cuh) instead of 4 warps x (3 | 4); measured 12.19 -> 11.77 ms user phase
     int64_t pair_gather = 0;      // streaming pipeline: gather (previous, current) block as one 64-byte row by lane pairs (0: two sector gathers)
     int64_t fuse_solve = 0;       // streaming pipeline: row updates in the tail of each pass by the row's last slice CTA (0: a launch of
                                   // their own; measured on B200: the release fence + ticket per slice CTA costs 160 us per pass, a launch 55)

@@ -120,6 +120,15 @@ __device__ __forceinline__ void scatter_quad(float* tot, float4 v, uint32_t oa, 
     tot[oa >> 24] = v.w;
     tot[ob >> 24] = v.w;
 }
+// keep a loop-invariant value in its register: ptxas otherwise re-derives the packed offsets inside the block loop from their
+// constant-memory bytes, and a constant load with a lane-dependent index replays once per distinct address (ncu: the address
+// arithmetic behind those loads was 11 % of the stall samples of row_resident2_kernel<6,1>)
+__device__ __forceinline__ void pin_register(uint32_t& v)
+{
+#ifndef SBMF_SIMT_EMU
+    asm volatile("mov.b32 %0, %0;" : "+r"(v));
+#endif
+}
 __device__ __forceinline__ void quad_offsets(int q, uint32_t& oa, uint32_t& ob)
 {
     oa = 0;
@@ -129,6 +138,8 @@ __device__ __forceinline__ void quad_offsets(int q, uint32_t& oa, uint32_t& ob)
         oa |= (uint32_t)c_nat_a[4 * q + i] << (8 * i);
         ob |= (uint32_t)c_nat_b[4 * q + i] << (8 * i);
     }
+    pin_register(oa);
+    pin_register(ob);
 }
 
 // The lane-parallel solve of solve_lanes (kernels.cu) with the stores optional: rows owned by several warps solve in every
@@ -200,14 +211,16 @@ __device__ __forceinline__ void apply_deltas(const f8 (&f)[RPL], const float (&d
 // --------------------------------------------------------------------------------------------------------
 // WARPS warps own one row (WARPS == 1: four independent rows per CTA), RPL (idx, e, f) per lane in registers.
 // NR = rounds of the shared-memory reduction (2 halves the exchange buffer: the 8-warp shape would not fit 48 KB otherwise).
-template <int RPL, int WARPS, bool REFRESH, int NR>
+// SMEM_RED: the 48 sums go through the exchange buffer (warp_sum48); false: transposed shuffle tree of kernels.cu inside the new
+// structure (one barrier per block, pair operands) -- option row_kernels = 3, to tell the two changes apart.
+template <int RPL, int WARPS, bool REFRESH, int NR, bool SMEM_RED>
 __global__ void __launch_bounds__(WARPS == 1 ? 128 : WARPS * 32, (RPL >= 7 ? 512 : RPL >= 4 ? 640 : 768) / (WARPS == 1 ? 128 : WARPS * 32))
 row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows, int b_begin, int b_end, int do_bias)
 {
     using X = XbGeom<NR>;
     static_assert(WARPS > 1 || NR == 1, "single-warp rows reduce in one round");
     constexpr int WPC = (WARPS == 1) ? 4 : WARPS;   // warps per CTA
-    __shared__ __align__(16) float s_xb[WPC][X::FLOATS];
+    __shared__ __align__(16) float s_xb[SMEM_RED ? WPC : 1][SMEM_RED ? X::FLOATS : 4];
     __shared__ __align__(16) float s_tot[WPC][SOLVE_SMEM];
     __shared__ __align__(16) float s_part[(WARPS == 1) ? 1 : 2][(WARPS == 1) ? 1 : WARPS][NACC];
     __shared__ float s_bias[(WARPS == 1) ? 1 : WARPS];
@@ -220,7 +233,7 @@ row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nr
     const int t_in_row = (WARPS == 1) ? lane : threadIdx.x;
     constexpr int TPR = WARPS * 32;   // threads per row
     float* tot = s_tot[warp];
-    float* xb = s_xb[warp];
+    float* xb = s_xb[SMEM_RED ? warp : 0];
 
     const int mode = a.mode;
     const uint32_t K = a.K;
@@ -230,8 +243,28 @@ row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nr
     const uint32_t pad_row = ns_other - 1;
     const float* __restrict__ Fother = a.Fother;
     const int kq = lane & 7;
-    uint32_t off_a, off_b;   // solve-layout offsets of quad `lane` (lanes 0..11 scatter)
-    quad_offsets(lane < 12 ? lane : 0, off_a, off_b);
+    // solve-layout offsets of quad `lane` (lanes 0..11 scatter): native accumulator order (SMEM_RED) or the scalar order the
+    // shuffle tree delivers; single-warp rows on the shuffle path store their 3 sums per even lane like row_resident_kernel
+    uint32_t off_a = 0, off_b = 0;
+    if (SMEM_RED) quad_offsets(lane < 12 ? lane : 0, off_a, off_b);
+    else if (WARPS > 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            off_a |= (uint32_t)c_pk_a[4 * (lane < 12 ? lane : 0) + i] << (8 * i);
+            off_b |= (uint32_t)c_pk_b[4 * (lane < 12 ? lane : 0) + i] << (8 * i);
+        }
+        pin_register(off_a);
+        pin_register(off_b);
+    } else {
+        const int base = reduce_scatter_base(lane);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            off_a |= (uint32_t)c_pk_a[base + i] << (8 * i);
+            off_b |= (uint32_t)c_pk_b[base + i] << (8 * i);
+        }
+        pin_register(off_a);
+        pin_register(off_b);
+    }
 
     uint32_t id[RPL];
     float e[RPL];
@@ -301,16 +334,36 @@ row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nr
         ga.clear();
 #pragma unroll
         for (int r = 0; r < RPL; ++r) ga.add(f[r], e[r]);
-        float4 t4[NR];
-        warp_sum48<NR>(ga, xb, lane, t4);
-        if (WARPS == 1) {
-            if (lane < 12) scatter_quad(tot, t4[0], off_a, off_b);
-        } else {
-            float* part = s_part[b & 1][warp];
-            if (lane < X::QR) {
+        float* part = s_part[(WARPS == 1) ? 0 : (b & 1)][(WARPS == 1) ? 0 : warp];
+        if (SMEM_RED) {
+            float4 t4[NR];
+            warp_sum48<NR>(ga, xb, lane, t4);
+            if (WARPS == 1) {
+                if (lane < 12) scatter_quad(tot, t4[0], off_a, off_b);
+            } else if (lane < X::QR) {
 #pragma unroll
                 for (int r = 0; r < NR; ++r) *reinterpret_cast<float4*>(part + 4 * (r * X::QR + lane)) = t4[r];
             }
+        } else {
+            float acc[NACC];
+            ga.finish(acc);
+            warp_reduce_scatter48(acc, lane);
+            if ((lane & 1) == 0) {
+                if (WARPS == 1) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        tot[(off_a >> (8 * i)) & 0xff] = acc[i];
+                        tot[(off_b >> (8 * i)) & 0xff] = acc[i];
+                    }
+                } else {
+                    const int rb = reduce_scatter_base(lane);
+                    part[rb] = acc[0];
+                    part[rb + 1] = acc[1];
+                    part[rb + 2] = acc[2];
+                }
+            }
+        }
+        if (WARPS > 1) {
             __syncthreads();   // the only block barrier of a factor block: s_part is double-buffered by block parity
             if (lane < 12) {
                 float4 s = *reinterpret_cast<const float4*>(s_part[b & 1][0] + 4 * lane);
@@ -359,14 +412,15 @@ row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nr
 // --------------------------------------------------------------------------------------------------------
 // Short rows: G = 8 or 16 lanes own a row, 32 / G rows per warp (see row_group_kernel); the reduction serves all rows of the
 // warp with the same instructions.
-template <int RPL, int G, bool REFRESH>
+template <int RPL, int G, bool REFRESH, bool SMEM_RED>
 __global__ void __launch_bounds__(128, (RPL >= 6 ? 512 : RPL >= 4 ? 640 : 768) / 128)
 row_group2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows, int b_begin, int b_end, int do_bias)
 {
     using X = XbGeom<1>;
     constexpr int RPW = 32 / G;          // rows per warp
     constexpr int ZB = G / 8;            // blocks covered by one noise draw
-    __shared__ __align__(16) float s_xb[4][X::FLOATS];
+    constexpr int NV = (G == 16) ? 3 : 6;   // shuffle path: reduced values per lane
+    __shared__ __align__(16) float s_xb[SMEM_RED ? 4 : 1][SMEM_RED ? X::FLOATS : 4];
     __shared__ __align__(16) float s_tot[4 * RPW][SOLVE_SMEM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G, lg = lane % G, kq = lane & 7;
@@ -376,7 +430,7 @@ row_group2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows
     const int64_t beg = a.ptr[row];
     const int c = have_row ? (int)(a.ptr[row + 1] - beg) : 0;
     float* tot = s_tot[warp * RPW + grp];
-    float* xb = s_xb[warp];
+    float* xb = s_xb[SMEM_RED ? warp : 0];
 
     const int mode = a.mode;
     const uint32_t K = a.K;
@@ -386,8 +440,18 @@ row_group2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows
     const uint32_t pad_row = ns_other - 1;
     const float* __restrict__ Fother = a.Fother;
     // lanes 0..23 scatter: quad lane % 12 of row group(s) lane / 12 (G == 16) or 2 * (lane / 12) + {0, 1} (G == 8)
-    uint32_t off_a, off_b;
-    quad_offsets(lane < 24 ? lane % 12 : 0, off_a, off_b);
+    uint32_t off_a = 0, off_b = 0;
+    uint64_t sh_a = 0, sh_b = 0;   // shuffle path: NV x 8-bit offsets of this lane's reduced sums
+    if (SMEM_RED) quad_offsets(lane < 24 ? lane % 12 : 0, off_a, off_b);
+    else {
+        const int base0 = (G == 16) ? ((lg >> 3) & 1) * 24 + ((lg >> 2) & 1) * 12 + ((lg >> 1) & 1) * 6 + (lg & 1) * 3
+                                    : ((lg >> 2) & 1) * 24 + ((lg >> 1) & 1) * 12 + (lg & 1) * 6;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            sh_a |= (uint64_t)c_pk_a[base0 + i] << (8 * i);
+            sh_b |= (uint64_t)c_pk_b[base0 + i] << (8 * i);
+        }
+    }
     float* tot_s0 = s_tot[warp * RPW + ((G == 16) ? (lane < 24 ? lane / 12 : 0) : (lane < 24 ? 2 * (lane / 12) : 0))];
 
     uint32_t id[RPL];
@@ -450,11 +514,22 @@ row_group2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows
         ga.clear();
 #pragma unroll
         for (int r = 0; r < RPL; ++r) ga.add(f[r], e[r]);
-        float4 t4[RPW / 2];
-        group_sum48<RPW>(ga, xb, lane, t4);
-        if (lane < 24) {
-            scatter_quad(tot_s0, t4[0], off_a, off_b);
-            if (RPW == 4) scatter_quad(tot_s0 + SOLVE_SMEM, t4[RPW / 2 - 1], off_a, off_b);
+        if (SMEM_RED) {
+            float4 t4[RPW / 2];
+            group_sum48<RPW>(ga, xb, lane, t4);
+            if (lane < 24) {
+                scatter_quad(tot_s0, t4[0], off_a, off_b);
+                if (RPW == 4) scatter_quad(tot_s0 + SOLVE_SMEM, t4[RPW / 2 - 1], off_a, off_b);
+            }
+        } else {
+            float acc[NACC];
+            ga.finish(acc);
+            group_reduce_scatter48<G>(acc, lg);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                tot[(uint32_t)(sh_a >> (8 * i)) & 0xffu] = acc[i];
+                tot[(uint32_t)(sh_b >> (8 * i)) & 0xffu] = acc[i];
+            }
         }
         __syncwarp();
         const float z = __shfl_sync(0xffffffffu, zq, ((b % ZB) << 3) + kq, G);
