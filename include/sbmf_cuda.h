@@ -145,6 +145,10 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
      resident_max  (2048) rows with more ratings stream through the sliced pipeline          [before set_train]
      resident_max_user / resident_max_item  the same threshold per side (resident_max sets both)  [before set_train]
      slice_len     (0)    ratings per slice of a streamed row; 0 = chosen from the shard size  [before set_train]
+     relabel       (1)    rows are stored in order of decreasing rating count and the slots of a row in that order of the
+                          opposite side (sbmf_cuda_get_storage_layout): the popular rows become neighbours, so adjacent lanes of a
+                          factor gather share 128-byte lines.  0: the caller's ids and file order.  Same chain either way: every
+                          draw is keyed by the caller's row id; only fp32 summation order differs          [before set_train]
      group_rows    (1)    short rows share a warp (0: one warp per row)
      row_kernels   (1)    resident rows: 1 = csrc/kernels.cu (transposed shuffle reduction); 2 = csrc/rows2.cuh with the Gram sums reduced
                           through shared memory (fewer instructions, more L1TEX wavefronts: measured slower); 3 = rows2.cuh with the
@@ -200,6 +204,15 @@ int sbmf_cuda_set_test(sbmf_handle* h, uint64_t nt, const uint32_t* user, const 
    csc_id[n] (rating index per CSC slot), perm[n] (CSR slot of each CSC slot). */
 int sbmf_cuda_get_layout(sbmf_handle* h, int64_t* row_ptr, uint32_t* col, uint64_t* csr_id,
                          int64_t* col_ptr, uint32_t* row, uint64_t* csc_id, uint64_t* perm);
+/* The arrays the sweep kernels actually run on.  With option relabel = 0 that is get_layout.  With relabel = 1 (default) every
+   row lives at a POSITION -- rows ordered by decreasing number of training ratings, ties by id (G GPUs: ranks dealt round-robin
+   into G contiguous ranges) -- and the slots of a row are ordered by the opposite side's position, then file order:
+   user_pos[u] / item_pos[j] = position of the caller's row id; row_ptr / col_ptr are indexed by position, col / row hold
+   positions, csr_id / csc_id the caller's rating indices, perm the CSR slot of each CSC slot.  The same sampler runs on it
+   (draws are keyed by the caller's ids); the order only decides which factor sectors adjacent lanes of a gather fetch. */
+int sbmf_cuda_get_storage_layout(sbmf_handle* h, int64_t* row_ptr, uint32_t* col, uint64_t* csr_id,
+                                 int64_t* col_ptr, uint32_t* row, uint64_t* csc_id, uint64_t* perm);
+int sbmf_cuda_get_row_positions(sbmf_handle* h, uint32_t* user_pos, uint32_t* item_pos);
 
 /* libFM's transposed binary design matrix (".xt", fmatrix.h:34-52) of the training data from the layout get_layout returns:
    feature f < num_users is the user's CSR row, feature item_offset + j the item's CSC row, entries {rating index, 1.0f} in

@@ -54,6 +54,7 @@ static const OptionDesc kOptions[] = {
     {"resident_max_user", &Options::resident_max_user, 1, RESIDENT_MAX, true},
     {"resident_max_item", &Options::resident_max_item, 1, RESIDENT_MAX, true},
     {"slice_len", &Options::slice_len, 0, 1 << 24, true},
+    {"relabel", &Options::relabel, 0, 1, true},
     {"group_rows", &Options::group_rows, 0, 1, false},
     {"row_kernels", &Options::row_kernels, 1, 3, false},
     {"alt_bins", &Options::alt_bins, 0, 1, false},
@@ -424,21 +425,61 @@ int sbmf_cuda_set_test(sbmf_handle* h, uint64_t nt, const uint32_t* user, const 
     return build_test(m, nt, user, item, rating);
 }
 
+static int layout_preamble(Model& m, const char* who)
+{
+    if (!m.have_train) {
+        m.err = std::string(who) + ": no training set";
+        return SBMF_ERR_STATE;
+    }
+    if (m.world > 1) {
+        m.err = std::string(who) + ": only the single-GPU handle keeps the global layout";
+        return SBMF_ERR_UNSUPPORTED;
+    }
+    API_CK(cudaSetDevice(m.device));
+    API_CK(cudaStreamSynchronize(m.s_main));
+    return SBMF_OK;
+}
+
 int sbmf_cuda_get_layout(sbmf_handle* h, int64_t* row_ptr, uint32_t* col, uint64_t* csr_id, int64_t* col_ptr, uint32_t* row, uint64_t* csc_id,
                          uint64_t* perm)
 {
     if (!h) return SBMF_ERR_INVALID;
     Model& m = h->m;
+    const int rc = layout_preamble(m, "get_layout");
+    if (rc != SBMF_OK) return rc;
+    // relabelled model (option relabel): the stored arrays are in position space and sorted within rows; [T]'s layout of the
+    // caller's ids is built from the restored COO by the same device sorts (storage.cu)
+    if (m.us.id_at) return export_reference_layout(m, row_ptr, col, csr_id, col_ptr, row, csc_id, perm);
+    return sbmf_cuda_get_storage_layout(h, row_ptr, col, csr_id, col_ptr, row, csc_id, perm);
+}
+
+int sbmf_cuda_get_row_positions(sbmf_handle* h, uint32_t* user_pos, uint32_t* item_pos)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
     if (!m.have_train) {
-        m.err = "get_layout: no training set";
+        m.err = "get_row_positions: no training set";
         return SBMF_ERR_STATE;
     }
-    if (m.world > 1) {
-        m.err = "get_layout: only the single-GPU handle keeps the global layout";
-        return SBMF_ERR_UNSUPPORTED;
-    }
     API_CK(cudaSetDevice(m.device));
-    API_CK(cudaStreamSynchronize(m.s_main));
+    uint32_t* out[2] = {user_pos, item_pos};
+    const Side* sd[2] = {&m.us, &m.it};
+    for (int q = 0; q < 2; ++q) {
+        if (!out[q]) continue;
+        if (sd[q]->pos_of) API_CK(cudaMemcpy(out[q], sd[q]->pos_of, (size_t)sd[q]->n * 4, cudaMemcpyDeviceToHost));
+        else
+            for (uint32_t r = 0; r < sd[q]->n; ++r) out[q][r] = r;
+    }
+    return SBMF_OK;
+}
+
+int sbmf_cuda_get_storage_layout(sbmf_handle* h, int64_t* row_ptr, uint32_t* col, uint64_t* csr_id, int64_t* col_ptr, uint32_t* row,
+                                 uint64_t* csc_id, uint64_t* perm)
+{
+    if (!h) return SBMF_ERR_INVALID;
+    Model& m = h->m;
+    const int rc = layout_preamble(m, "get_storage_layout");
+    if (rc != SBMF_OK) return rc;
     std::vector<uint32_t> tmp;
     if (row_ptr) API_CK(cudaMemcpy(row_ptr, m.us.ptr, ((size_t)m.I + 1) * 8, cudaMemcpyDeviceToHost));
     if (col_ptr) API_CK(cudaMemcpy(col_ptr, m.it.ptr, ((size_t)m.J + 1) * 8, cudaMemcpyDeviceToHost));
@@ -862,12 +903,24 @@ int sbmf_cuda_get_state(sbmf_handle* h, sbmf_state* out)
             API_CK(cudaStreamSynchronize(st));
         }
     }
-    if (out->b_i) API_CK(cudaMemcpy(out->b_i, m.us.bias, (size_t)m.I * 4, cudaMemcpyDeviceToHost));
-    if (out->b_j) API_CK(cudaMemcpy(out->b_j, m.it.bias, (size_t)m.J * 4, cudaMemcpyDeviceToHost));
-    if (out->mu_b_i) API_CK(cudaMemcpy(out->mu_b_i, m.us.mu_b, (size_t)m.I * 4, cudaMemcpyDeviceToHost));
-    if (out->sigma_b_i) API_CK(cudaMemcpy(out->sigma_b_i, m.us.sigma_b, (size_t)m.I * 4, cudaMemcpyDeviceToHost));
-    if (out->mu_b_j) API_CK(cudaMemcpy(out->mu_b_j, m.it.mu_b, (size_t)m.J * 4, cudaMemcpyDeviceToHost));
-    if (out->sigma_b_j) API_CK(cudaMemcpy(out->sigma_b_j, m.it.sigma_b, (size_t)m.J * 4, cudaMemcpyDeviceToHost));
+    {   // per-row arrays: stored by position, returned by the caller's row id
+        std::vector<float> byp;
+        auto row_out = [&](float* dst, const float* d_src, const Side& sd) -> cudaError_t {
+            if (!dst) return cudaSuccess;
+            if (sd.h_id_at.empty()) return cudaMemcpy(dst, d_src, (size_t)sd.n * 4, cudaMemcpyDeviceToHost);
+            byp.resize(sd.n);
+            const cudaError_t e = cudaMemcpy(byp.data(), d_src, (size_t)sd.n * 4, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess)
+                for (uint32_t p = 0; p < sd.n; ++p) dst[sd.h_id_at[p]] = byp[p];
+            return e;
+        };
+        API_CK(row_out(out->b_i, m.us.bias, m.us));
+        API_CK(row_out(out->b_j, m.it.bias, m.it));
+        API_CK(row_out(out->mu_b_i, m.us.mu_b, m.us));
+        API_CK(row_out(out->sigma_b_i, m.us.sigma_b, m.us));
+        API_CK(row_out(out->mu_b_j, m.it.mu_b, m.it));
+        API_CK(row_out(out->sigma_b_j, m.it.sigma_b, m.it));
+    }
     if (out->sigma_u) API_CK(cudaMemcpy(out->sigma_u, m.us.sigma_k, (size_t)m.K * 8, cudaMemcpyDeviceToHost));
     if (out->mu_u) API_CK(cudaMemcpy(out->mu_u, m.us.mu_k, (size_t)m.K * 8, cudaMemcpyDeviceToHost));
     if (out->sigma_v) API_CK(cudaMemcpy(out->sigma_v, m.it.sigma_k, (size_t)m.K * 8, cudaMemcpyDeviceToHost));
@@ -913,15 +966,24 @@ int sbmf_cuda_set_state(sbmf_handle* h, const sbmf_state* in)
     if (rc != SBMF_OK) return rc;
     cudaStream_t st = m.s_main;
     struct Up {
-        void* dst;
-        const void* src;
-        size_t bytes;
+        float* dst;
+        const float* src;
+        const Side* sd;
     };
-    const Up ups[] = {{m.us.bias, in->b_i, (size_t)m.I * 4},    {m.it.bias, in->b_j, (size_t)m.J * 4},
-                      {m.us.mu_b, in->mu_b_i, (size_t)m.I * 4}, {m.us.sigma_b, in->sigma_b_i, (size_t)m.I * 4},
-                      {m.it.mu_b, in->mu_b_j, (size_t)m.J * 4}, {m.it.sigma_b, in->sigma_b_j, (size_t)m.J * 4}};
-    for (const Up& u : ups)
-        if (u.src) API_CK(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, st));
+    const Up ups[] = {{m.us.bias, in->b_i, &m.us},    {m.it.bias, in->b_j, &m.it},        {m.us.mu_b, in->mu_b_i, &m.us},
+                      {m.us.sigma_b, in->sigma_b_i, &m.us}, {m.it.mu_b, in->mu_b_j, &m.it}, {m.it.sigma_b, in->sigma_b_j, &m.it}};
+    std::vector<float> byp[6];   // per-row arrays arrive by the caller's row id and are stored by position (alive until the sync below)
+    for (int q = 0; q < 6; ++q) {
+        const Up& u = ups[q];
+        if (!u.src) continue;
+        const float* src = u.src;
+        if (!u.sd->h_id_at.empty()) {
+            byp[q].resize(u.sd->n);
+            for (uint32_t p = 0; p < u.sd->n; ++p) byp[q][p] = u.src[u.sd->h_id_at[p]];
+            src = byp[q].data();
+        }
+        API_CK(cudaMemcpyAsync(u.dst, src, (size_t)u.sd->n * 4, cudaMemcpyHostToDevice, st));
+    }
     // per-dimension hyper-parameters: fp64 masters (the next sweep's Gamma step needs the OLD means, [T]:424, 450) and the fp32
     // mirrors the row kernels read; padding dimensions K..KP-1 get the values dim_hyper_final_kernel gives them (1, 0)
     std::vector<double> hd[4];

@@ -53,6 +53,7 @@ struct PhaseArgs {
     uint64_t seed;
     uint32_t site_f, site_b;
     const uint32_t* rows_of_hrow;   // heavy_rows of this side
+    const uint32_t* row_id;         // [n] caller's id of each row (Side::id_at; nullptr = identity): Philox keys of the row's draws
     int mode;          // SampleMode
     int apply_shift;   // user phase: add sc->shift_f on the first touch of e ([T]:407-410)
     // residual refresh fused into this phase (REFRESH kernels): while the blocks are processed the prediction
@@ -192,6 +193,7 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
     const uint32_t r_idx = (WARPS == 1) ? blockIdx.x * WPC + warp : blockIdx.x;
     if (r_idx >= nrows) return;   // WARPS == 1: whole warp leaves; no block-wide barrier is used in that shape
     const uint32_t row = rows[r_idx];
+    const uint32_t rid = a.row_id ? a.row_id[row] : row;   // the caller's id of this row: the key of its draws (relabelled models)
     const int64_t beg = a.ptr[row];
     const int c = (int)(a.ptr[row + 1] - beg);
     const int t_in_row = (WARPS == 1) ? lane : threadIdx.x;
@@ -265,7 +267,7 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         const float s = 1.0f / (sb + alpha * (float)c);
         const float mean = s * (sb * mb + alpha * (t + (float)c * bo));
         float z = 0.f;
-        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, rid, 0u, sweep));
         const float bn = draw_f32(mode, mean, s, z);
         const float d = bo - bn;
 #pragma unroll
@@ -285,7 +287,7 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
         const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
         // this row's noise, 4 blocks at a time: lane l draws dimension 32*(b/4) + l
         if (mode != SAMPLE_ZERO && (((b & 3) == 0) || b == b_begin))
-            zq = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)((b & ~3) * 8 + lane), sweep));
+            zq = normal_f32(philox_site(a.seed, a.site_f, rid, (uint32_t)((b & ~3) * 8 + lane), sweep));
         float acc[NACC];
         {
             GramAcc ga;
@@ -425,6 +427,7 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
     const uint32_t r_idx = (blockIdx.x * 4 + warp) * RPW + grp;
     const bool have_row = r_idx < nrows;                 // idle groups run along (the shuffles are warp-wide) but touch nothing
     const uint32_t row = rows[have_row ? r_idx : nrows - 1];
+    const uint32_t rid = a.row_id ? a.row_id[row] : row;   // the caller's id of this row: the key of its draws (relabelled models)
     const int64_t beg = a.ptr[row];
     const int c = have_row ? (int)(a.ptr[row + 1] - beg) : 0;
     float* tot = s_tot[warp * RPW + grp];
@@ -485,7 +488,7 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
         const float s = 1.0f / (sb + alpha * (float)c);
         const float mean = s * (sb * mb + alpha * (t + (float)c * bo));
         float z = 0.f;
-        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, rid, 0u, sweep));
         const float bn = draw_f32(mode, mean, s, z);
         const float d = bo - bn;
 #pragma unroll
@@ -504,7 +507,7 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
         const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
         // this row's noise, ZB blocks at a time: lane lg of the group draws dimension 8 * ZB * (b / ZB) + lg
         if (mode != SAMPLE_ZERO && (((b % ZB) == 0) || b == b_begin))
-            zq = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)((b - b % ZB) * 8 + lg), sweep));
+            zq = normal_f32(philox_site(a.seed, a.site_f, rid, (uint32_t)((b - b % ZB) * 8 + lg), sweep));
         float acc[NACC];
         {
             GramAcc ga;
@@ -601,6 +604,7 @@ __device__ SBMF_SOLVE_INLINE void heavy_row_solve(const PhaseArgs& a, uint32_t h
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t row = a.rows_of_hrow[hrow];
+    const uint32_t rid = a.row_id ? a.row_id[row] : row;   // the caller's id: key of the draws
     if (CUR == 1) {
         float t = 0.f;
         for (uint32_t s = s0 + threadIdx.x; s < s1; s += NW * 32) t += __ldcg(hpart + (size_t)s * NACC);
@@ -618,7 +622,7 @@ __device__ SBMF_SOLVE_INLINE void heavy_row_solve(const PhaseArgs& a, uint32_t h
         const float s = 1.0f / (sb + alpha * c);
         const float mean = s * (sb * mb + alpha * (t + c * bo));
         float z = 0.f;
-        if (a.mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        if (a.mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, rid, 0u, sweep));
         const float bn = draw_f32(a.mode, mean, s, z);
         __syncwarp();   // every lane has read the old bias (all lanes compute the same value, lane 0 stores it)
         if (lane == 0) {
@@ -639,7 +643,7 @@ __device__ SBMF_SOLVE_INLINE void heavy_row_solve(const PhaseArgs& a, uint32_t h
         const float alpha = a.sc->alpha_f;
         const uint32_t sweep = a.sc->sweep;
         float zl = 0.f;
-        if (a.mode != SAMPLE_ZERO && lane < 8) zl = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)(b * 8 + lane), sweep));
+        if (a.mode != SAMPLE_ZERO && lane < 8) zl = normal_f32(philox_site(a.seed, a.site_f, rid, (uint32_t)(b * 8 + lane), sweep));
         a0 = 0.f;
         a1 = 0.f;
 #pragma unroll
@@ -1129,16 +1133,18 @@ dim_hyper_final_kernel(const double* __restrict__ part, uint32_t chunks, uint32_
 // Per-row bias hyper-parameters [T]:469-511.
 __global__ void __launch_bounds__(256)
 bias_hyper_kernel(const float* __restrict__ bias, float* __restrict__ mu_b, float* __restrict__ sigma_b, uint32_t n, const Scalars* sc,
-                  double pa, double pb, double pmu, double psigma, int mode, uint64_t seed, uint32_t site_sigma, uint32_t site_mu)
+                  double pa, double pb, double pmu, double psigma, int mode, uint64_t seed, uint32_t site_sigma, uint32_t site_mu,
+                  const uint32_t* __restrict__ row_id)
 {
     const uint32_t r = blockIdx.x * 256 + threadIdx.x;
     if (r >= n) return;
+    const uint32_t rid = row_id ? row_id[r] : r;   // draws are keyed by the caller's row id
     const uint32_t sweep = sc->sweep;
     const double b = (double)bias[r], mo = (double)mu_b[r];
-    const double sig = draw_gamma_f64(mode, seed, site_sigma, r, sweep, pa + 1.0, pb + 0.5 * (b - mo) * (b - mo));
+    const double sig = draw_gamma_f64(mode, seed, site_sigma, rid, sweep, pa + 1.0, pb + 0.5 * (b - mo) * (b - mo));
     const double s = 1.0 / (psigma + sig);
     const double m = s * (psigma * pmu + b * sig);
-    const double mu = draw_gauss_f64(mode, seed, site_mu, r, 0, sweep, m, s);
+    const double mu = draw_gauss_f64(mode, seed, site_mu, rid, 0, sweep, m, s);
     sigma_b[r] = (float)sig;
     mu_b[r] = (float)mu;
 }
@@ -1205,7 +1211,8 @@ eval_final_kernel(Scalars* sc, const double* __restrict__ out, uint64_t Nt, doub
 // --------------------------------------------------------------------------------------------------------
 // Factor layout conversion / initialisation.
 __global__ void __launch_bounds__(256)
-init_factors_kernel(float* __restrict__ F, uint32_t n, uint32_t K, uint32_t KB, uint64_t seed, uint32_t site, float stdev)
+init_factors_kernel(float* __restrict__ F, uint32_t n, uint32_t K, uint32_t KB, uint64_t seed, uint32_t site, float stdev,
+                    const uint32_t* __restrict__ row_id)
 {
     const uint32_t nreal = n - 1;   // n = stride = rows + 1 zero pad row
     const uint64_t total = (uint64_t)KB * n * 8;
@@ -1214,12 +1221,13 @@ init_factors_kernel(float* __restrict__ F, uint32_t n, uint32_t K, uint32_t KB, 
         const uint64_t br = t >> 3;
         const uint32_t row = (uint32_t)(br % n), b = (uint32_t)(br / n);
         const uint32_t k = b * 8 + k8;
-        F[t] = (k < K && row < nreal) ? stdev * normal_f32(philox_site(seed, site, row, k, 0u)) : 0.f;
+        F[t] = (k < K && row < nreal) ? stdev * normal_f32(philox_site(seed, site, row_id ? row_id[row] : row, k, 0u)) : 0.f;
     }
 }
 
 __global__ void __launch_bounds__(256)
-load_factors_kernel(float* __restrict__ F, const float* __restrict__ src, uint32_t n, uint32_t K, uint32_t KB, int dim_major)
+load_factors_kernel(float* __restrict__ F, const float* __restrict__ src, uint32_t n, uint32_t K, uint32_t KB, int dim_major,
+                    const uint32_t* __restrict__ row_id)
 {
     const uint32_t nreal = n - 1;   // n = stride = rows + 1 zero pad row
     const uint64_t total = (uint64_t)KB * n * 8;
@@ -1229,13 +1237,17 @@ load_factors_kernel(float* __restrict__ F, const float* __restrict__ src, uint32
         const uint32_t row = (uint32_t)(br % n), b = (uint32_t)(br / n);
         const uint32_t k = b * 8 + k8;
         float v = 0.f;
-        if (k < K && row < nreal) v = dim_major ? src[(size_t)k * nreal + row] : src[(size_t)row * K + k];
+        if (k < K && row < nreal) {
+            const uint32_t sr = row_id ? row_id[row] : row;   // src is in the caller's row order
+            v = dim_major ? src[(size_t)k * nreal + sr] : src[(size_t)sr * K + k];
+        }
         F[t] = v;
     }
 }
 
 __global__ void __launch_bounds__(256)
-export_factors_kernel(const float* __restrict__ F, float* __restrict__ dst, uint32_t n, uint32_t K, int dim_major)
+export_factors_kernel(const float* __restrict__ F, float* __restrict__ dst, uint32_t n, uint32_t K, int dim_major,
+                      const uint32_t* __restrict__ pos_of)
 {
     const uint64_t total = (uint64_t)n * K;
     for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
@@ -1247,7 +1259,7 @@ export_factors_kernel(const float* __restrict__ F, float* __restrict__ dst, uint
             row = (uint32_t)(t / K);
             k = (uint32_t)(t % K);
         }
-        dst[t] = F[((size_t)(k >> 3) * (n + 1) + row) * 8 + (k & 7)];
+        dst[t] = F[((size_t)(k >> 3) * (n + 1) + (pos_of ? pos_of[row] : row)) * 8 + (k & 7)];
     }
 }
 
@@ -1306,21 +1318,21 @@ static inline uint32_t grid_for(uint64_t n, int threads, int cap)
 void launch_init_factors(Model& m, Side& s, uint32_t site, cudaStream_t st)
 {
     const uint64_t total = (uint64_t)m.KB * (s.n + 1) * 8;
-    SBMF_LAUNCH((init_factors_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, st, s.F, s.n + 1, m.K, m.KB, m.cfg.seed, site, (float)m.cfg.init_stdev);
+    SBMF_LAUNCH((init_factors_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, st, s.F, s.n + 1, m.K, m.KB, m.cfg.seed, site, (float)m.cfg.init_stdev, s.id_at);
     m.launches++;
 }
 
 void launch_load_factors(Model& m, Side& s, const float* d_src, bool dim_major, cudaStream_t st)
 {
     const uint64_t total = (uint64_t)m.KB * (s.n + 1) * 8;
-    SBMF_LAUNCH((load_factors_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, st, s.F, d_src, s.n + 1, m.K, m.KB, dim_major ? 1 : 0);
+    SBMF_LAUNCH((load_factors_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, st, s.F, d_src, s.n + 1, m.K, m.KB, dim_major ? 1 : 0, s.id_at);
     m.launches++;
 }
 
 void launch_export_factors(Model& m, const Side& s, float* d_out, bool dim_major, cudaStream_t st)
 {
     const uint64_t total = (uint64_t)s.n * m.K;
-    SBMF_LAUNCH((export_factors_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, st, s.F, d_out, s.n, m.K, dim_major ? 1 : 0);
+    SBMF_LAUNCH((export_factors_kernel), grid_for(total, 256, m.sm_count * 16), 256, 0, st, s.F, d_out, s.n, m.K, dim_major ? 1 : 0, s.pos_of);
     m.launches++;
 }
 
@@ -1366,7 +1378,7 @@ void launch_bias_hypers(Model& m, cudaStream_t st)
     for (Side* s : {&m.us, &m.it}) {
         SBMF_LAUNCH((bias_hyper_kernel), (s->n + 255) / 256, 256, 0, st, s->bias, s->mu_b, s->sigma_b, s->n, m.sc, p.alpha[s->prior_b], p.beta[s->prior_b],
                                                               p.mu[s->prior_b], p.sigma[s->prior_b], m.cfg.sample_mode, m.cfg.seed,
-                                                              s->site_sigma_b, s->site_mu_b);
+                                                              s->site_sigma_b, s->site_mu_b, s->id_at);
         m.launches++;
     }
 }
@@ -1438,6 +1450,7 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
     a.pacc = m.pacc;
     a.KBtot = (int)m.KB;
     a.rows_of_hrow = self.heavy_rows;
+    a.row_id = self.id_at;
     a.ptr = self.ptr;
     a.idx = self.idx;
     a.e = self.e;

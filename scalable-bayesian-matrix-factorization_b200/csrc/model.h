@@ -51,6 +51,12 @@ struct Slice {
 // One side of the model: users with the CSR layout, or items with the CSC layout.
 struct Side {
     uint32_t n = 0;                   // rows on this side (I or J)
+    // Row relabelling (option relabel, storage.cu): every array of the model is indexed by a row's POSITION, positions ordered by
+    // decreasing number of ratings.  id_at[pos] = the caller's row id (Philox keys, exports), pos_of[id] = position (imports).
+    // nullptr = identity (relabel off).
+    uint32_t* id_at = nullptr;        // [n]
+    uint32_t* pos_of = nullptr;       // [n]
+    std::vector<uint32_t> h_id_at;    // host copy of id_at (empty = identity)
     int64_t* ptr = nullptr;           // [n+1]
     uint32_t* idx = nullptr;          // [N] opposite-side id of each slot
     float* e = nullptr;               // [N] residual e_ij in this side's slot order
@@ -87,6 +93,8 @@ struct Options {
     int64_t resident_max = RESIDENT_MAX;   // rows longer than this stream through the sliced pipeline (<= RESIDENT_MAX); sets both sides
     int64_t resident_max_user = RESIDENT_MAX, resident_max_item = RESIDENT_MAX;   // ... per side
     int64_t slice_len = 0;        // heavy-row slice length; 0 = chosen from the shard size (build_worklists)
+    int64_t relabel = 1;          // rows stored in order of decreasing rating count (adjacent lanes of a gather then share 128-byte lines
+                                  // on the popular rows); 0 = the caller's ids.  Draws are keyed by the caller's ids either way
     int64_t group_rows = 1;       // short rows: several rows per warp (row_group_kernel); 0 = one warp per row
     int64_t row_kernels = 1;      // resident rows: 1 = shuffle reduction (kernels.cu), 2 = rows2.cuh (shared-memory reduction, one barrier per block; measured slower, A/B)
     int64_t alt_bins = 1;         // resident rows of 193..512 ratings: 2 warps x (6 | 8) per lane (rows2.cuh) instead of 4 warps x (3 | 4); measured 12.19 -> 11.77 ms user phase
@@ -185,6 +193,7 @@ void free_storage(Model& m);
 void free_test(Model& m);
 
 // ---- kernels.cu: launch wrappers (all asynchronous on the given stream)
+int export_reference_layout(Model& m, int64_t* row_ptr, uint32_t* col, uint64_t* csr_id, int64_t* col_ptr, uint32_t* row, uint64_t* csc_id, uint64_t* perm);
 void init_constant_tables();   // once per device, after cudaSetDevice
 void launch_init_factors(Model& m, Side& s, uint32_t site, cudaStream_t st);
 // host layout -> K8-blocked.  dim_major: src is [K][n] (V of [T]:234-237), else [n][K] (U of [T]:229-232)

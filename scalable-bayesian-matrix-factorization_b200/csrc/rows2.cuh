@@ -228,6 +228,7 @@ row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nr
     const uint32_t r_idx = (WARPS == 1) ? blockIdx.x * WPC + warp : blockIdx.x;
     if (r_idx >= nrows) return;   // WARPS == 1: whole warp leaves; no block-wide barrier is used in that shape
     const uint32_t row = rows[r_idx];
+    const uint32_t rid = a.row_id ? a.row_id[row] : row;   // the caller's id of this row: the key of its draws (relabelled models)
     const int64_t beg = a.ptr[row];
     const int c = (int)(a.ptr[row + 1] - beg);
     const int t_in_row = (WARPS == 1) ? lane : threadIdx.x;
@@ -309,7 +310,7 @@ row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nr
         const float s = 1.0f / (sb + alpha * (float)c);
         const float mean = s * (sb * mb + alpha * (t + (float)c * bo));
         float z = 0.f;
-        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, rid, 0u, sweep));
         const float bn = draw_f32(mode, mean, s, z);
         const float d = bo - bn;
 #pragma unroll
@@ -329,7 +330,7 @@ row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nr
         const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
         // this row's noise, 4 blocks at a time: lane l draws dimension 32*(b/4) + l
         if (mode != SAMPLE_ZERO && (((b & 3) == 0) || b == b_begin))
-            zq = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)((b & ~3) * 8 + lane), sweep));
+            zq = normal_f32(philox_site(a.seed, a.site_f, rid, (uint32_t)((b & ~3) * 8 + lane), sweep));
         GramAcc ga;
         ga.clear();
 #pragma unroll
@@ -427,6 +428,7 @@ row_group2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows
     const uint32_t r_idx = (blockIdx.x * 4 + warp) * RPW + grp;
     const bool have_row = r_idx < nrows;                 // idle groups run along (the shuffles are warp-wide) but touch nothing
     const uint32_t row = rows[have_row ? r_idx : nrows - 1];
+    const uint32_t rid = a.row_id ? a.row_id[row] : row;   // the caller's id of this row: the key of its draws (relabelled models)
     const int64_t beg = a.ptr[row];
     const int c = have_row ? (int)(a.ptr[row + 1] - beg) : 0;
     float* tot = s_tot[warp * RPW + grp];
@@ -490,7 +492,7 @@ row_group2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows
         const float s = 1.0f / (sb + alpha * (float)c);
         const float mean = s * (sb * mb + alpha * (t + (float)c * bo));
         float z = 0.f;
-        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, row, 0u, sweep));
+        if (mode != SAMPLE_ZERO) z = normal_f32(philox_site(a.seed, a.site_b, rid, 0u, sweep));
         const float bn = draw_f32(mode, mean, s, z);
         const float d = bo - bn;
 #pragma unroll
@@ -509,7 +511,7 @@ row_group2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows
         const float sig = a.sigma_kf[b * 8 + kq], mu = a.mu_kf[b * 8 + kq];
         // this row's noise, ZB blocks at a time: lane lg of the group draws dimension 8 * ZB * (b / ZB) + lg
         if (mode != SAMPLE_ZERO && (((b % ZB) == 0) || b == b_begin))
-            zq = normal_f32(philox_site(a.seed, a.site_f, row, (uint32_t)((b - b % ZB) * 8 + lg), sweep));
+            zq = normal_f32(philox_site(a.seed, a.site_f, rid, (uint32_t)((b - b % ZB) * 8 + lg), sweep));
         GramAcc ga;
         ga.clear();
 #pragma unroll

@@ -157,6 +157,8 @@ def load_library(path=None):
     lib.sbmf_cuda_set_train.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     lib.sbmf_cuda_set_test.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sbmf_cuda_get_layout.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    lib.sbmf_cuda_get_storage_layout.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    lib.sbmf_cuda_get_row_positions.argtypes = [C.c_void_p] * 3
     lib.sbmf_cuda_init_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sbmf_cuda_get_state.argtypes = [C.c_void_p, P(State)]
     lib.sbmf_cuda_set_state.argtypes = [C.c_void_p, P(State)]
@@ -266,6 +268,16 @@ class SbmfModel:
                "col_ptr": np.empty(J + 1, np.int64), "row": np.empty(N, np.uint32), "csc_id": np.empty(N, np.uint64),
                "perm": np.empty(N, np.uint64)}
         self._ck(self.lib.sbmf_cuda_get_layout(self.h, *[_ptr(out[k]) for k in ("row_ptr", "col", "csr_id", "col_ptr", "row", "csc_id", "perm")]))
+        return out
+
+    def get_storage_layout(self):
+        """The arrays the kernels run on (position space when option relabel is on) + the row positions of the caller's ids."""
+        N, I, J = self.N, self.I, self.J
+        out = {"row_ptr": np.empty(I + 1, np.int64), "col": np.empty(N, np.uint32), "csr_id": np.empty(N, np.uint64),
+               "col_ptr": np.empty(J + 1, np.int64), "row": np.empty(N, np.uint32), "csc_id": np.empty(N, np.uint64),
+               "perm": np.empty(N, np.uint64), "user_pos": np.empty(I, np.uint32), "item_pos": np.empty(J, np.uint32)}
+        self._ck(self.lib.sbmf_cuda_get_storage_layout(self.h, *[_ptr(out[k]) for k in ("row_ptr", "col", "csr_id", "col_ptr", "row", "csc_id", "perm")]))
+        self._ck(self.lib.sbmf_cuda_get_row_positions(self.h, _ptr(out["user_pos"]), _ptr(out["item_pos"])))
         return out
 
     def init_factors(self, U0=None, V0=None):

@@ -54,6 +54,52 @@ def test_layout_bit_exact(case, ml100k, tiny):
     m.close()
 
 
+def relabelled_layout(d):
+    """What storage.cu builds with option relabel = 1 on one GPU, restated in numpy: positions by decreasing rating count (ties
+    by id), CSR sorted by (user position, item position, file order), CSC by (item position, user position, file order)."""
+    u, v = d["train_user"].astype(np.int64), d["train_item"].astype(np.int64)
+    I, J, n = d["num_users"], d["num_items"], u.size
+    pos = []
+    for ids, nr in ((u, I), (v, J)):
+        deg = np.bincount(ids, minlength=nr)
+        by_rank = np.argsort(-deg, kind="stable")
+        p = np.empty(nr, np.int64)
+        p[by_rank] = np.arange(nr)
+        pos.append(p)
+    up, vp = pos[0][u], pos[1][v]
+    idx = np.arange(n)
+    csr = np.lexsort((idx, vp, up))
+    csc = np.lexsort((idx, up, vp))
+    inv = np.empty(n, np.int64)
+    inv[csr] = np.arange(n)
+    row_ptr = np.concatenate([[0], np.cumsum(np.bincount(up, minlength=I))])
+    col_ptr = np.concatenate([[0], np.cumsum(np.bincount(vp, minlength=J))])
+    return {"row_ptr": row_ptr, "col": vp[csr], "csr_id": csr, "col_ptr": col_ptr, "row": up[csc], "csc_id": csc, "perm": inv[csc],
+            "user_pos": pos[0], "item_pos": pos[1]}
+
+
+@pytest.mark.parametrize("relabel", [0, 1])
+@pytest.mark.parametrize("case", ["ml100k", "tiny"])
+def test_storage_layout_bit_exact(case, relabel, ml100k, tiny):
+    """The arrays the kernels run on.  relabel = 0: [T]'s layout itself.  relabel = 1 (default): the position-space layout of
+    storage.cu, against its numpy restatement; and get_layout still returns [T]'s layout of the caller's ids."""
+    import sbmf
+    d = ml100k if case == "ml100k" else tiny
+    m = sbmf.SbmfModel(K=8, options={"relabel": relabel})
+    m.set_train(d["train_user"], d["train_item"], d["train_rating"], d["num_users"], d["num_items"])
+    o = orc.Oracle(d["train_user"], d["train_item"], d["train_rating"], d["test_user"], d["test_item"], d["test_rating"], d["num_users"],
+                   d["num_items"], 8, noise=orc.NOISE_ZERO)
+    ref = o.layout()
+    got = m.get_layout()
+    for k in ("row_ptr", "col", "csr_id", "col_ptr", "row", "csc_id", "perm"):
+        assert np.array_equal(got[k], ref[k]), k
+    st = m.get_storage_layout()
+    want = dict(ref, user_pos=np.arange(d["num_users"]), item_pos=np.arange(d["num_items"])) if relabel == 0 else relabelled_layout(d)
+    for k in ("user_pos", "item_pos", "row_ptr", "col", "csr_id", "col_ptr", "row", "csc_id", "perm"):
+        assert np.array_equal(st[k].astype(np.int64), np.asarray(want[k]).astype(np.int64)), (relabel, k)
+    m.close()
+
+
 # ------------------------------------------------------------------------------------------ zero-noise parity
 def check_state(gs, os_, tol, what=("U", "V", "b_i", "b_j", "mu_b_i", "sigma_b_i", "mu_b_j", "sigma_b_j", "sigma_u", "mu_u", "sigma_v", "mu_v")):
     worst = {}
@@ -523,6 +569,10 @@ OPTION_SETS = [
     {"pair_gather": 1, "resident_max": 128},            # streamed rows gather (previous, current) block as one 64-byte row by lane pairs
     {"fuse_solve": 1, "resident_max": 128},             # streamed rows: updates in the tail of the pass (last slice CTA of the row) instead of a launch of their own
     {"resident_max_user": 64, "resident_max_item": 1024},
+    {"relabel": 0},                                     # rows under the caller's ids instead of positions by decreasing rating count
+    {"relabel": 0, "alt_bins": 0, "row_kernels": 1},    # the round-1 resident-row kernels throughout
+    {"row_kernels": 2}, {"row_kernels": 3},             # rows2.cuh: shared-memory reduction / one-barrier structure with the shuffle tree
+    {"row_kernels": 2, "alt_bins": 0, "max_blocks_per_launch": 3, "relabel": 0},
 ]
 
 
