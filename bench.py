@@ -306,17 +306,19 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def load_traffic():
+def load_traffic(want_ncu=False):
     """measured DRAM bytes per rating of the dominant kernel (ncu --set full, profiles/): newest round first"""
     for name in ("traffic_r2.json", "traffic_r1.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             t = json.load(open(p)).get("heavy_accumulate_kernel<2,2>", {})
+            if want_ncu:
+                return {k: t[k] for k in ("l1tex_data_pipe_lsu_wavefronts_pct", "lts_t_sectors_srcunit_tex_pct", "l1tex_sectors_global_ld", "duration_us_under_ncu", "source") if k in t}
             if t.get("dram_bytes_per_rating"):
                 return float(t["dram_bytes_per_rating"]), name
             if t.get("dram_bytes_per_launch") and t.get("ratings_per_launch"):
                 return float(t["dram_bytes_per_launch"]) / float(t["ratings_per_launch"]), name
-    return None, None
+    return {} if want_ncu else (None, None)
 
 
 def build_roofline(t, pr, peak_hbm, peak_src, K, KB, ms_per_step, n_test, world):
@@ -352,9 +354,13 @@ def build_roofline(t, pr, peak_hbm, peak_src, K, KB, ms_per_step, n_test, world)
                 "traffic": per_rating * R if per_rating else None, "us_per_launch": us, "launches_timed": int(t["top_kernel_launches"]),
                 "units_per_launch": f"{int(R)} ratings x 8 dimensions (this rank)", "hbm": hbm, "l2_gather": l2,
                 "frac_survey_8d": survey,
-                "note": "frac_survey_8d prices the launch by SURVEY 8(d) (12 B per rating x DIMENSION, the reference's per-dimension "
-                        "formulation); the Gram-blocked kernel streams idx/e once per 8 dimensions, so that figure exceeds 1 and is kept only "
-                        "for comparison -- the binding resource is the L2 -> SM gather path"}
+                "ncu_committed": load_traffic(want_ncu=True),
+                "note": "the binding unit is the SM's L1TEX data pipe: a scattered 32-byte sector costs one wavefront there (ncu_committed: "
+                        "pipe utilisation of this kernel under ncu; the live figure is l2_gather: sectors delivered per second against the "
+                        "rates sbmf_cuda_probe measured in this run -- frac_same_form above 1 means adjacent lanes share lines on the popular "
+                        "rows, which the probe's random ids never do).  frac_survey_8d prices the launch by SURVEY 8(d) (12 B per rating x "
+                        "DIMENSION, the reference's per-dimension formulation); the Gram-blocked kernel streams idx/e once per 8 dimensions, so "
+                        "that figure exceeds 1 and is kept only for comparison"}
     # whole sweep: sector gathers issued by the phases + evaluation against the same probed rates
     sect_sweep = KB * (t["nnz_light_user"] + 2.0 * t["nnz_heavy_user"] + t["nnz_light_item"] + 2.0 * t["nnz_heavy_item"]) + 2.0 * KB * n_test / world
     s = ms_per_step * 1e-3
