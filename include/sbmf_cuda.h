@@ -159,7 +159,7 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
                           pair array instead of two sector gathers (measured slower on sorted rating rows)   [before set_train]
      fuse_solve    (0)    streamed rows: the row updates run in the tail of each pass, by the last slice CTA of the row, instead of
                           a launch of their own (halves the launch count of a phase; measured slower on one GPU)
-     fold_user / fold_item (1 / 0)  one GPU: residual hand-over between the slot orders folded into the phase's first touch
+     fold_user / fold_item (1 / 1)  one GPU: residual hand-over between the slot orders folded into the phase's first touch
      graph         (1)    steady-state sweep replayed from a CUDA graph when per-phase timing is off
      device_plan   (1)    multi-GPU: exchange plan computed on the device (0: host planner)  [before set_train]
      mgpu_pool     (1)    multi-GPU: rating-sized arrays from the stream-ordered pool        [before set_train]

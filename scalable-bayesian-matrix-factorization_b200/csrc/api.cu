@@ -559,9 +559,9 @@ static int enqueue_sweep(Model& m, bool timing)
     // One GPU: the residual changes slot order (CSR <-> CSC) between the phases.  CSC -> CSR (before the user phase) is not
     // a pass of its own: the first touch of e in the user phase reads it through the inverse permutation from the item side's
     // array (PhaseArgs::e_map), where the gather hides behind the factor gathers (measured on the Netflix-shaped matrix:
-    // -0.9 ms for the pass, +0.4 ms in the phase).  The other direction stays a stand-alone pass by default: the item phase is
-    // dominated by the streaming pipeline, whose first pass is pure streaming and turns HBM-sector-bound with the gather
-    // (-0.5 ms, +0.7 ms).  Options fold_user / fold_item switch either (A/B measurements, tests).
+    // -0.9 ms for the pass, +0.4 ms in the phase).  The other direction was a stand-alone pass in round 1 (the first streaming pass
+    // turns HBM-sector-bound with the gather: -0.5 ms, +0.7 ms); on the relabelled layout of round 2 it is folded as well
+    // (-0.61 ms for the pass, +0.41 ms in the phase).  Options fold_user / fold_item switch either (A/B measurements, tests).
     const bool fold_user = m.world == 1 && m.opt.fold_user;
     const bool fold = m.world == 1 && m.opt.fold_item;
     bool user_mapped = false;

@@ -141,6 +141,30 @@ __device__ __forceinline__ void st256(float* p, const f8& r)
 }
 #endif
 
+// Streaming accesses (index / residual / rating streams that are touched once per pass): -DSBMF_STREAM_HINTS=1 marks them
+// evict-first (ld.global.cs / st.global.cs) so that they do not displace the gathered factor block from L1 / L2.
+#ifndef SBMF_STREAM_HINTS
+#define SBMF_STREAM_HINTS 0
+#endif
+template <class T>
+__device__ __forceinline__ T ld_stream(const T* p)
+{
+#if SBMF_STREAM_HINTS && !defined(SBMF_SIMT_EMU)
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <class T>
+__device__ __forceinline__ void st_stream(T* p, T v)
+{
+#if SBMF_STREAM_HINTS && !defined(SBMF_SIMT_EMU)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // Reduce 48 per-lane values over the warp with 48 shuffles instead of 48*5: each step halves the vector a lane
 // still carries (the lane keeps one half and ships the other to its partner).  On return v[0..2] of every lane
 // hold the warp totals of the original entries reduce_scatter_base(lane) + {0,1,2}; lanes l and l^1 hold the

@@ -810,9 +810,9 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, float* __
             for (int u = 0; u < UNR; ++u) {
                 const uint32_t i = base + u * THREADS;
                 const bool ok = i < sl.len;
-                idn[u] = ok ? idx[i] : pad_row;
-                en[u] = ok ? ((PREV == 0) ? load_e_first(a, (int64_t)sl.start + i) : ep[i]) : 0.f;
-                if (REFRESH && PREV == 2) prn[u] = (ok && pb > 0) ? pp[i] : 0.f;
+                idn[u] = ok ? ld_stream(idx + i) : pad_row;
+                en[u] = ok ? ((PREV == 0) ? load_e_first(a, (int64_t)sl.start + i) : ld_stream(ep + i)) : 0.f;
+                if (REFRESH && PREV == 2) prn[u] = (ok && pb > 0) ? ld_stream(pp + i) : 0.f;
             }
         };
         fetch(threadIdx.x);
@@ -849,10 +849,10 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, float* __
                     if (REFRESH && PREV == 2) pr[u] += dot8(fp[u], unprev);
                 }
                 if (REFRESH && PREV == 2) {
-                    if (CUR == 0) e[u] = (i < sl.len) ? rp[i] - (row_const + a.bias_other[id[u]] + pr[u]) : 0.f;   // phase done: fresh residual
-                    else if (i < sl.len) pp[i] = pr[u];
+                    if (CUR == 0) e[u] = (i < sl.len) ? ld_stream(rp + i) - (row_const + a.bias_other[id[u]] + pr[u]) : 0.f;   // phase done: fresh residual
+                    else if (i < sl.len) st_stream(pp + i, pr[u]);
                 }
-                if (i < sl.len) ep[i] = e[u];
+                if (i < sl.len) st_stream(ep + i, e[u]);
                 if (CUR == 1 && i < sl.len) acc[0] += e[u];
                 if (CUR == 2) ga.add(fc[u], e[u]);
             }

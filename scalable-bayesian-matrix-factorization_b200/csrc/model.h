@@ -102,7 +102,7 @@ struct Options {
     int64_t fuse_solve = 0;       // streaming pipeline: row updates in the tail of each pass by the row's last slice CTA (0: a launch of
                                   // their own; measured on B200: the release fence + ticket per slice CTA costs 160 us per pass, a launch 55)
     int64_t fold_user = 1;        // one GPU: CSC->CSR residual hand-over folded into the user phase's first touch
-    int64_t fold_item = 0;        // one GPU: CSR->CSC hand-over folded into the item phase's first touch
+    int64_t fold_item = 1;        // one GPU: CSR->CSC hand-over folded into the item phase's first touch (22.46 -> 22.27 ms per sweep)
     int64_t graph = 1;            // replay the steady-state sweep from a CUDA graph when per-phase timing is off
     int64_t device_plan = 1;      // multi-GPU: exchange plan computed on the device (0 = host planner, plan.cpp)
     int64_t mgpu_pool = 1;        // multi-GPU: rating-sized arrays from the stream-ordered pool (0 = cudaMalloc)

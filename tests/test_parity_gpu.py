@@ -562,9 +562,9 @@ def test_ng_mode_live_same_streams(ml100k):
 OPTION_SETS = [
     {"max_blocks_per_launch": 1},                       # every block a launch of its own: b_begin > 0 continuation, pacc round trips
     {"max_blocks_per_launch": 2, "group_rows": 0},      # ... and short rows on the one-warp-per-row kernel
-    {"fold_user": 0}, {"fold_item": 1},                 # residual hand-over between the slot orders: stand-alone pass <-> folded
+    {"fold_user": 0}, {"fold_item": 0}, {"fold_user": 0, "fold_item": 0},   # residual hand-over between the slot orders: stand-alone pass <-> folded
     {"resident_max": 64, "slice_len": 256},             # most rows through the sliced streaming pipeline, many slices per row
-    {"resident_max": 300, "slice_len": 1024, "max_blocks_per_launch": 1, "fold_item": 1},
+    {"resident_max": 300, "slice_len": 1024, "max_blocks_per_launch": 1, "fold_item": 0},
     {"graph": 0},
     {"pair_gather": 1, "resident_max": 128},            # streamed rows gather (previous, current) block as one 64-byte row by lane pairs
     {"fuse_solve": 1, "resident_max": 128},             # streamed rows: updates in the tail of the pass (last slice CTA of the row) instead of a launch of their own

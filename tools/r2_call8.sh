@@ -20,7 +20,7 @@ except Exception as ex:
 E
 }
 run netflix_k100 29531 --steps 20 --warmup 3
-run netflix_k100_fused 29532 --steps 20 --warmup 3 --no-e2e --no-parity --options fuse_solve=1
+run netflix_k100_norelabel 29532 --steps 20 --warmup 3 --no-e2e --no-parity --options relabel=0
 run netflix_k50 29533 --steps 20 --warmup 3 --workload netflix_k50 --no-parity
 run netflix_k200 29534 --steps 20 --warmup 3 --workload netflix_k200 --no-parity
 if [ "$N" = "8" ]; then
