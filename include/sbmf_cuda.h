@@ -163,6 +163,10 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
      graph         (1)    steady-state sweep replayed from a CUDA graph when per-phase timing is off
      device_plan   (1)    multi-GPU: exchange plan computed on the device (0: host planner)  [before set_train]
      mgpu_pool     (1)    multi-GPU: rating-sized arrays from the stream-ordered pool        [before set_train]
+     fuse_exchange (0)    multi-GPU with peer pushes: the user phase writes its final residual straight into the receive buffer of
+                          the rank owning the rating's item and the item phase reads it in place (0: push kernel + barrier +
+                          unpack kernel between the phases; measured faster: peer stores from inside the phase kernels cost
+                          more than the two kernels they replace)                            [before set_train]
      peer          (1)    multi-GPU: peer-mapped replicas + direct NVLink pushes (0: NCCL)   [before set_train]
      trace         (0)    stage times of set_train on stderr
    Unknown name or value out of range: SBMF_ERR_INVALID; a [before set_train] option after set_train: SBMF_ERR_STATE. */

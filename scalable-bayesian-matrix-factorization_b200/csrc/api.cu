@@ -65,6 +65,7 @@ static const OptionDesc kOptions[] = {
     {"graph", &Options::graph, 0, 1, false},
     {"device_plan", &Options::device_plan, 0, 1, true},
     {"mgpu_pool", &Options::mgpu_pool, 0, 1, true},
+    {"fuse_exchange", &Options::fuse_exchange, 0, 1, true},
     {"peer", &Options::peer, 0, 1, true},
     {"trace", &Options::trace, 0, 2, false},
 };
@@ -582,12 +583,17 @@ static int enqueue_sweep(Model& m, bool timing)
     // peer-mapped replicas: the user phase writes U rows into every replica, so every rank must be done reading U first
     if (m.peer_ok) crc |= launch_barrier(m, st);
     if (timing) cudaEventRecord(m.ev_t[2], st);
-    launch_phase(m, m.us, m.it, true, fused, user_mapped ? m.it.e : nullptr, user_mapped ? m.perm_inv : nullptr);   // [T]:514-558 (+ the fused residual refresh)
+    // G GPUs with peer pushes (option fuse_exchange): the user phase stores its final residual straight into the receive buffer of
+    // the rank that owns the rating's item (PhaseArgs::xmap), overlapped with the phase; what is left between the phases is the
+    // barrier (every peer's residuals and U rows have landed), and the item phase reads through recv_pos like a folded hand-over
+    const bool fx = m.world > 1 && m.peer_ok && m.opt.fuse_exchange && m.xmap_fwd;
+    launch_phase(m, m.us, m.it, true, fused, user_mapped ? m.it.e : nullptr, user_mapped ? m.perm_inv : nullptr, fx);   // [T]:514-558 (+ the fused residual refresh)
     if (timing) cudaEventRecord(m.ev_t[3], st);
     // residual CSR order -> CSC order; multi-GPU: all-to-all grouped with the all-gather of the updated U rows and user biases
-    if (!fold) crc |= launch_permute(m, true, &m.us, st);
+    if (fx) crc |= launch_barrier(m, st);
+    else if (!fold) crc |= launch_permute(m, true, &m.us, st);
     if (timing) cudaEventRecord(m.ev_t[4], st);
-    launch_phase(m, m.it, m.us, false, false, fold ? m.us.e : nullptr, fold ? m.perm : nullptr);       // [T]:563-606
+    launch_phase(m, m.it, m.us, false, false, fx ? m.recvbuf : (fold ? m.us.e : nullptr), fx ? m.recv_pos : (fold ? m.perm : nullptr));   // [T]:563-606
     m.e_in_csc = true;
     if (timing) cudaEventRecord(m.ev_t[5], st);
     if (m.world > 1) {

@@ -68,7 +68,23 @@ struct PhaseArgs {
     // this phase has stored it.  Replaces the stand-alone permutation pass between the phases on one GPU.
     const float* e_src;
     const uint32_t* e_map;
+    // Fused forward exchange (G GPUs, peer pushes; Model::xmap_fwd): the phase's FINAL residual of local slot s does not go to e[s]
+    // but to xdst[x >> 28][x & 0x0fffffff], x = xmap[s] -- the receive buffer of the rank that owns the rating's row on the other
+    // side, at the position its own first touch will read it from (e_src / e_map of its next phase).
+    const uint32_t* xmap;
+    float* xdst[MAX_PEERS];
 };
+
+// final store of a phase's residual (last block processed): local array, or straight into the owner rank's receive buffer
+__device__ __forceinline__ void store_e_final(const PhaseArgs& a, int64_t slot, float v)
+{
+    if (a.xmap) {
+        const uint32_t x = a.xmap[slot];
+        a.xdst[x >> 28][x & 0x0fffffffu] = v;
+    } else {
+        a.e[slot] = v;
+    }
+}
 
 __device__ __forceinline__ float load_e_first(const PhaseArgs& a, int64_t slot)
 {
@@ -378,7 +394,7 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const int p = r * TPR + t_in_row;
-            if (p < c) a.e[beg + p] = a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]);
+            if (p < c) store_e_final(a, beg + p, a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]));
         }
         return;
     }
@@ -386,7 +402,8 @@ row_resident_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nro
     for (int r = 0; r < RPL; ++r) {
         const int p = r * TPR + t_in_row;
         if (p < c) {
-            a.e[beg + p] = e[r];
+            if (b_end == a.KBtot) store_e_final(a, beg + p, e[r]);   // (not a REFRESH phase: its last launch returned above)
+            else a.e[beg + p] = e[r];
             if (REFRESH) a.pacc[beg + p] = pr[r];
         }
     }
@@ -568,7 +585,7 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const int p = r * G + lg;
-            if (p < c) a.e[beg + p] = a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]);
+            if (p < c) store_e_final(a, beg + p, a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]));
         }
         return;
     }
@@ -576,7 +593,8 @@ row_group_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows,
     for (int r = 0; r < RPL; ++r) {
         const int p = r * G + lg;
         if (p < c) {
-            a.e[beg + p] = e[r];
+            if (b_end == a.KBtot) store_e_final(a, beg + p, e[r]);   // (not a REFRESH phase: its last launch returned above)
+            else a.e[beg + p] = e[r];
             if (REFRESH) a.pacc[beg + p] = pr[r];
         }
     }
@@ -852,7 +870,10 @@ heavy_accumulate_kernel(PhaseArgs a, const Slice* __restrict__ slices, float* __
                     if (CUR == 0) e[u] = (i < sl.len) ? ld_stream(rp + i) - (row_const + a.bias_other[id[u]] + pr[u]) : 0.f;   // phase done: fresh residual
                     else if (i < sl.len) st_stream(pp + i, pr[u]);
                 }
-                if (i < sl.len) st_stream(ep + i, e[u]);
+                if (i < sl.len) {
+                    if (CUR == 0) store_e_final(a, (int64_t)sl.start + i, e[u]);   // last pass of the phase
+                    else st_stream(ep + i, e[u]);
+                }
                 if (CUR == 1 && i < sl.len) acc[0] += e[u];
                 if (CUR == 2) ga.add(fc[u], e[u]);
             }
@@ -1440,9 +1461,12 @@ static void launch_bin(Model& m, const PhaseArgs& a, const Side& self, int b0, i
 }
 
 // One half-sweep: bias then all factor blocks of every row of `self` ([T]:514-558 users / 563-606 items).
-void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh, const float* e_src, const uint32_t* e_map)
+void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh, const float* e_src, const uint32_t* e_map,
+                  bool push_final)
 {
     PhaseArgs a;
+    a.xmap = push_final ? m.xmap_fwd : nullptr;
+    for (int q = 0; q < MAX_PEERS; ++q) a.xdst[q] = (push_final && q < m.world) ? m.precv[q] : nullptr;
     a.e_src = e_src;   // first touch of e (block 0 launches, first streaming pass) reads through the map, see PhaseArgs
     a.e_map = e_map;
     a.r = m.csr_r;              // only the user phase refreshes (refresh == false on the item side)

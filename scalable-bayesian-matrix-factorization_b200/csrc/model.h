@@ -106,6 +106,11 @@ struct Options {
     int64_t graph = 1;            // replay the steady-state sweep from a CUDA graph when per-phase timing is off
     int64_t device_plan = 1;      // multi-GPU: exchange plan computed on the device (0 = host planner, plan.cpp)
     int64_t mgpu_pool = 1;        // multi-GPU: rating-sized arrays from the stream-ordered pool (0 = cudaMalloc)
+    int64_t fuse_exchange = 0;    // multi-GPU with peer pushes: the user phase stores its final residual directly into the owner rank's receive
+                                  // buffer (over NVLink, overlapped with the phase) and the item phase reads it through recv_pos: no push /
+                                  // unpack kernels between the phases, only the barrier.  Measured: the exchange drops from 0.64 to 0.04 ms
+                                  // at N = 2 and 0.24 to 0.05 at N = 8, but the peer stores slow the phase itself by more (N = 2: 12.34 vs
+                                  // 12.38 ms per sweep; N = 8: 4.47 vs 3.91) -- off
     int64_t peer = 1;             // multi-GPU: peer-mapped replicas / direct NVLink pushes (0 = NCCL exchanges)
     int64_t trace = 0;            // 1: wall-clock of the set_train stages on stderr; 2: without device synchronisation
 };
@@ -152,6 +157,9 @@ struct Model {
     float* psend[8] = {};             // peers' sendbuf (reverse exchange target)
     std::vector<void*> ipc_opened;
     std::vector<size_t> fwd_dst_off, rev_dst_off;   // start of MY segment in rank q's recvbuf / sendbuf
+    // fused forward exchange (option fuse_exchange): xmap_fwd[local CSR slot] = (destination rank << 28) | position in that rank's
+    // recvbuf -- the user phase's final residual store goes straight there (kernels.cu store_e_final); nullptr = push_kernel path
+    uint32_t* xmap_fwd = nullptr;
     double* bar = nullptr;            // 1 double: payload of the barrier all-reduce
     uint64_t t_begin = 0, t_end = 0;  // this rank's slice of the test set
     double* red2 = nullptr;           // [2] reduced (and all-reduced) pair of sums: (sum e, sum e^2) or the two squared-error sums
@@ -206,7 +214,7 @@ void launch_dim_hypers(Model& m, cudaStream_t st);       // [T]:415-467
 void launch_bias_hypers(Model& m, cudaStream_t st);      // [T]:469-511
 // [T]:514-558 / 563-606; e_map != nullptr: the residual is taken over from e_src[e_map[slot]] (the other side's slot order)
 void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, bool refresh, const float* e_src = nullptr,
-                  const uint32_t* e_map = nullptr);
+                  const uint32_t* e_map = nullptr, bool push_final = false);
 bool ensure_perm_inverse(Model& m, cudaStream_t st);    // perm_inv (CSR slot -> CSC slot), built on first use; false: no memory
 // one GPU: gather through perm.  G GPUs: all-to-all over NVLink, grouped with the all-gather of gather_side's updated rows (may be null)
 int launch_permute(Model& m, bool csr_to_csc, Side* gather_side, cudaStream_t st);

@@ -396,7 +396,7 @@ row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nr
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const int p = r * TPR + t_in_row;
-            if (p < c) a.e[beg + p] = a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]);
+            if (p < c) store_e_final(a, beg + p, a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]));
         }
         return;
     }
@@ -404,7 +404,8 @@ row_resident2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nr
     for (int r = 0; r < RPL; ++r) {
         const int p = r * TPR + t_in_row;
         if (p < c) {
-            a.e[beg + p] = e[r];
+            if (b_end == a.KBtot) store_e_final(a, beg + p, e[r]);   // (not a REFRESH phase: its last launch returned above)
+            else a.e[beg + p] = e[r];
             if (REFRESH) a.pacc[beg + p] = pr[r];
         }
     }
@@ -557,7 +558,7 @@ row_group2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const int p = r * G + lg;
-            if (p < c) a.e[beg + p] = a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]);
+            if (p < c) store_e_final(a, beg + p, a.r[beg + p] - (b0 + bias_new + a.bias_other[id[r]] + pr[r]));
         }
         return;
     }
@@ -565,7 +566,8 @@ row_group2_kernel(PhaseArgs a, const uint32_t* __restrict__ rows, uint32_t nrows
     for (int r = 0; r < RPL; ++r) {
         const int p = r * G + lg;
         if (p < c) {
-            a.e[beg + p] = e[r];
+            if (b_end == a.KBtot) store_e_final(a, beg + p, e[r]);   // (not a REFRESH phase: its last launch returned above)
+            else a.e[beg + p] = e[r];
             if (REFRESH) a.pacc[beg + p] = pr[r];
         }
     }

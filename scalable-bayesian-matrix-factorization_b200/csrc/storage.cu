@@ -159,6 +159,23 @@ __global__ void restore_coo_kernel(const uint32_t* __restrict__ csr_id, const ui
     }
 }
 
+// fused forward exchange: position i of my send order (segment q = destination rank) is local CSR slot send_idx[i]; its value
+// belongs at recvbuf(q)[dst_off[q] + i - seg_off[q]]
+struct XSeg {
+    uint64_t seg_off[MAX_PEERS + 1];
+    uint64_t dst_off[MAX_PEERS];
+    int world;
+};
+__global__ void __launch_bounds__(256) xmap_kernel(const uint32_t* __restrict__ send_idx, uint64_t n, XSeg sg, uint32_t* __restrict__ xmap)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        int q = 0;
+#pragma unroll
+        for (int k = 1; k < MAX_PEERS; ++k) q += (k < sg.world && i >= sg.seg_off[k]) ? 1 : 0;
+        xmap[send_idx[i]] = ((uint32_t)q << 28) | (uint32_t)(sg.dst_off[q] + (i - sg.seg_off[q]));
+    }
+}
+
 static int bits_for(uint32_t n)
 {
     int b = 1;
@@ -305,8 +322,8 @@ void free_storage(Model& m)
     cudaFree(m.red_part); m.red_part = nullptr;
     cudaFree(m.red2); m.red2 = nullptr;
     cudaFree(m.send_idx); cudaFree(m.recv_pos); cudaFree(m.sendbuf); cudaFree(m.recvbuf);
-    cudaFree(m.perm_inv); cudaFree(m.recv_pos_inv); cudaFree(m.send_idx_inv);
-    m.perm_inv = m.recv_pos_inv = m.send_idx_inv = nullptr;
+    cudaFree(m.perm_inv); cudaFree(m.recv_pos_inv); cudaFree(m.send_idx_inv); cudaFree(m.xmap_fwd);
+    m.perm_inv = m.recv_pos_inv = m.send_idx_inv = m.xmap_fwd = nullptr;
     m.send_idx = m.recv_pos = nullptr; m.sendbuf = m.recvbuf = nullptr;
     m.n_csr = m.n_csc = 0;
     m.have_train = false;
@@ -659,6 +676,22 @@ static int shard_storage(Model& m)
     else cudaFree(m.perm);
     m.perm = nullptr;
     cudaStream_t st = m.s_main;
+    {   // option fuse_exchange: per-slot destination of the user phase's final residual (28 bits of position, 3 of rank)
+        bool fits = G <= MAX_PEERS && m.opt.fuse_exchange && m.opt.peer;
+        for (int q = 0; q < G && fits; ++q) fits = (uint64_t)(tb[q + 1] - tb[q]) < (1ull << 28);
+        if (fits && m.n_csr) {
+            XSeg sg;
+            sg.world = G;
+            for (int q = 0; q < MAX_PEERS; ++q) {
+                sg.seg_off[q] = q < G ? m.send_off[q] : m.n_csr;
+                sg.dst_off[q] = q < G ? m.fwd_dst_off[q] : 0;
+            }
+            sg.seg_off[MAX_PEERS] = m.n_csr;
+            CK(palloc(m, &m.xmap_fwd, m.n_csr, st));
+            SBMF_LAUNCH((xmap_kernel), (uint32_t)std::min<uint64_t>((m.n_csr + 255) / 256, (uint64_t)m.sm_count * 16), 256, 0, st, m.send_idx, m.n_csr, sg,
+                        m.xmap_fwd);
+        }
+    }
     CK(slice_inplace(m, m.us.idx, c0, m.n_csr, st)); CK(slice_inplace(m, m.us.e, c0, m.n_csr, st)); CK(slice_inplace(m, m.csr_urow, c0, m.n_csr, st));
     CK(slice_inplace(m, m.csr_r, c0, m.n_csr, st)); CK(slice_inplace(m, m.csr_id, c0, m.n_csr, st));
     CK(slice_inplace(m, m.it.idx, t0, m.n_csc, st)); CK(slice_inplace(m, m.it.e, t0, m.n_csc, st)); CK(slice_inplace(m, m.csc_id, t0, m.n_csc, st));

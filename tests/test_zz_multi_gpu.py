@@ -14,7 +14,7 @@ NGPU = len(glob.glob("/dev/nvidia[0-9]*"))
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(NGPU < 2, reason=f"needs >= 2 GPUs on the box (found {NGPU})")]
 
-OPTION_SETS = ["", "device_plan=0,mgpu_pool=0", "peer=0", "device_plan=0,peer=0"]
+OPTION_SETS = ["", "device_plan=0,mgpu_pool=0", "peer=0", "device_plan=0,peer=0", "fuse_exchange=1", "relabel=0"]
 
 
 @pytest.mark.parametrize("world", [2] + ([4] if NGPU >= 4 else []) + ([8] if NGPU >= 8 else []))
