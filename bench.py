@@ -563,7 +563,6 @@ def main():
     ap.add_argument("--no-full-point", action="store_true", help="skip the ML-10M-shaped full-configuration point")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the G-GPU vs 1-GPU chain check")
     ap.add_argument("--no-cli", action="store_true", help="skip e2e_cli (the job from files through bin/sbmf)")
-    ap.add_argument("--dev-relabel", action="store_true", help="developer experiment: relabel users / items by decreasing degree on the host first")
     ap.add_argument("--options", default="", help="name=value,... passed to sbmf_cuda_set_option on every handle (A/B measurements)")
     a = ap.parse_args()
     rank, local_rank, world = dist_env()
@@ -626,17 +625,8 @@ def main():
     t0 = time.perf_counter()
     d = generate(sbmf, a.workload, dev, rank, world, barrier)
     gen_s = time.perf_counter() - t0
-    if a.dev_relabel:   # developer experiment: what popularity-ordered row ids would buy (line sharing between adjacent lanes of a gather)
-        du = np.bincount(d["train_user"], minlength=I)
-        dv = np.bincount(d["train_item"], minlength=J)
-        ru = np.empty(I, np.uint32); ru[np.argsort(-du, kind="stable")] = np.arange(I, dtype=np.uint32)
-        rv = np.empty(J, np.uint32); rv[np.argsort(-dv, kind="stable")] = np.arange(J, dtype=np.uint32)
-        tu, ti = ru[d["train_user"]], rv[d["train_item"]]
-        o = np.argsort(tu.astype(np.int64) * J + ti, kind="stable")
-        d = dict(d, train_user=np.ascontiguousarray(tu[o]), train_item=np.ascontiguousarray(ti[o]), train_rating=np.ascontiguousarray(d["train_rating"][o]),
-                 test_user=np.ascontiguousarray(ru[d["test_user"]]), test_item=np.ascontiguousarray(rv[d["test_item"]]))
     n_train, n_test = int(d["train_user"].size), int(d["test_user"].size)
-    run = {"n_train": n_train, "n_test": n_test, "synth_seconds": round(gen_s, 2), "options": opts, "dev_relabel": bool(a.dev_relabel)}
+    run = {"n_train": n_train, "n_test": n_test, "synth_seconds": round(gen_s, 2), "options": opts}
     fu_per_sweep = float(n_train) * K
 
     # ---- value: K sweeps, everything resident, CUDA events on the library's stream
