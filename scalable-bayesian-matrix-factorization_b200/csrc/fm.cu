@@ -97,6 +97,10 @@ struct Model {
     sbmf_fm_config cfg;
     std::string err;
     cudaStream_t st = nullptr;
+    // the three column tiers of a run (warp / CTA / sliced columns) touch disjoint columns AND disjoint cases -- a run's columns share
+    // no case by construction -- so they execute concurrently: fork from st, join before the next run
+    cudaStream_t st_tier[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int sm_count = 148;
     uint32_t p = 0, K = 0, G = 1;
     bool have_train = false, have_test = false, inited = false;
@@ -838,12 +842,28 @@ template <int COORD>
 static void launch_run(Model& m, const ColArgs& a, const Run& R)
 {
     cudaStream_t st = m.st;
+    // tiers on their own streams when the run has more than one: the sliced chain (three dependent launches) stays on st, the
+    // warp and CTA tiers fork.  slice_part / long_scratch belong to the sliced tier alone, e / q entries are disjoint across tiers.
+    const int tiers = (R.w_cnt ? 1 : 0) + (R.c_cnt ? 1 : 0) + (R.g_cnt ? 1 : 0);
+    const bool fork = tiers > 1 && m.st_tier[0] && m.st_tier[1];
+    cudaStream_t sw = st, sc = st;
+    if (fork) {
+        cudaEventRecord(m.ev_fork, st);
+        if (R.w_cnt && (R.c_cnt || R.g_cnt)) {
+            sw = m.st_tier[0];
+            cudaStreamWaitEvent(sw, m.ev_fork, 0);
+        }
+        if (R.c_cnt && R.g_cnt) {
+            sc = m.st_tier[1];
+            cudaStreamWaitEvent(sc, m.ev_fork, 0);
+        }
+    }
     if (R.w_cnt) {
-        FM_LAUNCH(col_warp_kernel<COORD>, (R.w_cnt + BLOCK_T / 32 - 1) / (BLOCK_T / 32), BLOCK_T, st, a, m.wl_cols + R.w_off, R.w_cnt);
+        FM_LAUNCH(col_warp_kernel<COORD>, (R.w_cnt + BLOCK_T / 32 - 1) / (BLOCK_T / 32), BLOCK_T, sw, a, m.wl_cols + R.w_off, R.w_cnt);
         m.launches++;
     }
     if (R.c_cnt) {
-        FM_LAUNCH(col_block_kernel<COORD>, R.c_cnt, BLOCK_T, st, a, m.wl_cols + R.c_off);
+        FM_LAUNCH(col_block_kernel<COORD>, R.c_cnt, BLOCK_T, sc, a, m.wl_cols + R.c_off);
         m.launches++;
     }
     if (R.g_cnt) {
@@ -851,6 +871,14 @@ static void launch_run(Model& m, const ColArgs& a, const Run& R)
         FM_LAUNCH(slice_draw_kernel<COORD>, (R.g_cnt + 127) / 128, 128, st, a, m.wl_long + R.g_off, R.g_cnt, R.s_off, m.slice_part, m.long_scratch);
         FM_LAUNCH(slice_apply_kernel<COORD>, R.s_cnt, BLOCK_T, st, a, m.wl_slices + R.s_off, m.long_scratch);
         m.launches += 3;
+    }
+    if (sw != st) {
+        cudaEventRecord(m.ev_join[0], sw);
+        cudaStreamWaitEvent(st, m.ev_join[0], 0);
+    }
+    if (sc != st) {
+        cudaEventRecord(m.ev_join[1], sc);
+        cudaStreamWaitEvent(st, m.ev_join[1], 0);
     }
 }
 
@@ -1027,6 +1055,11 @@ int sbmf_fm_create(const sbmf_fm_config* cfg, sbmf_fm_handle** out)
     const uint32_t F = std::max<uint32_t>(m.K, 1);
     bool ok = cudaSetDevice(cfg->device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&m.st, cudaStreamNonBlocking) == cudaSuccess;
+    for (int q = 0; q < 2 && ok; ++q) {
+        ok = cudaStreamCreateWithFlags(&m.st_tier[q], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&m.ev_join[q], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && dmalloc(&m.sc, 1) == cudaSuccess && cudaMemset(m.sc, 0, sizeof(Scal)) == cudaSuccess;
     ok = ok && dmalloc(&m.w, (size_t)m.p) == cudaSuccess && dmalloc(&m.V, (size_t)m.p * F) == cudaSuccess;
     ok = ok && dmalloc(&m.w_mu, (size_t)m.G) == cudaSuccess && dmalloc(&m.w_lambda, (size_t)m.G) == cudaSuccess;
@@ -1056,6 +1089,14 @@ int sbmf_fm_destroy(sbmf_fm_handle* h)
     free_test(m);
     dfree(m.group); dfree(m.gs_attr); dfree(m.chunk_begin); dfree(m.gchunk_ptr); dfree(m.n_per_group); dfree(m.hyper_part);
     dfree(m.w); dfree(m.V); dfree(m.w_mu); dfree(m.w_lambda); dfree(m.v_mu); dfree(m.v_lambda); dfree(m.sc); dfree(m.red_part); dfree(m.hist);
+    for (int q = 0; q < 2; ++q) {
+        if (m.st_tier[q]) {
+            cudaStreamSynchronize(m.st_tier[q]);
+            cudaStreamDestroy(m.st_tier[q]);
+        }
+        if (m.ev_join[q]) cudaEventDestroy(m.ev_join[q]);
+    }
+    if (m.ev_fork) cudaEventDestroy(m.ev_fork);
     if (m.st) cudaStreamDestroy(m.st);
     delete h;
     return SBMF_OK;
