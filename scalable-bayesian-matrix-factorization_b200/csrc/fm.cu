@@ -282,6 +282,62 @@ __device__ __forceinline__ float draw_theta(const ColArgs& a, uint32_t j, double
     return (float)settle(post, z, (double)theta_old);
 }
 
+// The two passes over a column's entries [k0, en) with stride STEP (lanes of a warp / threads of a CTA), UNR entries per thread in
+// flight: the entry's case id, then e / q of that case, are dependent loads (two DRAM round trips), and with one entry at a time a
+// column pass ran at a few percent of the memory system (ncu, col_block_kernel: 103 long-scoreboard stalls per issue, DRAM 10 %).
+// A thread still visits its entries in ascending order, so every sum is formed exactly as before.
+constexpr int COL_UNR = 4;
+template <int COORD, int STEP>
+__device__ __forceinline__ void col_accumulate(const ColArgs& a, int64_t k0, int64_t en, float theta_old, ColSums& s)
+{
+    for (int64_t k = k0; k < en; k += (int64_t)STEP * COL_UNR) {
+        uint32_t c[COL_UNR];
+        float x[COL_UNR], ev[COL_UNR], qv[COL_UNR];
+#pragma unroll
+        for (int u = 0; u < COL_UNR; ++u) {
+            const int64_t kk = k + (int64_t)u * STEP;
+            c[u] = kk < en ? a.case_id[kk] : 0u;
+            x[u] = kk < en ? a.xc[kk] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < COL_UNR; ++u) {
+            const bool ok = k + (int64_t)u * STEP < en;
+            ev[u] = ok ? a.e[c[u]] : 0.f;
+            qv[u] = (ok && COORD == COORD_V) ? a.q[c[u]] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < COL_UNR; ++u)
+            if (k + (int64_t)u * STEP < en) accumulate_entry<COORD>(s, x[u], ev[u], qv[u], theta_old);
+    }
+}
+template <int COORD, int STEP>
+__device__ __forceinline__ void col_apply(const ColArgs& a, int64_t k0, int64_t en, float theta_old, float delta)
+{
+    for (int64_t k = k0; k < en; k += (int64_t)STEP * COL_UNR) {
+        uint32_t c[COL_UNR];
+        float x[COL_UNR], ev[COL_UNR], qv[COL_UNR];
+#pragma unroll
+        for (int u = 0; u < COL_UNR; ++u) {
+            const int64_t kk = k + (int64_t)u * STEP;
+            c[u] = kk < en ? a.case_id[kk] : 0u;
+            x[u] = kk < en ? a.xc[kk] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < COL_UNR; ++u) {
+            const bool ok = k + (int64_t)u * STEP < en;
+            ev[u] = ok ? a.e[c[u]] : 0.f;
+            qv[u] = (ok && COORD == COORD_V) ? a.q[c[u]] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < COL_UNR; ++u) {
+            if (k + (int64_t)u * STEP >= en) continue;
+            apply_entry<COORD>(x[u], ev[u], qv[u], theta_old, delta);
+            a.e[c[u]] = ev[u];
+            if (COORD == COORD_V) a.q[c[u]] = qv[u];
+        }
+    }
+}
+
 // one warp per column of <= WARP_COL_MAX entries (also the empty ones: a draw from the prior, [G]:458-466)
 template <int COORD>
 __global__ void __launch_bounds__(BLOCK_T) col_warp_kernel(ColArgs a, const uint32_t* __restrict__ cols, uint32_t ncols)
@@ -293,22 +349,13 @@ __global__ void __launch_bounds__(BLOCK_T) col_warp_kernel(ColArgs a, const uint
     float* th = a.theta + (size_t)j * a.stride + a.f;
     const float theta_old = *th;
     ColSums s{0.0, 0.0};
-    for (int64_t k = b + lane; k < en; k += 32) {
-        const uint32_t c = a.case_id[k];
-        accumulate_entry<COORD>(s, a.xc[k], a.e[c], COORD == COORD_V ? a.q[c] : 0.f, theta_old);
-    }
+    col_accumulate<COORD, 32>(a, b + lane, en, theta_old, s);
     const double hh = warp_sum(s.hh), he = warp_sum(s.he);     // identical on every lane
     const float theta_new = draw_theta<COORD>(a, j, hh, he, theta_old);
     const float delta = theta_old - theta_new;
     if (lane == 0) *th = theta_new;
     if (delta == 0.f) return;
-    for (int64_t k = b + lane; k < en; k += 32) {
-        const uint32_t c = a.case_id[k];
-        float ev = a.e[c], qv = COORD == COORD_V ? a.q[c] : 0.f;
-        apply_entry<COORD>(a.xc[k], ev, qv, theta_old, delta);
-        a.e[c] = ev;
-        if (COORD == COORD_V) a.q[c] = qv;
-    }
+    col_apply<COORD, 32>(a, b + lane, en, theta_old, delta);
 }
 
 // one CTA per column of <= BLOCK_COL_MAX entries
@@ -321,23 +368,14 @@ __global__ void __launch_bounds__(BLOCK_T) col_block_kernel(ColArgs a, const uin
     float* th = a.theta + (size_t)j * a.stride + a.f;
     const float theta_old = *th;
     ColSums s{0.0, 0.0};
-    for (int64_t k = b + threadIdx.x; k < en; k += BLOCK_T) {
-        const uint32_t c = a.case_id[k];
-        accumulate_entry<COORD>(s, a.xc[k], a.e[c], COORD == COORD_V ? a.q[c] : 0.f, theta_old);
-    }
+    col_accumulate<COORD, BLOCK_T>(a, b + threadIdx.x, en, theta_old, s);
     const double hh = block_sum(s.hh, sm);
     const double he = block_sum(s.he, sm);                    // (block_sum's leading barrier also orders the theta_old reads)
     const float theta_new = draw_theta<COORD>(a, j, hh, he, theta_old);
     const float delta = theta_old - theta_new;
     if (threadIdx.x == 0) *th = theta_new;
     if (delta == 0.f) return;
-    for (int64_t k = b + threadIdx.x; k < en; k += BLOCK_T) {
-        const uint32_t c = a.case_id[k];
-        float ev = a.e[c], qv = COORD == COORD_V ? a.q[c] : 0.f;
-        apply_entry<COORD>(a.xc[k], ev, qv, theta_old, delta);
-        a.e[c] = ev;
-        if (COORD == COORD_V) a.q[c] = qv;
-    }
+    col_apply<COORD, BLOCK_T>(a, b + threadIdx.x, en, theta_old, delta);
 }
 
 // long columns: per-slice partial sums, one draw per column (slices combined in slice order), per-slice apply
@@ -350,11 +388,7 @@ __global__ void __launch_bounds__(BLOCK_T) slice_reduce_kernel(ColArgs a, const 
     const uint32_t j = lcols[sl.gi].col;
     const float theta_old = a.theta[(size_t)j * a.stride + a.f];
     ColSums s{0.0, 0.0};
-    for (uint32_t i = threadIdx.x; i < sl.len; i += BLOCK_T) {
-        const int64_t k = sl.begin + i;
-        const uint32_t c = a.case_id[k];
-        accumulate_entry<COORD>(s, a.xc[k], a.e[c], COORD == COORD_V ? a.q[c] : 0.f, theta_old);
-    }
+    col_accumulate<COORD, BLOCK_T>(a, (int64_t)sl.begin + threadIdx.x, (int64_t)sl.begin + sl.len, theta_old, s);
     const double hh = block_sum(s.hh, sm);
     const double he = block_sum(s.he, sm);
     if (threadIdx.x == 0) part[blockIdx.x] = make_double2(hh, he);
@@ -384,14 +418,7 @@ __global__ void __launch_bounds__(BLOCK_T) slice_apply_kernel(ColArgs a, const S
     const Slice sl = slices[blockIdx.x];
     const float2 od = scratch[sl.gi];
     if (od.y == 0.f) return;
-    for (uint32_t i = threadIdx.x; i < sl.len; i += BLOCK_T) {
-        const int64_t k = sl.begin + i;
-        const uint32_t c = a.case_id[k];
-        float ev = a.e[c], qv = COORD == COORD_V ? a.q[c] : 0.f;
-        apply_entry<COORD>(a.xc[k], ev, qv, od.x, od.y);
-        a.e[c] = ev;
-        if (COORD == COORD_V) a.q[c] = qv;
-    }
+    col_apply<COORD, BLOCK_T>(a, (int64_t)sl.begin + threadIdx.x, (int64_t)sl.begin + sl.len, od.x, od.y);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

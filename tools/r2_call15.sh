@@ -4,9 +4,7 @@
 set -u
 O=gpurun_out; mkdir -p $O
 B="python tools/fm_devbench.py --shape ml10m -K 8 --iters 1 --warmup 2"
-$B > $O/c15_plain.log 2>&1; echo "plain rc=$?"; cat $O/c15_plain.log | cut -c1-300
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/c15_fm_launches.csv $B > $O/c15_ncu_list.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k regex:'col_warp_kernel<1>|col_block_kernel<1>|slice_apply_kernel<1>|slice_reduce_kernel<1>|q_rebuild_kernel|predict_kernel' \
+    -k regex:'col_warp_kernel<\(int\)1>|col_block_kernel<\(int\)1>|slice_apply_kernel<\(int\)1>|slice_reduce_kernel<\(int\)1>|q_rebuild_kernel|predict_kernel' \
     --launch-skip 40 --launch-count 12 -o $O/c15_fm -f $B > $O/c15_ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -2 $O/c15_ncu_full.log
 ls -la $O/c15_fm.ncu-rep
