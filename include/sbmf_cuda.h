@@ -150,9 +150,9 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
                           factor gather share 128-byte lines.  0: the caller's ids and file order.  Same chain either way: every
                           draw is keyed by the caller's row id; only fp32 summation order differs          [before set_train]
      group_rows    (1)    short rows share a warp (0: one warp per row)
-     row_kernels   (1)    resident rows: 1 = csrc/kernels.cu (transposed shuffle reduction); 2 = csrc/rows2.cuh with the Gram sums reduced
-                          through shared memory (fewer instructions, more L1TEX wavefronts: measured slower); 3 = rows2.cuh with the
-                          shuffle reduction (one block barrier per factor block, 64-bit pair operands: measured equal to 1)
+     row_kernels   (3)    resident rows: 3 = csrc/rows2.cuh with the transposed shuffle reduction (one block barrier per factor block,
+                          64-bit pair operands); 1 = csrc/kernels.cu (the round-1 kernels: 1 % slower on the final build); 2 = rows2.cuh
+                          with the Gram sums reduced through shared memory (fewer instructions, more L1TEX wavefronts: slower)
      alt_bins      (1)    resident rows of 193..512 ratings are owned by 2 warps with 6 | 8 ratings per lane (one-barrier kernels of
                           csrc/rows2.cuh) instead of 4 warps with 3 | 4: half the per-block reduction / solve work per rating
      pair_gather   (0)    streamed rows gather (previous, current) factor block as one 64-byte row by lane pairs from a per-phase

@@ -96,7 +96,8 @@ struct Options {
     int64_t relabel = 1;          // rows stored in order of decreasing rating count (adjacent lanes of a gather then share 128-byte lines
                                   // on the popular rows); 0 = the caller's ids.  Draws are keyed by the caller's ids either way
     int64_t group_rows = 1;       // short rows: several rows per warp (row_group_kernel); 0 = one warp per row
-    int64_t row_kernels = 1;      // resident rows: 1 = shuffle reduction (kernels.cu), 2 = rows2.cuh (shared-memory reduction, one barrier per block; measured slower, A/B)
+    int64_t row_kernels = 3;      // resident rows: 3 = rows2.cuh with the shuffle reduction (one barrier per block, 64-bit pair operands: 22.12 -> 21.87 ms
+                                  // per sweep on the final build), 1 = kernels.cu (round 1), 2 = rows2.cuh with the shared-memory reduction (slower)
     int64_t alt_bins = 1;         // resident rows of 193..512 ratings: 2 warps x (6 | 8) per lane (rows2.cuh) instead of 4 warps x (3 | 4); measured 12.19 -> 11.77 ms user phase
     int64_t pair_gather = 0;      // streaming pipeline: gather (previous, current) block as one 64-byte row by lane pairs (0: two sector gathers)
     int64_t fuse_solve = 0;       // streaming pipeline: row updates in the tail of each pass by the row's last slice CTA (0: a launch of

@@ -571,7 +571,7 @@ OPTION_SETS = [
     {"resident_max_user": 64, "resident_max_item": 1024},
     {"relabel": 0},                                     # rows under the caller's ids instead of positions by decreasing rating count
     {"relabel": 0, "alt_bins": 0, "row_kernels": 1},    # the round-1 resident-row kernels throughout
-    {"row_kernels": 2}, {"row_kernels": 3},             # rows2.cuh: shared-memory reduction / one-barrier structure with the shuffle tree
+    {"row_kernels": 2}, {"row_kernels": 1},             # rows2.cuh with the shared-memory reduction / the round-1 kernels (default: 3)
     {"row_kernels": 2, "alt_bins": 0, "max_blocks_per_launch": 3, "relabel": 0},
 ]
 
