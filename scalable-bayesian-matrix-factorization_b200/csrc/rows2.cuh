@@ -1,17 +1,18 @@
-// rows2.cuh -- second generation of the resident-row kernels (option row_kernels = 2); included by
-// kernels.cu after PhaseArgs / solve_lanes.  Same half-step as row_resident_kernel / row_group_kernel ([T]:514-558, 563-606), same
-// Gram-blocked arithmetic per rating; what changed is everything AROUND the per-rating work, which ncu and the SASS of round 1
-// showed to be most of the issue slots of a row block (profiles/r2/rows_sass_r2.txt):
+// rows2.cuh -- second generation of the resident-row kernels; included by kernels.cu after PhaseArgs / solve_lanes.
+// Same half-step as row_resident_kernel / row_group_kernel ([T]:514-558, 563-606), same Gram-blocked arithmetic per rating; what
+// changed is everything AROUND the per-rating work (profiles/sass/SUMMARY_r2.txt, profiles/r2/ncu_rows_rk*.txt):
 //
-//   * reduction through shared memory instead of the transposed shuffle tree.  A lane stores its 48 accumulators as 12 float4
-//     (conflict-free: row stride 52 floats), 24 lanes each sum one quad over 16 lanes' rows (16 LDS.128 + 60 FADD), one shuffle
-//     stage joins the halves: ~100 instructions per row block instead of 212 (48 SHFL + 90 FSEL + 57 FADD + moves), and the sums
-//     arrive as quads that go straight to the solve layout.
 //   * rows owned by several warps: ONE block barrier per factor block instead of four.  Every warp publishes its 48 sums
 //     (double-buffered by block parity), after the barrier every warp adds the W partials itself and runs the lane-parallel solve
 //     redundantly, so there is no "warp 0 solves, the others wait twice" and no second hop for the deltas.
 //   * (d, u_new) pairs of the residual update / prediction refresh prepared once per block as 64-bit operands (gram.cuh pair64):
 //     8 FFMA2 + 2 FADD per rating instead of 8 FFMA2 + ~14 moves + 3 FADD.
+//   * SMEM_RED = true (option row_kernels = 2): the 48 sums reduced through shared memory instead of the transposed shuffle tree.
+//     A lane stores its accumulators as 12 float4 (conflict-free: row stride 52 floats), 24 lanes each sum one quad over 16 lanes'
+//     rows (16 LDS.128 + 60 FADD), one shuffle stage joins the halves: ~100 instructions per row block instead of 212, ptxas
+//     fuses accumulation and store (4 live accumulators instead of 48).  Measured SLOWER: the kernels are bound by the L1TEX data
+//     pipe, where this reduction costs 96 wavefronts against 65 for the shuffles, and its buffers take L1 from the gathers.
+//     SMEM_RED = false (option row_kernels = 3, the default): the shuffle tree of common.cuh inside the new structure.
 #pragma once
 
 namespace sbmf {
@@ -21,8 +22,8 @@ namespace sbmf {
 __constant__ uint8_t c_nat_a[NACC];
 __constant__ uint8_t c_nat_b[NACC];
 
-constexpr int XB_STRIDE1 = 52;   // one round: 48 values + 4 floats of padding (13 quads: odd, so 8 consecutive rows cover all banks)
-constexpr int XB_STRIDE2 = 28;   // two rounds of 24 values (7 quads)
+// exchange buffer of the shared-memory reduction, NR rounds: rows of 48 / NR values + 4 floats of padding (13 or 7 quads per row:
+// odd, so the 8 lanes of an LDS.128 / STS.128 phase cover all banks)
 template <int NR> struct XbGeom {
     static constexpr int QR = 12 / NR;              // quads per round
     static constexpr int STRIDE = 4 * QR + 4;       // floats per lane row
