@@ -159,6 +159,8 @@ int sbmf_cuda_nccl_unique_id(uint8_t out[128]);
                           pair array instead of two sector gathers (measured slower on sorted rating rows)   [before set_train]
      fuse_solve    (0)    streamed rows: the row updates run in the tail of each pass, by the last slice CTA of the row, instead of
                           a launch of their own (halves the launch count of a phase; measured slower on one GPU)
+     heavy_chains  (2)    streamed rows as two independent pass -> update -> pass chains on two streams (the one-CTA-per-row updates of
+                          one half run under the passes of the other); 1: a single chain
      fold_user / fold_item (1 / 1)  one GPU: residual hand-over between the slot orders folded into the phase's first touch
      graph         (1)    steady-state sweep replayed from a CUDA graph when per-phase timing is off
      device_plan   (1)    multi-GPU: exchange plan computed on the device (0: host planner)  [before set_train]

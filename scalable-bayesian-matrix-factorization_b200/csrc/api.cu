@@ -60,6 +60,7 @@ static const OptionDesc kOptions[] = {
     {"alt_bins", &Options::alt_bins, 0, 1, false},
     {"pair_gather", &Options::pair_gather, 0, 1, true},
     {"fuse_solve", &Options::fuse_solve, 0, 1, false},
+    {"heavy_chains", &Options::heavy_chains, 1, 2, false},
     {"fold_user", &Options::fold_user, 0, 1, false},
     {"fold_item", &Options::fold_item, 0, 1, false},
     {"graph", &Options::graph, 0, 1, false},
@@ -284,6 +285,8 @@ int sbmf_cuda_create(const sbmf_config* cfg, sbmf_handle** out)
     }
     ok = ok && cudaStreamCreateWithFlags(&m.s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&m.s_aux, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&m.s_aux2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&m.ev_join2, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
         ok = cudaStreamCreateWithFlags(&m.s_res[i], cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&m.ev_join_res[i], cudaEventDisableTiming) == cudaSuccess;
@@ -352,6 +355,7 @@ int sbmf_cuda_destroy(sbmf_handle* h)
     cudaSetDevice(m.device);
     if (m.s_main) cudaStreamSynchronize(m.s_main);
     if (m.s_aux) cudaStreamSynchronize(m.s_aux);
+    if (m.s_aux2) cudaStreamSynchronize(m.s_aux2);
     free_storage(m);
     free_test(m);
     comm_destroy(m.comm);
@@ -367,8 +371,10 @@ int sbmf_cuda_destroy(sbmf_handle* h)
     if (m.graph_exec) cudaGraphExecDestroy(m.graph_exec);
     if (m.ev_fork) cudaEventDestroy(m.ev_fork);
     if (m.ev_join) cudaEventDestroy(m.ev_join);
+    if (m.ev_join2) cudaEventDestroy(m.ev_join2);
     if (m.s_main) cudaStreamDestroy(m.s_main);
     if (m.s_aux) cudaStreamDestroy(m.s_aux);
+    if (m.s_aux2) cudaStreamDestroy(m.s_aux2);
     for (int i = 0; i < 2; ++i) {
         if (m.ev_join_res[i]) cudaEventDestroy(m.ev_join_res[i]);
         if (m.s_res[i]) cudaStreamDestroy(m.s_res[i]);
@@ -816,6 +822,7 @@ int sbmf_cuda_synchronize(sbmf_handle* h)
     API_CK(cudaSetDevice(m.device));
     API_CK(cudaStreamSynchronize(m.s_main));
     API_CK(cudaStreamSynchronize(m.s_aux));
+    API_CK(cudaStreamSynchronize(m.s_aux2));
     return SBMF_OK;
 }
 

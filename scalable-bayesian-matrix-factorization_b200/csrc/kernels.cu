@@ -706,11 +706,12 @@ __device__ __forceinline__ uint32_t ticket_release(uint32_t* counter)
 template <int CUR, int NW>
 __global__ void __launch_bounds__(NW * 32)
 heavy_solve_kernel(PhaseArgs a, const uint32_t* __restrict__ slice_ptr, const float* __restrict__ hpart, float* __restrict__ hdelta,
-                   float* __restrict__ hbias_delta, int b)
+                   float* __restrict__ hbias_delta, int b, uint32_t hrow0)
 {
     __shared__ __align__(16) float s_part[NW][NACC];
     __shared__ __align__(16) float s_tot[NACC];
-    heavy_row_solve<CUR, NW>(a, blockIdx.x, slice_ptr[blockIdx.x], slice_ptr[blockIdx.x + 1], hpart, hdelta, hbias_delta, b, s_part, s_tot);
+    const uint32_t hrow = blockIdx.x + hrow0;   // hrow0: first streamed row of this chain
+    heavy_row_solve<CUR, NW>(a, hrow, slice_ptr[hrow], slice_ptr[hrow + 1], hpart, hdelta, hbias_delta, b, s_part, s_tot);
 }
 
 // PAIR (PREV == 2 and CUR == 2 only): the factor rows come from the pair array F2other.  Lanes (2k, 2k+1) fetch the 64-byte row
@@ -1558,36 +1559,60 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         const uint32_t ns = self.n_slices, nh = self.n_heavy;
         float* hbias = self.hdelta + (size_t)nh * 8;
     // 2 ratings per thread x 64 threads per slice CTA measured best on B200 (profiles/): small CTAs, ~20 warps per SM.
-    // The row updates (heavy_row_solve) run in the tail of each pass, by the last slice CTA of the row: one launch per step.
+    // The row updates run as a launch of their own between two passes (heavy_solve_kernel: one CTA per streamed row, latency-bound),
+    // or, option fuse_solve, in the tail of each pass by the last slice CTA of the row.
+    // Option heavy_chains = 2: the streamed rows are cut into two halves (by slices, at a row boundary) that run as two independent
+    // pass -> update -> pass chains on two streams, so the updates of one half execute under the passes of the other instead of
+    // leaving the GPU to ~9,000 tiny CTAs 2 KB + 2 times per phase.  Per-pass timing (timing_detail) keeps the single chain: it
+    // measures the kernel, not the overlap.
         const bool fuse = m.opt.fuse_solve != 0;
         uint32_t* hc = fuse ? self.hcount : nullptr;
-        const bool wide_solve = ns >= 8u * nh;   // >= 8 slices per streamed row on average
-#define HEAVY_ACC_T(PREV, CUR, RF, PR, FU, PB, B) \
-    SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, RF, PR, FU>), ns, 64, 0, sh, a, self.slices, self.hdelta, hbias, self.hpart, self.heavy_slice_ptr, hc, PB, B)
+        struct Chain {
+            cudaStream_t st;
+            uint32_t h0, nh, s0, ns;
+        };
+        Chain chains[2] = {{sh, 0, nh, 0, ns}, {m.s_aux2, 0, 0, 0, 0}};
+        int nch = 1;
+        const bool detail = m.timing_detail && !apply_shift;   // item phase only
+        if (m.opt.heavy_chains == 2 && !fuse && !m.timing_detail && m.s_aux2 && self.h_split > 0 && self.s_split > 0 && self.s_split < ns) {
+            chains[0] = Chain{sh, 0, self.h_split, 0, self.s_split};
+            chains[1] = Chain{m.s_aux2, self.h_split, nh - self.h_split, self.s_split, ns - self.s_split};
+            nch = 2;
+            cudaStreamWaitEvent(m.s_aux2, m.ev_fork, 0);
+        }
+#define HEAVY_ACC_T(PREV, CUR, RF, PR, FU, PB, B)                                                                                            \
+    SBMF_LAUNCH((heavy_accumulate_kernel<PREV, CUR, 2, 64, RF, PR, FU>), C.ns, 64, 0, C.st, a, self.slices + C.s0, self.hdelta, hbias,           \
+                self.hpart + (size_t)C.s0 * NACC, self.heavy_slice_ptr, hc, PB, B)
 #define HEAVY_ACC_P(PREV, CUR, PR, PB, B)                                     \
     do {                                                                      \
         if (refresh && fuse) HEAVY_ACC_T(PREV, CUR, true, PR, true, PB, B);   \
         else if (refresh) HEAVY_ACC_T(PREV, CUR, true, PR, false, PB, B);     \
         else if (fuse) HEAVY_ACC_T(PREV, CUR, false, PR, true, PB, B);        \
         else HEAVY_ACC_T(PREV, CUR, false, PR, false, PB, B);                 \
+        m.launches++;                                                         \
     } while (0)
 #define HEAVY_ACC(PREV, CUR, PB, B) HEAVY_ACC_P(PREV, CUR, false, PB, B)
-#define HEAVY_SOLVE(CUR, B)                                                                                                                      \
-    do {                                                                                                                                         \
-        if (fuse) break;                                                                                                                         \
-        if (wide_solve) SBMF_LAUNCH((heavy_solve_kernel<CUR, 8>), nh, 256, 0, sh, a, self.heavy_slice_ptr, self.hpart, self.hdelta, hbias, B);   \
-        else SBMF_LAUNCH((heavy_solve_kernel<CUR, 2>), nh, 64, 0, sh, a, self.heavy_slice_ptr, self.hpart, self.hdelta, hbias, B);               \
-        m.launches++;                                                                                                                            \
+#define HEAVY_SOLVE(CUR, B)                                                                                                                  \
+    do {                                                                                                                                     \
+        if (fuse) break;                                                                                                                     \
+        if (C.ns >= 8u * C.nh)   /* >= 8 slices per streamed row on average */                                                               \
+            SBMF_LAUNCH((heavy_solve_kernel<CUR, 8>), C.nh, 256, 0, C.st, a, self.heavy_slice_ptr, self.hpart, self.hdelta, hbias, B, C.h0);    \
+        else SBMF_LAUNCH((heavy_solve_kernel<CUR, 2>), C.nh, 64, 0, C.st, a, self.heavy_slice_ptr, self.hpart, self.hdelta, hbias, B, C.h0);    \
+        m.launches++;                                                                                                                        \
     } while (0)
+#define EACH_CHAIN(STEP)                    \
+    for (int c_ = 0; c_ < nch; ++c_) {      \
+        const Chain& C = chains[c_];        \
+        STEP;                               \
+    }
         if (with_bias) {
-            HEAVY_ACC(0, 1, 0, 0);
-            HEAVY_SOLVE(1, 0);
-            HEAVY_ACC(1, 2, 0, 0);
+            EACH_CHAIN(HEAVY_ACC(0, 1, 0, 0));
+            EACH_CHAIN(HEAVY_SOLVE(1, 0));
+            EACH_CHAIN(HEAVY_ACC(1, 2, 0, 0));
         } else {
-            HEAVY_ACC(0, 2, 0, 0);
+            EACH_CHAIN(HEAVY_ACC(0, 2, 0, 0));
         }
-        HEAVY_SOLVE(2, 0);
-        const bool detail = m.timing_detail && !apply_shift;   // item phase only
+        EACH_CHAIN(HEAVY_SOLVE(2, 0));
         if (detail && m.ev_top.size() < (size_t)2 * KB) {
             while (m.ev_top.size() < (size_t)2 * KB) {
                 cudaEvent_t ev;
@@ -1598,20 +1623,24 @@ void launch_phase(Model& m, Side& self, const Side& other, bool apply_shift, boo
         if (detail) m.ev_top_used = 0;
         const bool pair = other.F2 != nullptr && m.opt.pair_gather;
         for (int b = 1; b < KB; ++b) {
+            if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);   // (detail: one chain on sh)
+            if (!pair) { EACH_CHAIN(HEAVY_ACC(2, 2, b - 1, b)); }
+            else { EACH_CHAIN(HEAVY_ACC_P(2, 2, true, b - 1, b)); }
             if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
-            if (!pair) HEAVY_ACC(2, 2, b - 1, b);
-            else HEAVY_ACC_P(2, 2, true, b - 1, b);
-            if (detail) cudaEventRecord(m.ev_top[m.ev_top_used++], sh);
-            HEAVY_SOLVE(2, b);
+            EACH_CHAIN(HEAVY_SOLVE(2, b));
         }
-        HEAVY_ACC(2, 0, KB - 1, 0);
+        EACH_CHAIN(HEAVY_ACC(2, 0, KB - 1, 0));
+#undef EACH_CHAIN
 #undef HEAVY_ACC
 #undef HEAVY_ACC_P
 #undef HEAVY_ACC_T
 #undef HEAVY_SOLVE
-        m.launches += KB + 1 + (with_bias ? 1 : 0);
         cudaEventRecord(m.ev_join, sh);
         cudaStreamWaitEvent(sr, m.ev_join, 0);
+        if (nch == 2) {
+            cudaEventRecord(m.ev_join2, m.s_aux2);
+            cudaStreamWaitEvent(sr, m.ev_join2, 0);
+        }
     }
 }
 

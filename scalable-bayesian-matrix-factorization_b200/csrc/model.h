@@ -72,6 +72,7 @@ struct Side {
     uint32_t* bin_rows[NBINS] = {};
     uint32_t bin_count[NBINS] = {};
     uint32_t n_heavy = 0, n_slices = 0;
+    uint32_t h_split = 0, s_split = 0;    // streamed rows [0, h_split) own slices [0, s_split): about half of them (two-chain pipeline)
     uint32_t* heavy_rows = nullptr;       // [n_heavy] row id
     uint32_t* heavy_slice_ptr = nullptr;  // [n_heavy+1] slice range of each heavy row
     Slice* slices = nullptr;              // [n_slices]
@@ -102,6 +103,8 @@ struct Options {
     int64_t pair_gather = 0;      // streaming pipeline: gather (previous, current) block as one 64-byte row by lane pairs (0: two sector gathers)
     int64_t fuse_solve = 0;       // streaming pipeline: row updates in the tail of each pass by the row's last slice CTA (0: a launch of
                                   // their own; measured on B200: the release fence + ticket per slice CTA costs 160 us per pass, a launch 55)
+    int64_t heavy_chains = 2;     // streaming pipeline: the streamed rows as two independent pass -> update -> pass chains on two streams, so
+                                  // that the (latency-bound, one-CTA-per-row) updates of one half run under the passes of the other
     int64_t fold_user = 1;        // one GPU: CSC->CSR residual hand-over folded into the user phase's first touch
     int64_t fold_item = 1;        // one GPU: CSR->CSC hand-over folded into the item phase's first touch (22.46 -> 22.27 ms per sweep)
     int64_t graph = 1;            // replay the steady-state sweep from a CUDA graph when per-phase timing is off
@@ -175,6 +178,8 @@ struct Model {
     uint32_t hist_cap = 0;
 
     cudaStream_t s_main = nullptr, s_aux = nullptr;
+    cudaStream_t s_aux2 = nullptr;     // second chain of the streaming pipeline (option heavy_chains)
+    cudaEvent_t ev_join2 = nullptr;
     cudaStream_t s_res[2] = {};        // extra streams for the resident bins
     cudaEvent_t ev_join_res[2] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

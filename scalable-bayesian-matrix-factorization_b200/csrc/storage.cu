@@ -305,6 +305,7 @@ void free_storage(Model& m)
         // peers may still be writing into / reading from our buffers: meet them before anything is unmapped or freed
         cudaStreamSynchronize(m.s_main);
         cudaStreamSynchronize(m.s_aux);
+        if (m.s_aux2) cudaStreamSynchronize(m.s_aux2);
         if (m.bar) {
             std::string err;
             comm_allreduce_sum_f64(m.comm, m.bar, 1, m.s_main, err);
@@ -393,6 +394,14 @@ static int build_worklists(Model& m, Side& s, uint32_t row0, uint32_t row1)
     }
     s.n_heavy = (uint32_t)heavy.size();
     s.n_slices = (uint32_t)slices.size();
+    // the row boundary closest to half of the slices: the two chains of the streaming pipeline (option heavy_chains)
+    s.h_split = s.s_split = 0;
+    for (uint32_t h = 1; h < s.n_heavy; ++h)
+        if (hsp[h] * 2 >= s.n_slices) {
+            s.h_split = h;
+            s.s_split = hsp[h];
+            break;
+        }
     CK(dmalloc(&s.heavy_rows, heavy.size()));
     CK(dmalloc(&s.heavy_slice_ptr, hsp.size()));
     CK(dmalloc(&s.slices, slices.size()));

@@ -569,6 +569,7 @@ OPTION_SETS = [
     {"pair_gather": 1, "resident_max": 128},            # streamed rows gather (previous, current) block as one 64-byte row by lane pairs
     {"fuse_solve": 1, "resident_max": 128},             # streamed rows: updates in the tail of the pass (last slice CTA of the row) instead of a launch of their own
     {"resident_max_user": 64, "resident_max_item": 1024},
+    {"heavy_chains": 1, "resident_max": 128},           # streamed rows as one chain instead of two
     {"relabel": 0},                                     # rows under the caller's ids instead of positions by decreasing rating count
     {"relabel": 0, "alt_bins": 0, "row_kernels": 1},    # the round-1 resident-row kernels throughout
     {"row_kernels": 2}, {"row_kernels": 1},             # rows2.cuh with the shared-memory reduction / the round-1 kernels (default: 3)
